@@ -1,0 +1,195 @@
+/*
+ * gsb200.h -- C ABI of libgsb200.so: the B200-native (sm_100a) replacement for the rasteriser
+ * hot path of wanmeihuali/taichi_3d_gaussian_splatting.
+ *
+ * This header is the drop-in boundary.  Every entry point names the reference interface it
+ * replaces (file:line relative to the reference repo; GPCR =
+ * taichi_3d_gaussian_splatting/GaussianPointCloudRasterisation.py).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes only; no C++/torch types cross the boundary.
+ *  - All pointers in the *Args structs are DEVICE pointers unless the field name says "host".
+ *  - The caller owns every buffer, including the workspace; the library allocates nothing
+ *    persistent and keeps no global mutable state except a thread-local error string.
+ *  - Every call enqueues work on the given cudaStream_t (passed as void*) and returns without
+ *    synchronising, except the *_host entry points which return after the result is in host memory.
+ *  - Return value: 0 on success, negative GSB_E* code on failure; gsb200_last_error() gives text.
+ *  - dtypes are the reference's: f32 data, i32 indices, i8 masks (GPCR:31-45, 239-259, 318-343).
+ */
+#ifndef GSB200_H_
+#define GSB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSB200_VERSION 100 /* major*100 + minor */
+
+#define GSB_TILE_WIDTH 16     /* GPCR:27 */
+#define GSB_TILE_HEIGHT 16    /* GPCR:28 */
+#define GSB_BOUNDARY_TILES 3  /* GPCR:26 */
+#define GSB_FEATURE_DIM 56    /* GPCR:208-236: q(4) s(3) alpha(1) R/G/B SH(16 each) */
+#define GSB_RECORD_FLOATS 12  /* packed per-splat record written by the preprocess kernel */
+#define GSB_ACCUM_FLOATS 12   /* per-splat backward accumulator row */
+
+enum {
+    GSB_OK = 0,
+    GSB_EINVAL = -1,     /* bad argument (null pointer, H/W not multiple of 16, ...) */
+    GSB_ECUDA = -2,      /* a CUDA runtime call failed */
+    GSB_EWORKSPACE = -3, /* workspace too small for (N, key_capacity, H, W) */
+    GSB_EUNSUPPORTED = -4
+};
+
+/* flags */
+#define GSB_FLAG_EXACT_EXP 1u    /* blend kernels use expf instead of ex2.approx */
+#define GSB_FLAG_FORCE_KEY64 2u  /* always sort (tile<<32 | depth) 64-bit keys like GPCR:158-170 */
+
+/* Byte offsets of the sub-buffers inside the caller-owned workspace blob.  Filled by
+ * gsb200_workspace_layout(); the Python shim uses it to expose saved-for-backward tensors as views. */
+typedef struct GsbWorkspaceLayout {
+    int64_t total_bytes;
+    int64_t zero_bytes;        /* [0, zero_bytes) is memset to 0 at the start of every forward */
+    int64_t counters;          /* int64[8]: [0]=M in-frustum points, [1]=K (tile,splat) pairs needed,
+                                  [2]=overflow (K > key_capacity), [3]=sorted-buffer selector (0=a,1=b) */
+    int64_t tickets;           /* uint32[16] dynamic block tickets */
+    int64_t scan_state;        /* uint64[ceil(N/256)+1] decoupled look-back state of the compaction scan */
+    int64_t sort_hist;         /* uint32[8][256] global digit histograms */
+    int64_t sort_state;        /* uint32[passes][sort_blocks][256] onesweep look-back state */
+    int64_t tile_start;        /* int32[T]  GPCR:952-957 tile_points_start */
+    int64_t tile_end;          /* int32[T]  tile_points_end */
+    int64_t poses;             /* float[num_objects][20]: T_camera_pointcloud 3x4, camera centre, pad */
+    int64_t point_id;          /* int32[N]  point_id_in_camera_list (first M valid), GPCR:864 */
+    int64_t num_tiles;         /* int32[N]  num_overlap_tiles, GPCR:904-911 */
+    int64_t records;           /* float[N][12]: u v a b | c rescale opacity depth | r g b radius */
+    int64_t point_in_camera;   /* float[N][3] GPCR:877 */
+    int64_t keys_a, keys_b;    /* sort keys ping-pong, key_bytes each, key_capacity_padded entries */
+    int64_t vals_a, vals_b;    /* int32 payload = in-camera offset, GPCR:930 */
+    int32_t key_bytes;         /* 4 or 8 */
+    int32_t tile_bits, depth_bits, sort_passes;
+    int64_t key_capacity_padded;
+    int32_t sort_blocks, scan_blocks;
+} GsbWorkspaceLayout;
+
+/* Inputs of GaussianPointCloudRasterisationInput (GPCR:788-804) + config (GPCR:776-786). */
+typedef struct GsbForwardArgs {
+    int64_t num_points;                 /* N */
+    const float *pointcloud;            /* (N,3) */
+    float *pointcloud_features;         /* (N,56); q of in-frustum rows normalised IN PLACE (GPCR:264-266) */
+    const int8_t *point_invalid_mask;   /* (N) 1 = slot unused */
+    const int32_t *point_object_id;     /* (N) */
+    int32_t num_objects;
+    const float *q_pointcloud_camera;   /* (num_objects,4) xyzw, camera->pointcloud */
+    const float *t_pointcloud_camera;   /* (num_objects,3) */
+    const float *camera_intrinsics;     /* (3,3) row-major, device */
+    int32_t camera_height, camera_width;
+    float near_plane, far_plane, depth_to_sort_key_scale;
+    int32_t rgb_only;                   /* GPCR:781; aux outputs are left untouched when set */
+    uint32_t flags;
+    void *workspace;
+    int64_t workspace_bytes;
+    int64_t key_capacity;               /* capacity (entries) of the key/value buffers */
+    float *rasterized_image;            /* (H,W,3) */
+    float *rasterized_depth;            /* (H,W) */
+    float *pixel_accumulated_alpha;     /* (H,W) */
+    int32_t *pixel_offset_of_last_effective_point; /* (H,W) */
+    int32_t *pixel_valid_point_count;   /* (H,W) */
+    void *stream;
+} GsbForwardArgs;
+
+typedef struct GsbBackwardArgs {
+    int64_t num_points;
+    const float *pointcloud;
+    const float *pointcloud_features;   /* as left by forward (q normalised) */
+    const int32_t *point_object_id;
+    int32_t num_objects;
+    const float *t_pointcloud_camera;   /* camera centre for the SH direction, GPCR:731-732 */
+    const float *camera_intrinsics;
+    int32_t camera_height, camera_width;
+    float far_plane, depth_to_sort_key_scale; /* same values as the forward (fix the workspace layout) */
+    int32_t color_max_sh_band;          /* GPCR:1167-1182; any value outside {0,1,2} clears nothing */
+    float grad_q_factor, grad_s_factor, grad_alpha_factor, grad_color_factor,
+        grad_high_order_color_factor;   /* GPCR:782-786, 1105-1125 */
+    uint32_t flags;
+    void *workspace;                    /* the SAME workspace the forward of this frame used */
+    int64_t workspace_bytes;
+    int64_t key_capacity;
+    const float *grad_rasterized_image; /* (H,W,3) */
+    const float *pixel_accumulated_alpha;
+    const int32_t *pixel_offset_of_last_effective_point;
+    float *accum;                       /* (>=M,12) zero-initialised by this call:
+                                           guv.x guv.y gcov00 gcov01 gcov11 gr gg gb glogit magnitude n_pixels(i32) pad */
+    int64_t accum_rows;
+    float *grad_pointcloud;             /* (N,3) fully written (zeros for points outside the frustum) */
+    float *grad_pointcloud_features;    /* (N,56) fully written, band-masked and factor-scaled */
+    float *magnitude_grad_viewspace_on_image; /* (H,W,2) */
+    void *stream;
+} GsbBackwardArgs;
+
+/* version / errors */
+int gsb200_version(void);
+const char *gsb200_last_error(void);
+/* sizeof(GsbWorkspaceLayout), sizeof(GsbForwardArgs), sizeof(GsbBackwardArgs) as compiled: lets a
+ * foreign-language binding verify its struct mirrors. */
+void gsb200_abi_sizes(int64_t *out3);
+
+/* Workspace sizing.  far_plane*depth_to_sort_key_scale fixes the depth-key width; (H/16)*(W/16)
+ * the tile-id width; both <= 32 bits total selects 32-bit sort keys. */
+int gsb200_workspace_layout(int64_t num_points, int32_t num_objects, int64_t key_capacity,
+                            int32_t camera_height, int32_t camera_width, float far_plane,
+                            float depth_to_sort_key_scale, uint32_t flags,
+                            GsbWorkspaceLayout *out);
+
+/* Forward: replaces _module_function.forward, GPCR:830-1023 (K1 filter_point_in_camera GPCR:31-78,
+ * mask compaction GPCR:861-864, K2 generate_point_attributes_in_camera_plane GPCR:239-315,
+ * K3 generate_num_overlap_tiles GPCR:106-128, cumsum GPCR:913-922,
+ * K4 generate_point_sort_key_by_num_overlap_tiles GPCR:131-172, sort GPCR:947-950,
+ * K5 find_tile_start_and_end GPCR:175-193, K6 gaussian_point_rasterisation GPCR:318-485). */
+int gsb200_forward(const GsbForwardArgs *args);
+
+/* Backward: replaces _module_function.backward, GPCR:1025-1125 (K7
+ * gaussian_point_rasterisation_backward GPCR:488-772, _clear_grad_by_color_max_sh_band
+ * GPCR:1167-1182, factor scaling GPCR:1105-1125). */
+int gsb200_backward(const GsbBackwardArgs *args);
+
+/* Individual stages (same workspace), for tests and profiling. */
+int gsb200_stage_preprocess(const GsbForwardArgs *args);   /* K1+P1+K2+K3+P2+K4 fused */
+int gsb200_stage_sort(const GsbForwardArgs *args);         /* P3 */
+int gsb200_stage_tile_ranges(const GsbForwardArgs *args);  /* K5 */
+int gsb200_stage_blend(const GsbForwardArgs *args);        /* K6 */
+
+/* Diagnostic variants of forward/backward: identical launches with a CUDA event recorded on the
+ * launching stream between stages; block until done and return device milliseconds per stage in
+ * stage_ms_out[8] (host): forward = {workspace memset, preprocess, sort, tile ranges, blend};
+ * backward = {grad/accumulator memsets, blend backward, per-point chain rule}.  (The reference's
+ * counterpart is the Taichi kernel profiler, GaussianPointTrainer.py:217-219.) */
+int gsb200_forward_timed(const GsbForwardArgs *args, float *stage_ms_out);
+int gsb200_backward_timed(const GsbBackwardArgs *args, float *stage_ms_out);
+
+/* find_tile_start_and_end, GPCR:175-193, on the reference's own key packing: sorted int64 keys
+ * (tile << 32 | depth) -> [start, end) per tile; outputs must be zero-initialised (GPCR:954-957). */
+int gsb200_find_tile_start_and_end(const int64_t *sorted_keys, int64_t num_keys, int32_t *tile_points_start,
+                                   int32_t *tile_points_end, int32_t num_tiles, void *stream);
+
+/* Stand-alone stable LSD radix sort of (key, int32 payload) pairs on the device; key_bytes 4 or 8,
+ * bits [0, end_bit) are sorted.  temp must hold gsb200_sort_temp_bytes(n, key_bytes). Result is
+ * left in keys_out / vals_out.  (Replaces torch.sort + gather, GPCR:947-950.) */
+int64_t gsb200_sort_temp_bytes(int64_t n, int32_t key_bytes);
+int gsb200_sort_pairs(const void *keys_in, const int32_t *vals_in, void *keys_out, int32_t *vals_out,
+                      int64_t n, int32_t key_bytes, int32_t end_bit, void *temp, int64_t temp_bytes,
+                      void *stream);
+
+/* Host-buffer entry point (end-to-end inference call): the scene stays resident on the device, the
+ * per-view inputs (pose, intrinsics) come from HOST memory and the image is returned to HOST memory.
+ * host pointers should be pinned.  Blocks until the image is in host memory.
+ * Replaces the render loop body gaussian_point_render.py:106-121 (pose .cuda(), forward, image .cpu()). */
+int gsb200_render_host(const GsbForwardArgs *device_args, const float *host_q_pointcloud_camera,
+                       const float *host_t_pointcloud_camera, const float *host_camera_intrinsics,
+                       float *staging_device_pose /* >= num_objects*7+9 floats, device */,
+                       float *host_image_out /* (H,W,3) */, int64_t *host_counters_out /* int64[4] or NULL */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSB200_H_ */

@@ -1,0 +1,16 @@
+"""taichi_3d_gaussian_splatting_b200 -- B200-native (sm_100a) differentiable 3D Gaussian splatting
+rasteriser, a drop-in for the hot path of wanmeihuali/taichi_3d_gaussian_splatting
+(``GaussianPointCloudRasterisation``).  Host code is Python/PyTorch (memory, streams, autograd,
+``torch.distributed``); every kernel is hand-written CUDA behind the C ABI in ``include/gsb200.h``.
+"""
+from .Camera import CameraInfo, CameraView  # noqa: F401
+from .GaussianPointCloudRasterisation import (  # noqa: F401
+    BOUNDARY_TILES,
+    TILE_HEIGHT,
+    TILE_WIDTH,
+    GaussianPointCloudRasterisation,
+    find_tile_start_and_end,
+)
+
+__all__ = ["CameraInfo", "CameraView", "GaussianPointCloudRasterisation", "find_tile_start_and_end",
+           "TILE_WIDTH", "TILE_HEIGHT", "BOUNDARY_TILES"]

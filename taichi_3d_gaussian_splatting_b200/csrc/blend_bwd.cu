@@ -1,0 +1,398 @@
+// blend_bwd.cu -- backward of the blend (replaces gaussian_point_rasterisation_backward, GPCR:488-772).
+//
+// Kernel A (loop A, GPCR:531-705): one CTA per tile replays its splat list back-to-front.  The
+// reference issues 11 global atomics per contributing (pixel, splat); here the 11 per-splat partials
+// (d/duv x2, d/dcov x3, d/dcolour x3, d/dlogit, |d/duv|, pixel count) are reduced across the warp
+// with a transposing butterfly (16 shuffles for all of them), then across the 8 warps in a
+// shared-memory accumulator, and flushed with ONE atomic row per (tile, splat).
+// Kernel B (loop B, GPCR:708-772 + GPCR:1102-1125, 1167-1182): per in-frustum point chain rule to
+// xyz / q / s / SH with the SH-band masking and the constant gradient factors fused in.
+#include "common.cuh"
+
+namespace gsb {
+
+struct BlendBwdParams {
+    int H, W, tiles_x;
+    const int *tile_start;
+    const int *tile_end;
+    const int *sorted_vals;
+    const float4 *records;
+    const float *grad_image;
+    const float *acc_alpha;
+    const int *last_effective;
+    float *accum;      // rows of 12 floats
+    float *mag_image;  // (H,W,2)
+};
+
+__device__ __forceinline__ float fast_exp_b(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+
+// Reduce 16 per-lane values across the warp with 16 shuffles.  On return lane l holds in v[0] the warp
+// total of value index (l >> 1) & 15 (both lanes of a pair hold the same total).
+__device__ __forceinline__ void warp_transpose_reduce16(float (&v)[16], int lane) {
+    {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float send = hi ? v[i] : v[i + 8];
+            const float keep = hi ? v[i + 8] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float send = hi ? v[i] : v[i + 4];
+            const float keep = hi ? v[i + 4] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool hi = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float send = hi ? v[i] : v[i + 2];
+            const float keep = hi ? v[i + 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    {
+        const bool hi = lane & 2;
+        const float send = hi ? v[0] : v[1];
+        const float keep = hi ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+constexpr int ACC_STRIDE = 13;  // odd row stride: conflict-free per-row and per-column access
+
+template <bool EXACT_EXP>
+__global__ void __launch_bounds__(GSB_TILE_PIXELS)
+blend_backward_kernel(const BlendBwdParams p) {
+    __shared__ float4 s_r0[GSB_TILE_PIXELS];
+    __shared__ float4 s_r1[GSB_TILE_PIXELS];
+    __shared__ float4 s_r2[GSB_TILE_PIXELS];
+    __shared__ int s_off[GSB_TILE_PIXELS];
+    __shared__ float s_acc[GSB_TILE_PIXELS * ACC_STRIDE];
+    __shared__ int s_max_last;
+
+    const int tile = blockIdx.x;
+    const int tu = tile % p.tiles_x, tv = tile / p.tiles_x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pu = tu * GSB_TILE_WIDTH + (warp & 1) * 8 + (lane & 7);
+    const int pv = tv * GSB_TILE_HEIGHT + (warp >> 1) * 4 + (lane >> 3);
+    const float px = (float)pu + 0.5f, py = (float)pv + 0.5f;
+    const size_t pix = (size_t)pv * p.W + pu;
+    const int start = p.tile_start[tile];
+
+    const int last = p.last_effective[pix];
+    float T = 1.0f - p.acc_alpha[pix];  // GPCR:559-560
+    float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f;
+    const float g0 = p.grad_image[3 * pix], g1 = p.grad_image[3 * pix + 1], g2 = p.grad_image[3 * pix + 2];
+    float mag0 = 0.0f, mag1 = 0.0f;
+
+    if (tid == 0) s_max_last = start;
+    __syncthreads();
+    atomicMax(&s_max_last, last);
+    __syncthreads();
+    // nothing behind the deepest effective splat of the tile contributes (GPCR:609-610)
+    const int end = min(p.tile_end[tile], s_max_last);
+
+    for (int block_end = end; block_end > start; block_end -= GSB_TILE_PIXELS) {
+        const int block_start = max(block_end - GSB_TILE_PIXELS, start);
+        const int nb = block_end - block_start;
+        __syncthreads();  // previous batch fully flushed before smem is reused
+        {
+            const int idx = block_end - 1 - tid;  // element j <-> sorted index block_end-1-j
+            if (idx >= block_start) {
+                const int o = __ldg(&p.sorted_vals[idx]);
+                const float4 *rec = p.records + 3 * (size_t)o;
+                s_r0[tid] = __ldg(rec);
+                s_r1[tid] = __ldg(rec + 1);
+                s_r2[tid] = __ldg(rec + 2);
+                s_off[tid] = o;
+            }
+#pragma unroll
+            for (int k = 0; k < 11; ++k) s_acc[tid * ACC_STRIDE + k] = 0.0f;
+        }
+        __syncthreads();
+        for (int j = 0; j < nb; ++j) {
+            const int idx = block_end - 1 - j;
+            float v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = 0.0f;
+            bool contributes = false;
+            if (idx < last) {
+                const float4 r0 = s_r0[j];  // u v a b
+                const float4 r1 = s_r1[j];  // c rescale opacity depth
+                const float d0 = px - r0.x, d1 = py - r0.y;
+                const float q0 = r0.z * d0 + r0.w * d1;  // conic @ d   (UT:337-339)
+                const float q1 = r0.w * d0 + r1.x * d1;
+                const float power = -0.5f * (d0 * q0 + d1 * q1);
+                const float gp = (EXACT_EXP ? expf(power) : fast_exp_b(power)) * r1.y;
+                const float opa = r1.z;
+                const float prod_alpha = gp * opa;
+                if (prod_alpha >= 1.0f / 255.0f) {  // GPCR:634
+                    contributes = true;
+                    const float alpha = fminf(prod_alpha, 0.99f);
+                    const float4 r2 = s_r2[j];
+                    const float inv = 1.0f / (1.0f - alpha);
+                    T = T * inv;                               // GPCR:643
+                    const float aT = alpha * T;                // d pixel / d colour (GPCR:649)
+                    const float a_grad = (r2.x * T - w0 * inv) * g0 + (r2.y * T - w1 * inv) * g1 +
+                                         (r2.z * T - w2 * inv) * g2;  // GPCR:653-657
+                    w0 += r2.x * aT;
+                    w1 += r2.y * aT;
+                    w2 += r2.z * aT;
+                    const float g_grad = a_grad * opa;         // d/d gaussian (GPCR:662)
+                    const float vs0 = g_grad * gp * q0, vs1 = g_grad * gp * q1;  // view-space grad
+                    mag0 += fabsf(vs0);
+                    mag1 += fabsf(vs1);
+                    const float hc = 0.5f * g_grad * gp;       // UT:345: 0.5 p (S^-1 d d^T S^-1)
+                    v[0] = vs0;
+                    v[1] = vs1;
+                    v[2] = hc * q0 * q0;
+                    v[3] = hc * q0 * q1;
+                    v[4] = hc * q1 * q1;
+                    v[5] = aT * g0;
+                    v[6] = aT * g1;
+                    v[7] = aT * g2;
+                    v[8] = a_grad * gp * (1.0f - opa) * opa;   // d/d logit (GPCR:658-661)
+                    v[9] = sqrtf(vs0 * vs0 + vs1 * vs1);       // GPCR:691-694
+                    v[10] = 1.0f;                              // affected-pixel count
+                }
+            }
+            if (__any_sync(0xffffffffu, contributes)) {
+                warp_transpose_reduce16(v, lane);
+                const int k = (lane >> 1) & 15;
+                if ((lane & 1) == 0 && k < 11) atomicAdd(&s_acc[j * ACC_STRIDE + k], v[0]);
+            }
+        }
+        __syncthreads();
+        if (tid < nb) {
+            const float cntf = s_acc[tid * ACC_STRIDE + 10];
+            if (cntf > 0.0f) {
+                float *row = p.accum + (size_t)s_off[tid] * GSB_ACCUM_FLOATS;
+#pragma unroll
+                for (int k = 0; k < 10; ++k) atomicAdd(row + k, s_acc[tid * ACC_STRIDE + k]);
+                atomicAdd(reinterpret_cast<int *>(row + 10), (int)(cntf + 0.5f));
+            }
+        }
+    }
+    p.mag_image[2 * pix] = mag0;      // GPCR:700-704
+    p.mag_image[2 * pix + 1] = mag1;
+}
+
+int launch_blend_backward(const GsbBackwardArgs &a, const Workspace &ws, cudaStream_t stream) {
+    const GsbWorkspaceLayout &L = ws.layout;
+    BlendBwdParams p;
+    p.H = a.camera_height;
+    p.W = a.camera_width;
+    p.tiles_x = a.camera_width / GSB_TILE_WIDTH;
+    p.tile_start = ws.tile_start;
+    p.tile_end = ws.tile_end;
+    p.sorted_vals = (L.sort_passes % 2) == 1 ? ws.vals_b : ws.vals_a;
+    p.records = ws.records;
+    p.grad_image = a.grad_rasterized_image;
+    p.acc_alpha = a.pixel_accumulated_alpha;
+    p.last_effective = a.pixel_offset_of_last_effective_point;
+    p.accum = a.accum;
+    p.mag_image = a.magnitude_grad_viewspace_on_image;
+    const int tiles = p.tiles_x * (a.camera_height / GSB_TILE_HEIGHT);
+    if (tiles <= 0) return GSB_OK;
+    if (a.flags & GSB_FLAG_EXACT_EXP)
+        blend_backward_kernel<true><<<tiles, GSB_TILE_PIXELS, 0, stream>>>(p);
+    else
+        blend_backward_kernel<false><<<tiles, GSB_TILE_PIXELS, 0, stream>>>(p);
+    GSB_CUDA_CHECK(cudaGetLastError());
+    return GSB_OK;
+}
+
+// ------------------------------------------------------------------ loop B + P4
+struct PointsBwdParams {
+    const long long *counters;
+    const int *point_id;
+    const float4 *records;
+    const float *point_in_camera;
+    const float *accum;
+    const PoseBlock *poses;
+    const float *xyz;
+    const float *features;
+    const int *obj_id;
+    const float *t_pc_cam;
+    const float *K;
+    int first_cleared;  // first SH coefficient index whose gradient is zeroed (GPCR:1167-1182)
+    float q_f, s_f, a_f, c_f, h_f;
+    float *grad_xyz;
+    float *grad_feat;
+};
+
+__global__ void __launch_bounds__(128)
+backward_points_kernel(const PointsBwdParams p) {
+    const long long M = p.counters[CNT_M];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < M; o += stride) {
+        const int id = p.point_id[o];
+        const float4 *accp = reinterpret_cast<const float4 *>(p.accum + (size_t)o * GSB_ACCUM_FLOATS);
+        const float4 a0 = accp[0], a1 = accp[1], a2 = accp[2];
+        // a0 = guv.x guv.y g00 g01 | a1 = g11 gr gg gb | a2 = glogit mag n pad
+        const float4 r2 = __ldg(p.records + 3 * (size_t)o + 2);  // r g b radius
+        const float pcx = p.point_in_camera[3 * o], pcy = p.point_in_camera[3 * o + 1],
+                    pcz = p.point_in_camera[3 * o + 2];
+        const int ob = p.obj_id[id];
+        const PoseBlock *pb = p.poses + ob;
+        float Wm[9] = {pb->T[0], pb->T[1], pb->T[2], pb->T[4], pb->T[5], pb->T[6], pb->T[8], pb->T[9], pb->T[10]};
+        float Kc[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Kc[k] = __ldg(&p.K[k]);
+        const float x = p.xyz[3 * (size_t)id], y = p.xyz[3 * (size_t)id + 1], z = p.xyz[3 * (size_t)id + 2];
+        const float4 *frow = reinterpret_cast<const float4 *>(p.features + (size_t)GSB_FEATURE_DIM * id);
+        const float4 qv = __ldg(frow);
+        const float4 sv = __ldg(frow + 1);  // s0 s1 s2 logit
+
+        // d uv / d xyz (GP3D:132-159): full-K projection Jacobian times W
+        const float iz = 1.0f / pcz, iz2 = iz * iz;
+        float dj[6] = {Kc[0] * iz, Kc[1] * iz, (-Kc[0] * pcx - Kc[1] * pcy) * iz2,
+                       Kc[3] * iz, Kc[4] * iz, (-Kc[3] * pcx - Kc[4] * pcy) * iz2};
+        float gx[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float d0 = dj[0] * Wm[c] + dj[1] * Wm[3 + c] + dj[2] * Wm[6 + c];
+            const float d1 = dj[3] * Wm[c] + dj[4] * Wm[3 + c] + dj[5] * Wm[6 + c];
+            gx[c] = a0.x * d0 + a0.y * d1;
+        }
+        // Sigma' = U Sigma U^T, U = J W with J from fx, fy only (GP3D:65-87, 237-331)
+        const float fx = Kc[0], fy = Kc[4];
+        float J[6] = {fx * iz, 0.0f, -(fx * pcx) * iz2, 0.0f, fy * iz, -(fy * pcy) * iz2};
+        float U[6];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            U[c] = J[0] * Wm[c] + J[1] * Wm[3 + c] + J[2] * Wm[6 + c];
+            U[3 + c] = J[3] * Wm[c] + J[4] * Wm[3 + c] + J[5] * Wm[6 + c];
+        }
+        const float g00 = a0.z, g01 = a0.w, g11 = a1.x;
+        // V = U^T G U  (dL/dSigma with the (g00,g01,g01,g11) weighting of GPCR:716-721)
+        float V[9];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float t0 = g00 * U[k] + g01 * U[3 + k];
+            const float t1 = g01 * U[k] + g11 * U[3 + k];
+#pragma unroll
+            for (int l = 0; l < 3; ++l) V[k * 3 + l] = t0 * U[l] + t1 * U[3 + l];
+        }
+        // R(q) (GP3D:30-48), M = R S
+        const float qx = qv.x, qy = qv.y, qz = qv.z, qw = qv.w;
+        float R[9];
+        R[0] = 1 - 2 * (qy * qy + qz * qz); R[1] = 2 * (qx * qy - qw * qz); R[2] = 2 * (qx * qz + qw * qy);
+        R[3] = 2 * (qx * qy + qw * qz); R[4] = 1 - 2 * (qx * qx + qz * qz); R[5] = 2 * (qy * qz - qw * qx);
+        R[6] = 2 * (qx * qz - qw * qy); R[7] = 2 * (qy * qz + qw * qx); R[8] = 1 - 2 * (qx * qx + qy * qy);
+        const float es[3] = {expf(sv.x), expf(sv.y), expf(sv.z)};
+        // dL/dM = (V + V^T) M,  M_ij = R_ij es_j
+        float dM[9];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int l = 0; l < 3; ++l) acc += (V[a * 3 + l] + V[l * 3 + a]) * (R[l * 3 + b] * es[b]);
+                dM[a * 3 + b] = acc;
+            }
+        // d/ds_j = sum_i dM_ij R_ij es_j
+        float gs[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) gs[j] = (dM[j] * R[j] + dM[3 + j] * R[3 + j] + dM[6 + j] * R[6 + j]) * es[j];
+        // d/dq = sum_ij dM_ij es_j dR_ij/dq  (table GP3D:316-329)
+        const float sx = es[0], sy = es[1], sz = es[2];
+        float gq[4];
+        gq[0] = dM[1] * (2 * sy * qy) + dM[2] * (2 * sz * qz) + dM[3] * (2 * sx * qy) + dM[4] * (-4 * sy * qx) +
+                dM[5] * (-2 * sz * qw) + dM[6] * (2 * sx * qz) + dM[7] * (2 * sy * qw) + dM[8] * (-4 * sz * qx);
+        gq[1] = dM[0] * (-4 * sx * qy) + dM[1] * (2 * sy * qx) + dM[2] * (2 * sz * qw) + dM[3] * (2 * sx * qx) +
+                dM[5] * (2 * sz * qz) + dM[6] * (-2 * sx * qw) + dM[7] * (2 * sy * qz) + dM[8] * (-4 * sz * qy);
+        gq[2] = dM[0] * (-4 * sx * qz) + dM[1] * (-2 * sy * qw) + dM[2] * (2 * sz * qx) + dM[3] * (2 * sx * qw) +
+                dM[4] * (-4 * sy * qz) + dM[5] * (2 * sz * qy) + dM[6] * (2 * sx * qx) + dM[7] * (2 * sy * qy);
+        gq[3] = dM[1] * (-2 * sy * qz) + dM[2] * (2 * sz * qy) + dM[3] * (2 * sx * qz) + dM[5] * (-2 * sz * qx) +
+                dM[6] * (-2 * sx * qy) + dM[7] * (2 * sy * qx);
+        // SH basis along xyz - camera centre (GPCR:731-732, 749; SH:10-32)
+        float dx = x - p.t_pc_cam[3 * ob], dy = y - p.t_pc_cam[3 * ob + 1], dz = z - p.t_pc_cam[3 * ob + 2];
+        const float dinv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+        dx *= dinv; dy *= dinv; dz *= dinv;
+        float sh[16];
+        sh[0] = 0.28209479177387814f;
+        sh[1] = -0.48860251190291987f * dy;
+        sh[2] = 0.48860251190291987f * dz;
+        sh[3] = -0.48860251190291987f * dx;
+        sh[4] = 1.0925484305920792f * dx * dy;
+        sh[5] = -1.0925484305920792f * dy * dz;
+        sh[6] = 0.94617469575755997f * dz * dz - 0.31539156525251999f;
+        sh[7] = -1.0925484305920792f * dx * dz;
+        sh[8] = 0.54627421529603959f * dx * dx - 0.54627421529603959f * dy * dy;
+        sh[9] = 0.59004358992664352f * dy * (-3.0f * dx * dx + dy * dy);
+        sh[10] = 2.8906114426405538f * dx * dy * dz;
+        sh[11] = 0.45704579946446572f * dy * (1.0f - 5.0f * dz * dz);
+        sh[12] = 0.3731763325901154f * dz * (5.0f * dz * dz - 3.0f);
+        sh[13] = 0.45704579946446572f * dx * (1.0f - 5.0f * dz * dz);
+        sh[14] = 1.4453057213202769f * dz * (dx * dx - dy * dy);
+        sh[15] = 0.59004358992664352f * dx * (-dx * dx + 3.0f * dy * dy);
+        // sigmoid'(.) from the stored colour: c (1 - c)  (UT:356-359)
+        const float gcol[3] = {a1.y * (r2.x * (1.0f - r2.x)), a1.z * (r2.y * (1.0f - r2.y)),
+                               a1.w * (r2.z * (1.0f - r2.z))};
+
+        float *gxp = p.grad_xyz + 3 * (size_t)id;
+        gxp[0] = gx[0]; gxp[1] = gx[1]; gxp[2] = gx[2];
+        float4 *gf = reinterpret_cast<float4 *>(p.grad_feat + (size_t)GSB_FEATURE_DIM * id);
+        gf[0] = make_float4(gq[0] * p.q_f, gq[1] * p.q_f, gq[2] * p.q_f, gq[3] * p.q_f);
+        gf[1] = make_float4(gs[0] * p.s_f, gs[1] * p.s_f, gs[2] * p.s_f, a2.x * p.a_f);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            float o16[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const float factor = k == 0 ? p.c_f : p.h_f;
+                o16[k] = k < p.first_cleared ? gcol[ch] * sh[k] * factor : 0.0f;
+            }
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+                gf[2 + 4 * ch + k4] = make_float4(o16[4 * k4], o16[4 * k4 + 1], o16[4 * k4 + 2], o16[4 * k4 + 3]);
+        }
+    }
+}
+
+int launch_backward_points(const GsbBackwardArgs &a, const Workspace &ws, cudaStream_t stream) {
+    if (a.num_points <= 0) return GSB_OK;
+    PointsBwdParams p;
+    p.counters = ws.counters;
+    p.point_id = ws.point_id;
+    p.records = ws.records;
+    p.point_in_camera = ws.point_in_camera;
+    p.accum = a.accum;
+    p.poses = ws.poses;
+    p.xyz = a.pointcloud;
+    p.features = a.pointcloud_features;
+    p.obj_id = a.point_object_id;
+    p.t_pc_cam = a.t_pointcloud_camera;
+    p.K = a.camera_intrinsics;
+    const int band = a.color_max_sh_band;
+    p.first_cleared = band <= 0 ? 1 : band == 1 ? 4 : band == 2 ? 9 : 16;
+    p.q_f = a.grad_q_factor;
+    p.s_f = a.grad_s_factor;
+    p.a_f = a.grad_alpha_factor;
+    p.c_f = a.grad_color_factor;
+    p.h_f = a.grad_high_order_color_factor;
+    p.grad_xyz = a.grad_pointcloud;
+    p.grad_feat = a.grad_pointcloud_features;
+    long long blocks = (a.accum_rows + 127) / 128;
+    const long long cap = 16LL * num_sms();
+    if (blocks > cap) blocks = cap;
+    if (blocks <= 0) return GSB_OK;
+    backward_points_kernel<<<(int)blocks, 128, 0, stream>>>(p);
+    GSB_CUDA_CHECK(cudaGetLastError());
+    return GSB_OK;
+}
+
+}  // namespace gsb

@@ -1,0 +1,137 @@
+// blend_fwd.cu -- per-tile front-to-back alpha blending (replaces gaussian_point_rasterisation,
+// GPCR:318-485, with get_point_probability_density_from_conic_and_rescale, UT:275-284).
+//
+// One CTA per 16x16 tile, one pixel per thread; a warp owns an 8x4 pixel patch so that the
+// alpha < 1/255 rejection and the saturation exit stay warp-coherent.  The tile's splat list is
+// streamed through shared memory in batches of 256 packed 48-byte records (3 x float4, gathered by
+// the sorted in-camera offsets); the inner loop reads them as broadcasts.  The CTA leaves the list as
+// soon as every pixel has saturated (__syncthreads_and) -- the reference walks the whole list
+// (GPCR:387-394).  Compute-bound (FP32 + MUFU.EX2), not HBM-bound: 48 B per (tile, splat) are reused
+// by 256 pixels.
+#include "common.cuh"
+
+namespace gsb {
+
+struct BlendFwdParams {
+    int H, W, tiles_x;
+    const int *tile_start;
+    const int *tile_end;
+    const int *sorted_vals;
+    const float4 *records;
+    float *image;
+    float *depth;
+    float *acc_alpha;
+    int *last_effective;
+    int *valid_count;
+};
+
+__device__ __forceinline__ float fast_exp(float x) {
+    // ex2.approx(x * log2e) -> one FMUL + one MUFU.EX2; rel. error ~2^-21 for the arguments met here
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+
+template <bool RGB_ONLY, bool EXACT_EXP>
+__global__ void __launch_bounds__(GSB_TILE_PIXELS)
+blend_forward_kernel(const BlendFwdParams p) {
+    __shared__ float4 s_r0[GSB_TILE_PIXELS];
+    __shared__ float4 s_r1[GSB_TILE_PIXELS];
+    __shared__ float4 s_r2[GSB_TILE_PIXELS];
+
+    const int tile = blockIdx.x;
+    const int tu = tile % p.tiles_x, tv = tile / p.tiles_x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // warp w covers the 8x4 patch at ((w & 1) * 8, (w >> 1) * 4)
+    const int pu = tu * GSB_TILE_WIDTH + (warp & 1) * 8 + (lane & 7);
+    const int pv = tv * GSB_TILE_HEIGHT + (warp >> 1) * 4 + (lane >> 3);
+    const float px = (float)pu + 0.5f, py = (float)pv + 0.5f;  // GPCR:442 pixel centre
+    const int start = p.tile_start[tile], end = p.tile_end[tile];
+
+    float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, D = 0.0f, Wt = 0.0f;
+    int last = start, cnt = 0;
+    bool done = false;
+
+    for (int base = start; base < end; base += GSB_TILE_PIXELS) {
+        if (__syncthreads_and(done)) break;  // barrier (smem reuse) + tile-level early exit
+        const int idx = base + tid;
+        if (idx < end) {
+            const int o = __ldg(&p.sorted_vals[idx]);
+            const float4 *rec = p.records + 3 * (size_t)o;
+            s_r0[tid] = __ldg(rec);
+            s_r1[tid] = __ldg(rec + 1);
+            s_r2[tid] = __ldg(rec + 2);
+        }
+        __syncthreads();
+        const int nb = min(GSB_TILE_PIXELS, end - base);
+        if (!done) {
+            for (int j = 0; j < nb; ++j) {
+                const float4 r0 = s_r0[j];  // u v a b
+                const float4 r1 = s_r1[j];  // c rescale opacity depth
+                const float dx = px - r0.x, dy = py - r0.y;
+                const float power = -0.5f * (dx * dx * r0.z + dy * dy * r1.x) - dx * dy * r0.w;
+                const float g = (EXACT_EXP ? expf(power) : fast_exp(power)) * r1.y;
+                float alpha = g * r1.z;
+                if (alpha < 1.0f / 255.0f) continue;   // GPCR:451
+                alpha = fminf(alpha, 0.99f);           // GPCR:453
+                const float nT = T * (1.0f - alpha);
+                if (nT < 0.0001f) {                     // GPCR:457-460: saturated, splat not blended
+                    done = true;
+                    break;
+                }
+                last = base + j + 1;
+                const float4 r2 = s_r2[j];
+                C0 += r2.x * alpha * T;
+                C1 += r2.y * alpha * T;
+                C2 += r2.z * alpha * T;
+                if (!RGB_ONLY) {
+                    D += r1.w * alpha * T;
+                    Wt += alpha * T;
+                    cnt += 1;
+                }
+                T = nT;
+            }
+        }
+    }
+    const size_t pix = (size_t)pv * p.W + pu;
+    p.image[3 * pix] = C0;
+    p.image[3 * pix + 1] = C1;
+    p.image[3 * pix + 2] = C2;
+    if (!RGB_ONLY) {
+        p.depth[pix] = D / fmaxf(Wt, 1e-6f);  // GPCR:479-480
+        p.acc_alpha[pix] = 1.0f - T;
+        p.last_effective[pix] = last;
+        p.valid_count[pix] = cnt;
+    }
+}
+
+int launch_blend_forward(const GsbForwardArgs &a, const Workspace &ws, cudaStream_t stream) {
+    const GsbWorkspaceLayout &L = ws.layout;
+    BlendFwdParams p;
+    p.H = a.camera_height;
+    p.W = a.camera_width;
+    p.tiles_x = a.camera_width / GSB_TILE_WIDTH;
+    p.tile_start = ws.tile_start;
+    p.tile_end = ws.tile_end;
+    p.sorted_vals = (L.sort_passes % 2) == 1 ? ws.vals_b : ws.vals_a;
+    p.records = ws.records;
+    p.image = a.rasterized_image;
+    p.depth = a.rasterized_depth;
+    p.acc_alpha = a.pixel_accumulated_alpha;
+    p.last_effective = a.pixel_offset_of_last_effective_point;
+    p.valid_count = a.pixel_valid_point_count;
+    const int tiles = p.tiles_x * (a.camera_height / GSB_TILE_HEIGHT);
+    if (tiles <= 0) return GSB_OK;
+    const bool exact = (a.flags & GSB_FLAG_EXACT_EXP) != 0;
+    if (a.rgb_only) {
+        if (exact) blend_forward_kernel<true, true><<<tiles, GSB_TILE_PIXELS, 0, stream>>>(p);
+        else blend_forward_kernel<true, false><<<tiles, GSB_TILE_PIXELS, 0, stream>>>(p);
+    } else {
+        if (exact) blend_forward_kernel<false, true><<<tiles, GSB_TILE_PIXELS, 0, stream>>>(p);
+        else blend_forward_kernel<false, false><<<tiles, GSB_TILE_PIXELS, 0, stream>>>(p);
+    }
+    GSB_CUDA_CHECK(cudaGetLastError());
+    return GSB_OK;
+}
+
+}  // namespace gsb

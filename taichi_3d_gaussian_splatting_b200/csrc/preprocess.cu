@@ -1,0 +1,404 @@
+// preprocess.cu -- per-Gaussian stage, ONE pass over the N rows of the scene:
+//   frustum filter (GPCR:31-78) + order-preserving compaction (GPCR:861-864)
+//   + projection / EWA covariance / conic / opacity / SH colour / radius (GPCR:239-315)
+//   + tile-rect count (GPCR:81-128) + exclusive scan of the counts (GPCR:913-922)
+//   + (tile, depth) key emission (GPCR:131-172)
+// fused behind a single-pass decoupled look-back scan of the pair (in-frustum flag, tile count), so a
+// point's in-camera offset and its key range are known inside the same kernel and nothing is re-read.
+//
+// This translation unit is compiled with -fmad=false: every float op is a plain IEEE op in the same
+// order as the CPU oracle, and exp() is evaluated in double and rounded once, so all discrete per-point
+// decisions (frustum test, tile bbox, depth key) are bit-reproducible.  The stage is HBM-bound
+// (~240 B read, ~70 B + 8..12 B/key written per in-frustum point), the extra ALU work is free.
+#include "common.cuh"
+
+namespace gsb {
+
+// ------------------------------------------------------------------ small device math (IEEE order)
+template <int AR, int AC, int BC>
+__device__ __forceinline__ void matmul(const float *a, const float *b, float *out) {
+#pragma unroll
+    for (int i = 0; i < AR; ++i)
+#pragma unroll
+        for (int j = 0; j < BC; ++j) {
+            float s = a[i * AC] * b[j];
+#pragma unroll
+            for (int k = 1; k < AC; ++k) s = s + a[i * AC + k] * b[k * BC + j];
+            out[i * BC + j] = s;
+        }
+}
+
+// GP3D:30-48 (xyzw, not re-normalised)
+__device__ __forceinline__ void rotation_from_quaternion(float x, float y, float z, float w, float *R) {
+    float xx = x * x, yy = y * y, zz = z * z;
+    float xy = x * y, xz = x * z, yz = y * z;
+    float wx = w * x, wy = w * y, wz = w * z;
+    R[0] = 1 - 2 * (yy + zz); R[1] = 2 * (xy - wz);     R[2] = 2 * (xz + wy);
+    R[3] = 2 * (xy + wz);     R[4] = 1 - 2 * (xx + zz); R[5] = 2 * (yz - wx);
+    R[6] = 2 * (xz - wy);     R[7] = 2 * (yz + wx);     R[8] = 1 - 2 * (xx + yy);
+}
+
+__device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x); }
+__device__ __forceinline__ float sigmoid_cr(float x) { return 1.0f / (1.0f + exp_cr(-x)); }
+
+// quaternion product, UT:396-411
+__device__ __forceinline__ void quat_mul(const float *a, const float *b, float *o) {
+    float x0 = a[0], y0 = a[1], z0 = a[2], w0 = a[3];
+    float x1 = b[0], y1 = b[1], z1 = b[2], w1 = b[3];
+    o[0] = w0 * x1 + x0 * w1 + y0 * z1 - z0 * y1;
+    o[1] = w0 * y1 - x0 * z1 + y0 * w1 + z0 * x1;
+    o[2] = w0 * z1 + x0 * y1 - y0 * x1 + z0 * w1;
+    o[3] = w0 * w1 - x0 * x1 - y0 * y1 - z0 * z1;
+}
+
+// ------------------------------------------------------------------ pose kernel
+// inverse_SE3_qt_torch (UT:426-432, called at GPCR:845) + transform_matrix_from_quaternion_and_translation
+// (GP3D:51-62) + camera centre of taichi_inverse_SE3 (UT:495-510), once per object instead of per point.
+__global__ void pose_kernel(const float *__restrict__ q_pc, const float *__restrict__ t_pc, int n_obj,
+                            PoseBlock *__restrict__ poses) {
+    int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_obj) return;
+    float qi[4] = {-q_pc[4 * o], -q_pc[4 * o + 1], -q_pc[4 * o + 2], q_pc[4 * o + 3]};
+    float t[3] = {t_pc[3 * o], t_pc[3 * o + 1], t_pc[3 * o + 2]};
+    float n = sqrtf(((qi[0] * qi[0] + qi[1] * qi[1]) + qi[2] * qi[2]) + qi[3] * qi[3]);
+    float qn[4] = {qi[0] / n, qi[1] / n, qi[2] / n, qi[3] / n};
+    float v[4] = {t[0], t[1], t[2], 0.0f};
+    float qc[4] = {-qn[0], -qn[1], -qn[2], qn[3]};
+    float tmp[4], rot[4];
+    quat_mul(qn, v, tmp);
+    quat_mul(tmp, qc, rot);
+    float ti[3] = {-rot[0], -rot[1], -rot[2]};
+    float R[9];
+    rotation_from_quaternion(qi[0], qi[1], qi[2], qi[3], R);
+    PoseBlock pb;
+    pb.T[0] = R[0]; pb.T[1] = R[1]; pb.T[2] = R[2];  pb.T[3] = ti[0];
+    pb.T[4] = R[3]; pb.T[5] = R[4]; pb.T[6] = R[5];  pb.T[7] = ti[1];
+    pb.T[8] = R[6]; pb.T[9] = R[7]; pb.T[10] = R[8]; pb.T[11] = ti[2];
+    float nRT[9] = {-R[0], -R[3], -R[6], -R[1], -R[4], -R[7], -R[2], -R[5], -R[8]};
+    matmul<3, 3, 1>(nRT, ti, pb.centre);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) pb.pad[k] = 0.0f;
+    poses[o] = pb;
+}
+
+// ------------------------------------------------------------------ look-back scan state
+// 64-bit word: [63:62] status, [61:36] point count (26 b), [35:0] tile-pair count (36 b).
+constexpr unsigned long long ST_AGGREGATE = 1ull << 62;
+constexpr unsigned long long ST_INCLUSIVE = 2ull << 62;
+constexpr unsigned long long ST_VALUE_MASK = (1ull << 62) - 1;
+constexpr int CNT_SHIFT = 36;
+
+__device__ __forceinline__ unsigned long long ld_state(const unsigned long long *p) {
+    return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+__device__ __forceinline__ void st_state(unsigned long long *p, unsigned long long v) {
+    *reinterpret_cast<volatile unsigned long long *>(p) = v;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+struct PreParams {
+    long long N;
+    const float *xyz;
+    float *features;
+    const signed char *invalid;
+    const int *obj_id;
+    const PoseBlock *poses;
+    const float *K;
+    int W, H;
+    float near_plane, far_plane, depth_scale;
+    int depth_bits;
+    long long key_capacity;
+    int num_blocks;
+    // outputs
+    long long *counters;
+    unsigned int *tickets;
+    unsigned long long *scan_state;
+    int *point_id;
+    int *num_tiles;
+    float4 *records;
+    float *point_in_camera;
+    void *keys;
+    int *vals;
+};
+
+// GPCR:81-103
+__device__ __forceinline__ void bounding_box(float u, float v, float radii, int W, int H, int &a, int &b,
+                                             int &c, int &d) {
+    radii = fmaxf(radii, 1.0f);
+    float min_u = fmaxf(0.0f, u - radii), max_u = u + radii;
+    float min_v = fmaxf(0.0f, v - radii), max_v = v + radii;
+    int tw = W / GSB_TILE_WIDTH, th = H / GSB_TILE_HEIGHT;
+    a = min((int)floorf(min_u / (float)GSB_TILE_WIDTH), tw);
+    b = min(max((int)floorf(max_u / (float)GSB_TILE_WIDTH) + 1, a + 1), tw);
+    c = min((int)floorf(min_v / (float)GSB_TILE_HEIGHT), th);
+    d = min(max((int)floorf(max_v / (float)GSB_TILE_HEIGHT) + 1, c + 1), th);
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(SCAN_BLOCK_THREADS)
+preprocess_kernel(const PreParams p) {
+    __shared__ unsigned int s_ticket;
+    __shared__ unsigned long long s_warp_sums[SCAN_BLOCK_THREADS / 32];
+    __shared__ unsigned long long s_block_exclusive;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_ticket = atomicAdd(&p.tickets[TICKET_SCAN], 1u);
+    __syncthreads();
+    const int blk = (int)s_ticket;
+    const long long i = (long long)blk * SCAN_BLOCK_THREADS + tid;
+
+    bool in = false;
+    int ntiles = 0, min_tu = 0, max_tu = 0, min_tv = 0, max_tv = 0;
+    float4 r0 = make_float4(0, 0, 0, 0), r1 = r0, r2 = r0;
+    float pc[3] = {0, 0, 0};
+
+    if (i < p.N && p.invalid[i] != 1) {
+        const PoseBlock *pb = p.poses + p.obj_id[i];
+        float T[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) T[k] = __ldg(&pb->T[k]);
+        float Kc[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Kc[k] = __ldg(&p.K[k]);
+        const float x = __ldg(&p.xyz[3 * i]), y = __ldg(&p.xyz[3 * i + 1]), z = __ldg(&p.xyz[3 * i + 2]);
+        // GP3D:14-27: T @ (x,y,z,1), then uv = (K @ pc) / pc.z
+        pc[0] = ((T[0] * x + T[1] * y) + T[2] * z) + T[3] * 1.0f;
+        pc[1] = ((T[4] * x + T[5] * y) + T[6] * z) + T[7] * 1.0f;
+        pc[2] = ((T[8] * x + T[9] * y) + T[10] * z) + T[11] * 1.0f;
+        float uv1[3];
+        matmul<3, 3, 1>(Kc, pc, uv1);
+        const float u = uv1[0] / pc[2], v = uv1[1] / pc[2];
+        in = pc[2] > p.near_plane && pc[2] < p.far_plane &&
+             u >= (float)(-GSB_TILE_WIDTH * GSB_BOUNDARY_TILES) &&
+             u < (float)(p.W + GSB_TILE_WIDTH * GSB_BOUNDARY_TILES) &&
+             v >= (float)(-GSB_TILE_HEIGHT * GSB_BOUNDARY_TILES) &&
+             v < (float)(p.H + GSB_TILE_HEIGHT * GSB_BOUNDARY_TILES);
+        if (in) {
+            float4 *frow = reinterpret_cast<float4 *>(p.features + (size_t)GSB_FEATURE_DIM * i);
+            float4 qv = frow[0];  // plain load: this row's q is rewritten below
+            float f[GSB_FEATURE_DIM - 4];
+#pragma unroll
+            for (int k = 1; k < GSB_FEATURE_DIM / 4; ++k) {
+                float4 t4 = __ldg(reinterpret_cast<const float4 *>(frow) + k);
+                f[4 * (k - 1)] = t4.x; f[4 * (k - 1) + 1] = t4.y;
+                f[4 * (k - 1) + 2] = t4.z; f[4 * (k - 1) + 3] = t4.w;
+            }
+            // GPCR:196-205: q <- q / |q| (invlen * q), written back in place
+            float qn = sqrtf(((qv.x * qv.x + qv.y * qv.y) + qv.z * qv.z) + qv.w * qv.w);
+            float inv = 1.0f / qn;
+            qv.x = inv * qv.x; qv.y = inv * qv.y; qv.z = inv * qv.z; qv.w = inv * qv.w;
+            frow[0] = qv;
+            // GP3D:161-191: Sigma' = J W R S S^T R^T W^T J^T
+            float J[6];
+            const float fx = Kc[0], fy = Kc[4];
+            J[0] = fx / pc[2]; J[1] = 0.0f; J[2] = -(fx * pc[0]) / (pc[2] * pc[2]);
+            J[3] = 0.0f; J[4] = fy / pc[2]; J[5] = -(fy * pc[1]) / (pc[2] * pc[2]);
+            float R[9], S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, RS[9], RSS[9], RT[9], Sigma[9];
+            rotation_from_quaternion(qv.x, qv.y, qv.z, qv.w, R);
+            S[0] = exp_cr(f[0]); S[4] = exp_cr(f[1]); S[8] = exp_cr(f[2]);
+            matmul<3, 3, 3>(R, S, RS);
+            matmul<3, 3, 3>(RS, S, RSS);  // S^T == S (diagonal)
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) RT[b * 3 + a] = R[a * 3 + b];
+            matmul<3, 3, 3>(RSS, RT, Sigma);
+            float Wm[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
+            float WT[9], JW[6], JWS[6], JWSW[6], JT[6], cov[4];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) WT[b * 3 + a] = Wm[a * 3 + b];
+            matmul<2, 3, 3>(J, Wm, JW);
+            matmul<2, 3, 3>(JW, Sigma, JWS);
+            matmul<2, 3, 3>(JWS, WT, JWSW);
+            JT[0] = J[0]; JT[1] = J[3]; JT[2] = J[1]; JT[3] = J[4]; JT[4] = J[2]; JT[5] = J[5];
+            matmul<2, 3, 2>(JWSW, JT, cov);
+            // UT:257-272 conic + rescale (+0.3 low-pass)
+            float c00 = cov[0], c01 = cov[1], c10 = cov[2], c11 = cov[3];
+            const float det_pre = c00 * c11 - c01 * c10;
+            c00 += 0.3f;
+            c11 += 0.3f;
+            const float det = c00 * c11 - c01 * c10;
+            const float rescale = sqrtf(fmaxf(0.0f, det_pre / det));
+            const float inv_det = 1.0f / det;
+            // GPCR:311-315 radius from the un-blurred covariance
+            const float ca = cov[0], cd = cov[3];
+            const float large = (ca + cd + sqrtf((ca - cd) * (ca - cd) + 4.0f * cov[1] * cov[2])) / 2.0f;
+            const float radius = sqrtf(large) * 3.0f;
+            // GPCR:299-310 opacity + SH colour along (xyz - camera centre)
+            const float opacity = 1.0f / (1.0f + exp_cr(-f[3]));
+            float dx = x - __ldg(&pb->centre[0]), dy = y - __ldg(&pb->centre[1]),
+                  dz = z - __ldg(&pb->centre[2]);
+            float dn = sqrtf(dx * dx + dy * dy + dz * dz);
+            float dinv = 1.0f / dn;
+            dx = dinv * dx; dy = dinv * dy; dz = dinv * dz;
+            float sh[16];
+            sh[0] = 0.28209479177387814f;
+            sh[1] = -0.48860251190291987f * dy;
+            sh[2] = 0.48860251190291987f * dz;
+            sh[3] = -0.48860251190291987f * dx;
+            sh[4] = 1.0925484305920792f * dx * dy;
+            sh[5] = -1.0925484305920792f * dy * dz;
+            sh[6] = 0.94617469575755997f * dz * dz - 0.31539156525251999f;
+            sh[7] = -1.0925484305920792f * dx * dz;
+            sh[8] = 0.54627421529603959f * dx * dx - 0.54627421529603959f * dy * dy;
+            sh[9] = 0.59004358992664352f * dy * (-3.0f * dx * dx + dy * dy);
+            sh[10] = 2.8906114426405538f * dx * dy * dz;
+            sh[11] = 0.45704579946446572f * dy * (1.0f - 5.0f * dz * dz);
+            sh[12] = 0.3731763325901154f * dz * (5.0f * dz * dz - 3.0f);
+            sh[13] = 0.45704579946446572f * dx * (1.0f - 5.0f * dz * dz);
+            sh[14] = 1.4453057213202769f * dz * (dx * dx - dy * dy);
+            sh[15] = 0.59004358992664352f * dx * (-dx * dx + 3.0f * dy * dy);
+            float col[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float *cf = f + 4 + 16 * ch;
+                float acc = cf[0] * sh[0];
+#pragma unroll
+                for (int k = 1; k < 16; ++k) acc = acc + cf[k] * sh[k];
+                col[ch] = sigmoid_cr(acc);
+            }
+            bounding_box(u, v, radius, p.W, p.H, min_tu, max_tu, min_tv, max_tv);
+            ntiles = (max_tu - min_tu) * (max_tv - min_tv);
+            r0 = make_float4(u, v, inv_det * c11, inv_det * (-c01));
+            r1 = make_float4(inv_det * c00, rescale, opacity, pc[2]);
+            r2 = make_float4(col[0], col[1], col[2], radius);
+        }
+    }
+
+    // ---- block-level exclusive scan of the packed pair (count << 36 | tiles)
+    const unsigned long long mine = ((unsigned long long)(in ? 1 : 0) << CNT_SHIFT) | (unsigned long long)ntiles;
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_warp_sums[warp] = incl;
+    __syncthreads();
+    unsigned long long warp_prefix = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_BLOCK_THREADS / 32; ++w) {
+        unsigned long long s = s_warp_sums[w];
+        if (w < warp) warp_prefix += s;
+        block_total += s;
+    }
+    // ---- decoupled look-back across blocks (warp 0)
+    if (warp == 0) {
+        unsigned long long exclusive = 0;
+        if (blk == 0) {
+            if (lane == 0) st_state(&p.scan_state[0], ST_INCLUSIVE | block_total);
+        } else {
+            if (lane == 0) st_state(&p.scan_state[blk], ST_AGGREGATE | block_total);
+            int look = blk - 1;
+            while (true) {
+                const int idx = look - lane;
+                unsigned long long word = ST_INCLUSIVE;  // virtual predecessor of block 0
+                if (idx >= 0) {
+                    word = ld_state(&p.scan_state[idx]);
+                    while ((word >> 62) == 0) word = ld_state(&p.scan_state[idx]);
+                }
+                const unsigned incl_mask = __ballot_sync(0xffffffffu, (word >> 62) == 2);
+                unsigned long long val = word & ST_VALUE_MASK;
+                if (incl_mask) {
+                    const int first = __ffs(incl_mask) - 1;
+                    if (lane > first) val = 0;
+                    exclusive += warp_sum_u64(val);
+                    break;
+                }
+                exclusive += warp_sum_u64(val);
+                look -= 32;
+            }
+            if (lane == 0) st_state(&p.scan_state[blk], ST_INCLUSIVE | (exclusive + block_total));
+        }
+        if (lane == 0) {
+            s_block_exclusive = exclusive;
+            if (blk == p.num_blocks - 1) {
+                const unsigned long long tot = exclusive + block_total;
+                const long long Ktot = (long long)(tot & ((1ull << CNT_SHIFT) - 1));
+                p.counters[CNT_M] = (long long)(tot >> CNT_SHIFT);
+                p.counters[CNT_K] = Ktot;
+                p.counters[CNT_OVERFLOW] = Ktot > p.key_capacity ? 1 : 0;
+            }
+        }
+    }
+    __syncthreads();
+    if (!in) return;
+    const unsigned long long excl = s_block_exclusive + warp_prefix + (incl - mine);
+    const long long off = (long long)(excl >> CNT_SHIFT);
+    const long long key_base = (long long)(excl & ((1ull << CNT_SHIFT) - 1));
+
+    p.point_id[off] = (int)i;
+    p.num_tiles[off] = ntiles;
+    p.records[3 * off] = r0;
+    p.records[3 * off + 1] = r1;
+    p.records[3 * off + 2] = r2;
+    p.point_in_camera[3 * off] = pc[0];
+    p.point_in_camera[3 * off + 1] = pc[1];
+    p.point_in_camera[3 * off + 2] = pc[2];
+
+    // GPCR:158-170: key = tile_id << depth_bits | int32(depth * scale)   (tile_u outer, tile_v inner)
+    const int depth_key = (int)(pc[2] * p.depth_scale);
+    KeyT *keys = reinterpret_cast<KeyT *>(p.keys);
+    const int tiles_x = p.W / GSB_TILE_WIDTH;
+    long long pos = key_base;
+    for (int tu = min_tu; tu < max_tu; ++tu)
+        for (int tv = min_tv; tv < max_tv; ++tv, ++pos) {
+            if (pos < p.key_capacity) {
+                const KeyT tile = (KeyT)(tu + tv * tiles_x);
+                keys[pos] = (tile << p.depth_bits) | (KeyT)(unsigned int)depth_key;
+                p.vals[pos] = (int)off;
+            }
+        }
+}
+
+int launch_preprocess(const GsbForwardArgs &a, const Workspace &ws, cudaStream_t stream) {
+    const GsbWorkspaceLayout &L = ws.layout;
+    if (a.num_objects > 0) {
+        const int threads = 64;
+        pose_kernel<<<(a.num_objects + threads - 1) / threads, threads, 0, stream>>>(
+            a.q_pointcloud_camera, a.t_pointcloud_camera, a.num_objects, ws.poses);
+        GSB_CUDA_CHECK(cudaGetLastError());
+    }
+    if (a.num_points <= 0) return GSB_OK;
+    PreParams p;
+    p.N = a.num_points;
+    p.xyz = a.pointcloud;
+    p.features = a.pointcloud_features;
+    p.invalid = reinterpret_cast<const signed char *>(a.point_invalid_mask);
+    p.obj_id = a.point_object_id;
+    p.poses = ws.poses;
+    p.K = a.camera_intrinsics;
+    p.W = a.camera_width;
+    p.H = a.camera_height;
+    p.near_plane = a.near_plane;
+    p.far_plane = a.far_plane;
+    p.depth_scale = a.depth_to_sort_key_scale;
+    p.depth_bits = L.depth_bits;
+    p.key_capacity = a.key_capacity;
+    p.num_blocks = L.scan_blocks;
+    p.counters = ws.counters;
+    p.tickets = ws.tickets;
+    p.scan_state = ws.scan_state;
+    p.point_id = ws.point_id;
+    p.num_tiles = ws.num_tiles;
+    p.records = ws.records;
+    p.point_in_camera = ws.point_in_camera;
+    p.keys = ws.keys_a;
+    p.vals = ws.vals_a;
+    if (L.key_bytes == 4)
+        preprocess_kernel<unsigned int><<<L.scan_blocks, SCAN_BLOCK_THREADS, 0, stream>>>(p);
+    else
+        preprocess_kernel<unsigned long long><<<L.scan_blocks, SCAN_BLOCK_THREADS, 0, stream>>>(p);
+    GSB_CUDA_CHECK(cudaGetLastError());
+    return GSB_OK;
+}
+
+}  // namespace gsb

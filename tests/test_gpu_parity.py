@@ -1,0 +1,232 @@
+"""-m gpu parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star): forward RGB within 1e-4 abs, gradients within 1e-3 rel
+(denominator floor 1e-6 * max|g|).  Integer / index work (compaction order, tile counts,
+keys, sort order, tile ranges, last-effective offsets, pixel counts) must be bit-exact; the per-point
+float attributes are bit-exact too because the preprocess kernel evaluates the oracle's op order
+(-fmad=false, exp rounded once from double).
+"""
+import numpy as np
+import pytest
+import torch
+
+from taichi_3d_gaussian_splatting_b200.synthetic import CONFIGS, make_scene
+
+from helpers import oracle_backward, oracle_forward, rel_err
+from gpu_helpers import count_above, cuda_scene, make_op, n, run_forward
+
+pytestmark = pytest.mark.gpu
+
+
+def _small_scene(seed, npts=3000, h=64, w=96, sigma=0.06, yaw=7.0, sh_degree=3):
+    sc = make_scene(npts, h, w, sigma, seed, sh_degree=sh_degree, yaw_degrees=yaw)
+    sc.point_cloud[:, 2] = sc.point_cloud[:, 2] * 0.6
+    sc.point_cloud_features[:, 7] += 1.0
+    sc.point_cloud_features[:, :4] *= 1.7  # un-normalised quaternions on input
+    sc.point_invalid_mask[::11] = 1
+    return sc
+
+
+def _check_stages(frame, fwd, exact_floats=True):
+    assert frame.num_points_in_camera == fwd.point_id_in_camera_list.shape[0]
+    assert frame.num_keys == fwd.point_offset_with_sort_key.shape[0]
+    assert (n(frame.point_id_in_camera_list) == fwd.point_id_in_camera_list).all()
+    assert (n(frame.num_overlap_tiles) == fwd.num_overlap_tiles).all()
+    pairs = [(frame.point_uv, fwd.point_uv), (frame.point_in_camera, fwd.point_in_camera),
+             (frame.point_uv_conic_and_rescale, fwd.point_uv_conic_and_rescale),
+             (frame.point_alpha_after_activation, fwd.point_alpha_after_activation),
+             (frame.point_color, fwd.point_color), (frame.point_radii, fwd.point_radii)]
+    for got, exp in pairs:
+        got = n(got)
+        if exact_floats:
+            assert np.array_equal(got, exp), f"max abs diff {np.abs(got - exp).max()}"
+        else:
+            assert np.allclose(got, exp, rtol=1e-5, atol=1e-5)
+    # sorted (key, value) arrays bit-exact vs the oracle's stable sort
+    L = frame.layout
+    okeys = fwd.point_in_camera_sort_key
+    packed = ((okeys >> 32) << L.depth_bits) | (okeys & 0xFFFFFFFF)
+    assert (n(frame.sorted_keys) == packed).all()
+    assert (n(frame.point_offset_with_sort_key) == fwd.point_offset_with_sort_key).all()
+    assert (n(frame.tile_points_start) == fwd.tile_points_start).all()
+    assert (n(frame.tile_points_end) == fwd.tile_points_end).all()
+
+
+@pytest.mark.parametrize("exact_exp", [True, False])
+@pytest.mark.parametrize("force_key64", [False, True])
+def test_c1_forward_backward_vs_oracle(exact_exp, force_key64):
+    """BASELINE config 1 (correctness gate): 1e4 Gaussians, 256x256, SH deg 0."""
+    scene = make_scene(**CONFIGS["C1"])
+    o, fwd, feats_n = oracle_forward(scene)
+    sc = cuda_scene(scene, requires_grad=True)
+    captured = {}
+    op = make_op(hook=lambda h: captured.setdefault("hook", h), exact_exp=exact_exp, force_key64=force_key64)
+    image, depth, count = run_forward(op, sc, band=0)
+    frame = op.last_frame
+    assert frame.layout.key_bytes == (8 if force_key64 else 4)
+    _check_stages(frame, fwd)
+    # in-place quaternion normalisation (GPCR:264-266)
+    assert np.array_equal(n(sc.point_cloud_features), feats_n)
+    # forward image: 1e-4 abs
+    assert np.abs(n(image) - fwd.image).max() <= 1e-4
+    assert np.abs(n(depth) - fwd.depth).max() <= 1e-3
+    assert count_above(n(count), fwd.pixel_valid_point_count, 0) == 0
+    g = torch.Generator().manual_seed(1)
+    grad_image = torch.randn(image.shape, generator=g, dtype=torch.float32)
+    image.backward(grad_image.cuda())
+    bwd = oracle_backward(o, fwd, scene, feats_n, grad_image.numpy(), 0)
+    assert rel_err(n(sc.point_cloud.grad), bwd.grad_pointcloud) <= 1e-3
+    gf = n(sc.point_cloud_features.grad)
+    for sl in (slice(0, 4), slice(4, 7), slice(7, 8), slice(8, 56)):
+        assert rel_err(gf[:, sl], bwd.grad_pointcloud_features[:, sl]) <= 1e-3
+    h = captured["hook"]
+    assert (n(h.point_id_in_camera_list) == bwd.point_id_in_camera_list).all()
+    assert rel_err(n(h.grad_point_in_camera), bwd.grad_point_in_camera) <= 1e-3
+    assert rel_err(n(h.grad_pointfeatures_in_camera), bwd.grad_pointfeatures_in_camera) <= 1e-3
+    assert rel_err(n(h.grad_viewspace), bwd.grad_viewspace) <= 1e-3
+    assert rel_err(n(h.magnitude_grad_viewspace), bwd.magnitude_grad_viewspace) <= 1e-3
+    assert np.abs(n(h.magnitude_grad_viewspace_on_image) - bwd.magnitude_grad_viewspace_on_image).max() <= \
+        1e-3 * max(1.0, np.abs(bwd.magnitude_grad_viewspace_on_image).max())
+    assert (n(h.num_overlap_tiles) == bwd.num_overlap_tiles).all()
+    assert (n(h.num_affected_pixels) == bwd.num_affected_pixels).all()
+    assert np.array_equal(n(h.point_depth), bwd.point_depth)
+    assert np.array_equal(n(h.point_uv_in_camera), bwd.point_uv_in_camera)
+    assert h.grad_point_in_camera.shape[1] == 3 and h.grad_pointfeatures_in_camera.shape[1] == 56 \
+        and h.grad_viewspace.shape[1] == 2  # reference test_backward_hook widths
+
+
+@pytest.mark.parametrize("seed,band,scale", [(21, 3, 100.0), (22, 1, 10.0), (23, 2, 2.0)])
+def test_small_scene_sh3_vs_oracle(seed, band, scale):
+    """SH deg 3, rotated camera, un-normalised q, invalid slots, saturation, coarse depth keys (ties)."""
+    scene = _small_scene(seed)
+    o, fwd, feats_n = oracle_forward(scene, depth_to_sort_key_scale=scale, near_plane=0.4)
+    sc = cuda_scene(scene, requires_grad=True)
+    op = make_op(exact_exp=True, depth_to_sort_key_scale=scale, near_plane=0.4)
+    image, depth, count = run_forward(op, sc, band=band)
+    _check_stages(op.last_frame, fwd)
+    assert fwd.pixel_valid_point_count.max() >= 8
+    assert np.abs(n(image) - fwd.image).max() <= 1e-4
+    assert (n(count) == fwd.pixel_valid_point_count).all()
+    g = torch.Generator().manual_seed(seed)
+    grad_image = torch.randn(image.shape, generator=g, dtype=torch.float32)
+    image.backward(grad_image.cuda())
+    bwd = oracle_backward(o, fwd, scene, feats_n, grad_image.numpy(), band)
+    assert rel_err(n(sc.point_cloud.grad), bwd.grad_pointcloud) <= 1e-3
+    gf = n(sc.point_cloud_features.grad)
+    for sl in (slice(0, 4), slice(4, 7), slice(7, 8), slice(8, 56)):
+        assert rel_err(gf[:, sl], bwd.grad_pointcloud_features[:, sl]) <= 1e-3
+
+
+def test_two_points_scene_golden():
+    """Scene of reference tests/GaussianPointCloudRasterisation_test.py:152-205, hand-derived values
+     through the CUDA path."""
+    dev = "cuda"
+    xyz = torch.tensor([[0.0, 0.0, 1.0], [0.0, 0.0, 2.0]], device=dev)
+    feat = torch.zeros((2, 56), device=dev)
+    feat[:, 3] = 1.0
+    feat[0, 4:7] = 1.0
+    feat[1, 4:7] = 4.0
+    feat[:, 8] = 5.0
+    feat[:, 24] = 1.0
+    feat[:, 40] = 1.0
+    from taichi_3d_gaussian_splatting_b200 import CameraInfo
+    from gpu_helpers import Input
+    mask = torch.tensor([1, 0], dtype=torch.int8, device=dev)
+    op = make_op(near_plane=0.0, far_plane=10.0, exact_exp=True)
+    image, depth, count = op(Input(
+        point_cloud=xyz, point_cloud_features=feat, point_object_id=torch.zeros(2, dtype=torch.int32, device=dev),
+        point_invalid_mask=mask,
+        camera_info=CameraInfo(torch.tensor([[1., 0, 8], [0, 1, 8], [0, 0, 1]], device=dev), 16, 16, 0),
+        q_pointcloud_camera=torch.tensor([[0., 0, 0, 1]], device=dev),
+        t_pointcloud_camera=torch.zeros((1, 3), device=dev), color_max_sh_band=0))
+    img = n(image)
+    assert np.allclose(img[7, 7], [0.40162393, 0.28481966, 0.28481966], atol=2e-6)
+    for (v, u) in [(0, 0), (0, 15), (15, 15)]:
+        assert np.allclose(img[v, u], [0.37256175, 0.26420963, 0.26420963], atol=2e-6)
+    assert np.allclose(n(depth), 2.0, atol=1e-5)
+    assert (n(count) == 1).all()
+    assert op.last_frame.num_points_in_camera == 1 and op.last_frame.num_keys == 1
+
+
+def test_multi_object_poses_vs_oracle():
+    scene = _small_scene(31, npts=2000)
+    scene.point_object_id[1::2] = 1
+    q = torch.tensor([[0.0, 0.03, 0.0, 1.0], [0.02, -0.05, 0.01, 0.99]])
+    scene.q_pointcloud_camera = q / q.norm(dim=-1, keepdim=True)
+    scene.t_pointcloud_camera = torch.tensor([[0.0, 0.0, 0.0], [0.3, -0.1, -0.5]])
+    o, fwd, feats_n = oracle_forward(scene)
+    sc = cuda_scene(scene, requires_grad=True)
+    op = make_op(exact_exp=True)
+    image, _, _ = run_forward(op, sc, band=3)
+    _check_stages(op.last_frame, fwd)
+    assert np.abs(n(image) - fwd.image).max() <= 1e-4
+    grad_image = torch.ones(image.shape)
+    image.backward(grad_image.cuda())
+    bwd = oracle_backward(o, fwd, scene, feats_n, grad_image.numpy(), 3)
+    assert rel_err(n(sc.point_cloud.grad), bwd.grad_pointcloud) <= 1e-3
+    assert rel_err(n(sc.point_cloud_features.grad), bwd.grad_pointcloud_features) <= 1e-3
+
+
+def test_empty_and_degenerate_frames():
+    """K == 0 (the reference returns uninitialised memory, GPCR:967-997; we define zeros), all-invalid
+    scene, and no gradient when nothing requires grad (GPCR:1028)."""
+    scene = _small_scene(41, npts=500)
+    scene.point_invalid_mask[:] = 1
+    sc = cuda_scene(scene, requires_grad=True)
+    op = make_op()
+    image, depth, count = run_forward(op, sc)
+    assert op.last_frame.num_points_in_camera == 0 and op.last_frame.num_keys == 0
+    assert float(image.abs().max()) == 0.0 and float(depth.abs().max()) == 0.0 and int(count.max()) == 0
+    image.sum().backward()
+    assert float(sc.point_cloud.grad.abs().max()) == 0.0
+    assert float(sc.point_cloud_features.grad.abs().max()) == 0.0
+    # everything behind the camera
+    scene2 = _small_scene(42, npts=500)
+    scene2.point_cloud[:, 2] = -scene2.point_cloud[:, 2].abs() - 1.0
+    image2, _, _ = run_forward(make_op(), cuda_scene(scene2))
+    assert float(image2.abs().max()) == 0.0
+    # no requires_grad -> autograd never calls backward; forward under no_grad works
+    with torch.no_grad():
+        image3, _, _ = run_forward(make_op(), cuda_scene(_small_scene(43)))
+    assert not image3.requires_grad
+
+
+def test_key_capacity_overflow_regrows():
+    scene = _small_scene(51)
+    _, fwd, _ = oracle_forward(scene)
+    op = make_op(initial_key_capacity=64, exact_exp=True)
+    image, _, _ = run_forward(op, cuda_scene(scene))
+    assert op.last_frame.key_capacity >= fwd.point_offset_with_sort_key.shape[0] > 64
+    _check_stages(op.last_frame, fwd)
+    assert np.abs(n(image) - fwd.image).max() <= 1e-4
+
+
+def test_rgb_only_matches_full():
+    scene = _small_scene(61)
+    full, _, _ = run_forward(make_op(exact_exp=True), cuda_scene(scene))
+    rgb, depth, count = run_forward(make_op(exact_exp=True, rgb_only=True), cuda_scene(scene))
+    assert torch.equal(full, rgb)
+    assert float(depth.abs().max()) == 0.0 and int(count.max()) == 0
+
+
+def test_requires_cuda_tensors_and_alignment():
+    scene = _small_scene(71, npts=100)
+    op = make_op()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        run_forward(op, scene)  # CPU tensors: there is no fallback
+    from taichi_3d_gaussian_splatting_b200 import CameraInfo
+    sc = cuda_scene(scene)
+    sc.camera_info = CameraInfo(sc.camera_info.camera_intrinsics, 60, 96, 0)
+    with pytest.raises(AssertionError):
+        run_forward(op, sc)  # H % 16 != 0 (GPCR:1193-1194)
+
+
+def test_find_tile_start_and_end_known_answer(golden):
+    """reference tests/GaussianPointCloudRasterisation_test.py:18-51 through the CUDA kernel."""
+    from taichi_3d_gaussian_splatting_b200 import find_tile_start_and_end
+    g = golden["tile_ranges"]
+    keys = torch.tensor(g["keys"], dtype=torch.int64, device="cuda")
+    start = torch.zeros(g["num_tiles"], dtype=torch.int32, device="cuda")
+    end = torch.zeros(g["num_tiles"], dtype=torch.int32, device="cuda")
+    find_tile_start_and_end(keys, start, end)
+    assert start.tolist() == g["start"] and end.tolist() == g["end"]
