@@ -45,6 +45,9 @@ enum {
 /* flags */
 #define GSB_FLAG_EXACT_EXP 1u    /* blend kernels use expf instead of ex2.approx */
 #define GSB_FLAG_FORCE_KEY64 2u  /* always sort (tile<<32 | depth) 64-bit keys like GPCR:158-170 */
+#define GSB_FLAG_Q_ALREADY_NORMALISED 4u /* forward only: take q as stored and do not rewrite it.  Used when a
+                                            frame is re-run after a key-capacity overflow, so that the second
+                                            pass is bit-identical to the first (normalising twice is not). */
 
 /* Byte offsets of the sub-buffers inside the caller-owned workspace blob.  Filled by
  * gsb200_workspace_layout(); the Python shim uses it to expose saved-for-backward tensors as views. */

@@ -298,6 +298,7 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
                 last_effective = torch.empty((H, W), dtype=torch.int32, device=device)
                 valid_count = torch.empty((H, W), dtype=torch.int32, device=device)
             pinned, event = _PinnedCounters.get(device)
+            retry_flag = 0
             while True:
                 key_capacity = self._key_capacity
                 layout = _lib.workspace_layout(N, n_obj, key_capacity, H, W, cfg.far_plane,
@@ -310,7 +311,7 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
                     camera_intrinsics=_ptr(K), camera_height=H, camera_width=W,
                     near_plane=cfg.near_plane, far_plane=cfg.far_plane,
                     depth_to_sort_key_scale=cfg.depth_to_sort_key_scale, rgb_only=1 if cfg.rgb_only else 0,
-                    flags=self._flags, workspace=_ptr(ws), workspace_bytes=layout.total_bytes,
+                    flags=self._flags | retry_flag, workspace=_ptr(ws), workspace_bytes=layout.total_bytes,
                     key_capacity=key_capacity, rasterized_image=_ptr(image), rasterized_depth=_ptr(depth),
                     pixel_accumulated_alpha=_ptr(acc_alpha),
                     pixel_offset_of_last_effective_point=_ptr(last_effective),
@@ -326,8 +327,10 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
                 frame.num_keys = int(pinned[1])
                 if int(pinned[2]) == 0:
                     break
-                # more (tile, splat) pairs than capacity: grow and redo the frame
+                # more (tile, splat) pairs than capacity: grow and redo the frame.  The first pass already
+                # normalised the quaternions in place; the re-run must not normalise them a second time.
                 self._key_capacity = int(frame.num_keys * 1.25) + 4096
+                retry_flag = _lib.GSB_FLAG_Q_ALREADY_NORMALISED
         self.last_frame = frame
         return (image, depth, acc_alpha, last_effective, valid_count), frame, {"camera_intrinsics": K}
 

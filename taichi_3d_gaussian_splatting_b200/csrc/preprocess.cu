@@ -112,6 +112,7 @@ struct PreParams {
     int W, H;
     float near_plane, far_plane, depth_scale;
     int depth_bits;
+    int skip_q_normalise;
     long long key_capacity;
     int num_blocks;
     // outputs
@@ -190,10 +191,12 @@ preprocess_kernel(const PreParams p) {
                 f[4 * (k - 1) + 2] = t4.z; f[4 * (k - 1) + 3] = t4.w;
             }
             // GPCR:196-205: q <- q / |q| (invlen * q), written back in place
-            float qn = sqrtf(((qv.x * qv.x + qv.y * qv.y) + qv.z * qv.z) + qv.w * qv.w);
-            float inv = 1.0f / qn;
-            qv.x = inv * qv.x; qv.y = inv * qv.y; qv.z = inv * qv.z; qv.w = inv * qv.w;
-            frow[0] = qv;
+            if (!p.skip_q_normalise) {
+                float qn = sqrtf(((qv.x * qv.x + qv.y * qv.y) + qv.z * qv.z) + qv.w * qv.w);
+                float inv = 1.0f / qn;
+                qv.x = inv * qv.x; qv.y = inv * qv.y; qv.z = inv * qv.z; qv.w = inv * qv.w;
+                frow[0] = qv;
+            }
             // GP3D:161-191: Sigma' = J W R S S^T R^T W^T J^T
             float J[6];
             const float fx = Kc[0], fy = Kc[4];
@@ -382,6 +385,7 @@ int launch_preprocess(const GsbForwardArgs &a, const Workspace &ws, cudaStream_t
     p.far_plane = a.far_plane;
     p.depth_scale = a.depth_to_sort_key_scale;
     p.depth_bits = L.depth_bits;
+    p.skip_q_normalise = (a.flags & GSB_FLAG_Q_ALREADY_NORMALISED) ? 1 : 0;
     p.key_capacity = a.key_capacity;
     p.num_blocks = L.scan_blocks;
     p.counters = ws.counters;
