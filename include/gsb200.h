@@ -122,7 +122,7 @@ typedef struct GsbBackwardArgs {
     const float *pixel_accumulated_alpha;
     const int32_t *pixel_offset_of_last_effective_point;
     float *accum;                       /* (>=M,12) zero-initialised by this call:
-                                           guv.x guv.y gcov00 gcov01 gcov11 gr gg gb glogit magnitude n_pixels(i32) pad */
+                                           guv.x guv.y gcov00 gcov01 gcov11 gr gg gb glogit magnitude n_pixels(as f32) pad */
     int64_t accum_rows;
     float *grad_pointcloud;             /* (N,3) fully written (zeros for points outside the frustum) */
     float *grad_pointcloud_features;    /* (N,56) fully written, band-masked and factor-scaled */

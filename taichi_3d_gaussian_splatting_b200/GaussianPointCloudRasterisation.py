@@ -386,7 +386,7 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
                     magnitude_grad_viewspace=acc[:, 9].contiguous(),
                     magnitude_grad_viewspace_on_image=magnitude_on_image,
                     num_overlap_tiles=frame.num_overlap_tiles,
-                    num_affected_pixels=acc.view(torch.int32)[:, 10].contiguous(),
+                    num_affected_pixels=acc[:, 10].round().to(torch.int32),
                     point_uv_in_camera=frame.point_uv.contiguous(),
                     point_depth=frame.point_in_camera[:, 2],
                 ))

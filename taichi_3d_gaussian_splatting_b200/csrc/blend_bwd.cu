@@ -3,8 +3,8 @@
 // Kernel A (loop A, GPCR:531-705): one CTA per tile replays its splat list back-to-front.  The
 // reference issues 11 global atomics per contributing (pixel, splat); here the 11 per-splat partials
 // (d/duv x2, d/dcov x3, d/dcolour x3, d/dlogit, |d/duv|, pixel count) are reduced across the warp
-// with a transposing butterfly (16 shuffles for all of them), then across the 8 warps in a
-// shared-memory accumulator, and flushed with ONE atomic row per (tile, splat).
+// with a transposing butterfly (16 shuffles for all of them) and flushed with ONE 11-lane RED.ADD.F32
+// per (warp patch, splat) -- per-warp culling (common.cuh) leaves ~2 of the 8 patches per (tile, splat).
 // Kernel B (loop B, GPCR:708-772 + GPCR:1102-1125, 1167-1182): per in-frustum point chain rule to
 // xyz / q / s / SH with the SH-band masking and the constant gradient factors fused in.
 #include "common.cuh"
@@ -24,9 +24,19 @@ struct BlendBwdParams {
     float *mag_image;  // (H,W,2)
 };
 
-__device__ __forceinline__ float fast_exp_b(float x) {
+__device__ __forceinline__ float ex2_approx_b(float x) {
     float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, <= 1 ulp
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {  // MUFU.RSQ based, ~1 ulp
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 
@@ -69,7 +79,6 @@ __device__ __forceinline__ void warp_transpose_reduce16(float (&v)[16], int lane
     v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-constexpr int ACC_STRIDE = 13;  // odd row stride: conflict-free per-row and per-column access
 
 template <bool EXACT_EXP>
 __global__ void __launch_bounds__(GSB_TILE_PIXELS)
@@ -78,7 +87,7 @@ blend_backward_kernel(const BlendBwdParams p) {
     __shared__ float4 s_r1[GSB_TILE_PIXELS];
     __shared__ float4 s_r2[GSB_TILE_PIXELS];
     __shared__ int s_off[GSB_TILE_PIXELS];
-    __shared__ float s_acc[GSB_TILE_PIXELS * ACC_STRIDE];
+    __shared__ unsigned int s_bits[8][8];  // [consumer warp patch][loader warp]
     __shared__ int s_max_last;
 
     const int tile = blockIdx.x;
@@ -87,6 +96,7 @@ blend_backward_kernel(const BlendBwdParams p) {
     const int pu = tu * GSB_TILE_WIDTH + (warp & 1) * 8 + (lane & 7);
     const int pv = tv * GSB_TILE_HEIGHT + (warp >> 1) * 4 + (lane >> 3);
     const float px = (float)pu + 0.5f, py = (float)pv + 0.5f;
+    const float tile_x0 = (float)(tu * GSB_TILE_WIDTH), tile_y0 = (float)(tv * GSB_TILE_HEIGHT);
     const size_t pix = (size_t)pv * p.W + pu;
     const int start = p.tile_start[tile];
 
@@ -96,91 +106,104 @@ blend_backward_kernel(const BlendBwdParams p) {
     const float g0 = p.grad_image[3 * pix], g1 = p.grad_image[3 * pix + 1], g2 = p.grad_image[3 * pix + 2];
     float mag0 = 0.0f, mag1 = 0.0f;
 
+    // deepest effective splat of this warp's patch and of the whole tile (GPCR:609-610: nothing at or
+    // behind a pixel's last effective offset contributes to it)
+    int warp_last = last;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, d));
     if (tid == 0) s_max_last = start;
     __syncthreads();
-    atomicMax(&s_max_last, last);
+    if (lane == 0) atomicMax(&s_max_last, warp_last);
     __syncthreads();
-    // nothing behind the deepest effective splat of the tile contributes (GPCR:609-610)
     const int end = min(p.tile_end[tile], s_max_last);
 
     for (int block_end = end; block_end > start; block_end -= GSB_TILE_PIXELS) {
         const int block_start = max(block_end - GSB_TILE_PIXELS, start);
         const int nb = block_end - block_start;
-        __syncthreads();  // previous batch fully flushed before smem is reused
+        __syncthreads();  // every warp is done with the previous batch before smem is reused
         {
             const int idx = block_end - 1 - tid;  // element j <-> sorted index block_end-1-j
+            unsigned int mask = 0;
             if (idx >= block_start) {
                 const int o = __ldg(&p.sorted_vals[idx]);
                 const float4 *rec = p.records + 3 * (size_t)o;
-                s_r0[tid] = __ldg(rec);
-                s_r1[tid] = __ldg(rec + 1);
+                const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
+                s_r0[tid] = r0;
+                s_r1[tid] = r1;
                 s_r2[tid] = __ldg(rec + 2);
                 s_off[tid] = o;
+                mask = splat_patch_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y * r1.z, tile_x0, tile_y0);
             }
 #pragma unroll
-            for (int k = 0; k < 11; ++k) s_acc[tid * ACC_STRIDE + k] = 0.0f;
+            for (int w = 0; w < 8; ++w) {
+                const unsigned int bits = __ballot_sync(0xffffffffu, (mask >> w) & 1u);
+                if (lane == 0) s_bits[w][warp] = bits;
+            }
         }
         __syncthreads();
-        for (int j = 0; j < nb; ++j) {
-            const int idx = block_end - 1 - j;
-            float v[16];
+        if (block_start < warp_last) {  // otherwise every splat of this batch is behind the whole patch
+#pragma unroll 1
+            for (int lw = 0; lw < 8; ++lw) {
+                unsigned int bits = s_bits[warp][lw];
+                while (bits) {
+                    const int j = lw * 32 + __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const int idx = block_end - 1 - j;
+                    if (idx >= warp_last) continue;  // warp-uniform
+                    float v[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = 0.0f;
-            bool contributes = false;
-            if (idx < last) {
-                const float4 r0 = s_r0[j];  // u v a b
-                const float4 r1 = s_r1[j];  // c rescale opacity depth
-                const float d0 = px - r0.x, d1 = py - r0.y;
-                const float q0 = r0.z * d0 + r0.w * d1;  // conic @ d   (UT:337-339)
-                const float q1 = r0.w * d0 + r1.x * d1;
-                const float power = -0.5f * (d0 * q0 + d1 * q1);
-                const float gp = (EXACT_EXP ? expf(power) : fast_exp_b(power)) * r1.y;
-                const float opa = r1.z;
-                const float prod_alpha = gp * opa;
-                if (prod_alpha >= 1.0f / 255.0f) {  // GPCR:634
-                    contributes = true;
-                    const float alpha = fminf(prod_alpha, 0.99f);
-                    const float4 r2 = s_r2[j];
-                    const float inv = 1.0f / (1.0f - alpha);
-                    T = T * inv;                               // GPCR:643
-                    const float aT = alpha * T;                // d pixel / d colour (GPCR:649)
-                    const float a_grad = (r2.x * T - w0 * inv) * g0 + (r2.y * T - w1 * inv) * g1 +
-                                         (r2.z * T - w2 * inv) * g2;  // GPCR:653-657
-                    w0 += r2.x * aT;
-                    w1 += r2.y * aT;
-                    w2 += r2.z * aT;
-                    const float g_grad = a_grad * opa;         // d/d gaussian (GPCR:662)
-                    const float vs0 = g_grad * gp * q0, vs1 = g_grad * gp * q1;  // view-space grad
-                    mag0 += fabsf(vs0);
-                    mag1 += fabsf(vs1);
-                    const float hc = 0.5f * g_grad * gp;       // UT:345: 0.5 p (S^-1 d d^T S^-1)
-                    v[0] = vs0;
-                    v[1] = vs1;
-                    v[2] = hc * q0 * q0;
-                    v[3] = hc * q0 * q1;
-                    v[4] = hc * q1 * q1;
-                    v[5] = aT * g0;
-                    v[6] = aT * g1;
-                    v[7] = aT * g2;
-                    v[8] = a_grad * gp * (1.0f - opa) * opa;   // d/d logit (GPCR:658-661)
-                    v[9] = sqrtf(vs0 * vs0 + vs1 * vs1);       // GPCR:691-694
-                    v[10] = 1.0f;                              // affected-pixel count
+                    for (int k = 0; k < 16; ++k) v[k] = 0.0f;
+                    bool contributes = false;
+                    if (idx < last) {
+                        const float4 r0 = s_r0[j];  // u v a b
+                        const float4 r1 = s_r1[j];  // c rescale opacity depth
+                        const float d0 = px - r0.x, d1 = py - r0.y;
+                        const float q0 = r0.z * d0 + r0.w * d1;  // conic @ d   (UT:337-339)
+                        const float q1 = r0.w * d0 + r1.x * d1;
+                        float gp;
+                        if (EXACT_EXP) gp = expf(-0.5f * (d0 * q0 + d1 * q1)) * r1.y;  // UT:340-342
+                        else gp = ex2_approx_b(-0.72134752044448170368f * (d0 * q0 + d1 * q1)) * r1.y;
+                        const float opa = r1.z;
+                        const float prod_alpha = gp * opa;
+                        if (prod_alpha >= 1.0f / 255.0f) {  // GPCR:634
+                            contributes = true;
+                            const float alpha = fminf(prod_alpha, 0.99f);
+                            const float4 r2 = s_r2[j];
+                            const float inv = EXACT_EXP ? 1.0f / (1.0f - alpha) : rcp_approx(1.0f - alpha);
+                            T = T * inv;                               // GPCR:643
+                            const float aT = alpha * T;                // d pixel / d colour (GPCR:649)
+                            const float a_grad = (r2.x * T - w0 * inv) * g0 + (r2.y * T - w1 * inv) * g1 +
+                                                 (r2.z * T - w2 * inv) * g2;  // GPCR:653-657
+                            w0 += r2.x * aT;
+                            w1 += r2.y * aT;
+                            w2 += r2.z * aT;
+                            const float g_grad = a_grad * opa;         // d/d gaussian (GPCR:662)
+                            const float vs0 = g_grad * gp * q0, vs1 = g_grad * gp * q1;  // view-space grad
+                            mag0 += fabsf(vs0);
+                            mag1 += fabsf(vs1);
+                            const float hc = 0.5f * g_grad * gp;       // UT:345: 0.5 p (S^-1 d d^T S^-1)
+                            v[0] = vs0;
+                            v[1] = vs1;
+                            v[2] = hc * q0 * q0;
+                            v[3] = hc * q0 * q1;
+                            v[4] = hc * q1 * q1;
+                            v[5] = aT * g0;
+                            v[6] = aT * g1;
+                            v[7] = aT * g2;
+                            v[8] = a_grad * gp * (1.0f - opa) * opa;   // d/d logit (GPCR:658-661)
+                            v[9] = EXACT_EXP ? sqrtf(vs0 * vs0 + vs1 * vs1)
+                                             : sqrt_approx(vs0 * vs0 + vs1 * vs1);  // GPCR:691-694
+                            v[10] = 1.0f;                              // affected-pixel count
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, contributes)) {
+                        // 11 partials of this (warp, splat) -> 11 lanes -> one RED.ADD.F32 row update
+                        warp_transpose_reduce16(v, lane);
+                        const int k = (lane >> 1) & 15;
+                        if ((lane & 1) == 0 && k < 11)
+                            atomicAdd(p.accum + (size_t)s_off[j] * GSB_ACCUM_FLOATS + k, v[0]);
+                    }
                 }
-            }
-            if (__any_sync(0xffffffffu, contributes)) {
-                warp_transpose_reduce16(v, lane);
-                const int k = (lane >> 1) & 15;
-                if ((lane & 1) == 0 && k < 11) atomicAdd(&s_acc[j * ACC_STRIDE + k], v[0]);
-            }
-        }
-        __syncthreads();
-        if (tid < nb) {
-            const float cntf = s_acc[tid * ACC_STRIDE + 10];
-            if (cntf > 0.0f) {
-                float *row = p.accum + (size_t)s_off[tid] * GSB_ACCUM_FLOATS;
-#pragma unroll
-                for (int k = 0; k < 10; ++k) atomicAdd(row + k, s_acc[tid * ACC_STRIDE + k]);
-                atomicAdd(reinterpret_cast<int *>(row + 10), (int)(cntf + 0.5f));
             }
         }
     }

@@ -25,19 +25,20 @@ struct BlendFwdParams {
     int *valid_count;
 };
 
-__device__ __forceinline__ float fast_exp(float x) {
-    // ex2.approx(x * log2e) -> one FMUL + one MUFU.EX2; rel. error ~2^-21 for the arguments met here
+__device__ __forceinline__ float ex2_approx(float x) {
+    // one MUFU.EX2; rel. error ~2^-22
     float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 
 template <bool RGB_ONLY, bool EXACT_EXP>
-__global__ void __launch_bounds__(GSB_TILE_PIXELS)
+__global__ void __launch_bounds__(GSB_TILE_PIXELS, 5)
 blend_forward_kernel(const BlendFwdParams p) {
     __shared__ float4 s_r0[GSB_TILE_PIXELS];
     __shared__ float4 s_r1[GSB_TILE_PIXELS];
     __shared__ float4 s_r2[GSB_TILE_PIXELS];
+    __shared__ unsigned int s_bits[8][8];  // [consumer warp patch][loader warp] -> splats that can reach it
 
     const int tile = blockIdx.x;
     const int tu = tile % p.tiles_x, tv = tile / p.tiles_x;
@@ -46,6 +47,7 @@ blend_forward_kernel(const BlendFwdParams p) {
     const int pu = tu * GSB_TILE_WIDTH + (warp & 1) * 8 + (lane & 7);
     const int pv = tv * GSB_TILE_HEIGHT + (warp >> 1) * 4 + (lane >> 3);
     const float px = (float)pu + 0.5f, py = (float)pv + 0.5f;  // GPCR:442 pixel centre
+    const float tile_x0 = (float)(tu * GSB_TILE_WIDTH), tile_y0 = (float)(tv * GSB_TILE_HEIGHT);
     const int start = p.tile_start[tile], end = p.tile_end[tile];
 
     float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, D = 0.0f, Wt = 0.0f;
@@ -55,29 +57,54 @@ blend_forward_kernel(const BlendFwdParams p) {
     for (int base = start; base < end; base += GSB_TILE_PIXELS) {
         if (__syncthreads_and(done)) break;  // barrier (smem reuse) + tile-level early exit
         const int idx = base + tid;
+        unsigned int mask = 0;
         if (idx < end) {
             const int o = __ldg(&p.sorted_vals[idx]);
             const float4 *rec = p.records + 3 * (size_t)o;
-            s_r0[tid] = __ldg(rec);
-            s_r1[tid] = __ldg(rec + 1);
+            const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
+            if (EXACT_EXP) {
+                s_r0[tid] = r0;
+                s_r1[tid] = r1;
+            } else {
+                // fast path: fold -1/2, log2(e) and rescale*opacity into the staged record, so that the
+                // inner loop is  alpha = ex2(A dx^2 + C dy^2 + B dx dy) * ro
+                constexpr float L2E = 1.4426950408889634f;
+                s_r0[tid] = make_float4(r0.x, r0.y, -0.5f * L2E * r0.z, -L2E * r0.w);
+                s_r1[tid] = make_float4(-0.5f * L2E * r1.x, r1.y * r1.z, 0.0f, r1.w);
+            }
             s_r2[tid] = __ldg(rec + 2);
+            mask = splat_patch_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y * r1.z, tile_x0, tile_y0);
+        }
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const unsigned int bits = __ballot_sync(0xffffffffu, (mask >> w) & 1u);
+            if (lane == 0) s_bits[w][warp] = bits;
         }
         __syncthreads();
-        const int nb = min(GSB_TILE_PIXELS, end - base);
-        if (!done) {
-            for (int j = 0; j < nb; ++j) {
+        if (__all_sync(0xffffffffu, done)) continue;  // whole patch saturated: only help with loads
+#pragma unroll 1
+        for (int lw = 0; lw < 8; ++lw) {
+            unsigned int bits = s_bits[warp][lw];
+            while (bits) {
+                const int j = lw * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (done) continue;
                 const float4 r0 = s_r0[j];  // u v a b
                 const float4 r1 = s_r1[j];  // c rescale opacity depth
                 const float dx = px - r0.x, dy = py - r0.y;
-                const float power = -0.5f * (dx * dx * r0.z + dy * dy * r1.x) - dx * dy * r0.w;
-                const float g = (EXACT_EXP ? expf(power) : fast_exp(power)) * r1.y;
-                float alpha = g * r1.z;
+                float alpha;
+                if (EXACT_EXP) {  // the reference's op order (UT:275-284)
+                    const float power = -0.5f * (dx * dx * r0.z + dy * dy * r1.x) - dx * dy * r0.w;
+                    alpha = expf(power) * r1.y * r1.z;
+                } else {
+                    alpha = ex2_approx(dx * (r0.z * dx + r0.w * dy) + r1.x * dy * dy) * r1.y;
+                }
                 if (alpha < 1.0f / 255.0f) continue;   // GPCR:451
                 alpha = fminf(alpha, 0.99f);           // GPCR:453
                 const float nT = T * (1.0f - alpha);
                 if (nT < 0.0001f) {                     // GPCR:457-460: saturated, splat not blended
                     done = true;
-                    break;
+                    continue;
                 }
                 last = base + j + 1;
                 const float4 r2 = s_r2[j];

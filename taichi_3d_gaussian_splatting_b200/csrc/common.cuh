@@ -79,6 +79,53 @@ constexpr int SORT_ITEMS_PER_THREAD = 16;
 constexpr int SORT_TILE = SORT_BLOCK_THREADS * SORT_ITEMS_PER_THREAD;  // 4096 keys per CTA
 constexpr int SCAN_BLOCK_THREADS = 256;
 
+// ---- per-warp culling shared by the forward and backward blend kernels.
+// A CTA renders a 16x16 tile with 8 warps; warp w owns the 8x4 pixel patch at ((w & 1) * 8, (w >> 1) * 4).
+// When a batch of splats is staged into shared memory the loading thread computes, for its splat, which
+// of the 8 patches it can reach with alpha >= 1/255: alpha = exp(-q/2) * rescale * opacity >= 1/255 needs
+// q(d) = d^T conic d <= t2 = 2 ln(255 * rescale * opacity).  A patch is kept iff the minimum of the convex
+// quadratic q over the rectangle spanned by the patch's pixel centres is <= t2 (0 if the splat centre is
+// inside; otherwise attained on one of the four edges, a clamped 1-D minimisation each).  The test is
+// conservative (t2 padded by 0.2 % + 1e-3; degenerate or NaN conics keep every patch), so it never
+// changes a result -- it only lets a warp skip splats none of its 32 pixels can see.
+#ifdef __CUDACC__
+__device__ __forceinline__ float quad_form(float a, float b, float c, float dx, float dy) {
+    return a * dx * dx + 2.0f * b * dx * dy + c * dy * dy;
+}
+
+__device__ __forceinline__ unsigned int splat_patch_mask(float u, float v, float a, float b, float c,
+                                                         float rescale_times_opacity, float tile_x0,
+                                                         float tile_y0) {
+    const float ro = rescale_times_opacity;
+    if (!(ro == ro)) return 0xFFu;                 // NaN opacity: keep the reference behaviour
+    if (ro < (1.0f / 255.0f) * 0.999f) return 0u;  // can never reach 1/255 (exp(.) <= 1)
+    const float det = a * c - b * b;
+    if (!(det > 0.0f) || !(a > 0.0f) || !(c > 0.0f)) return 0xFFu;  // NaN / degenerate conic: keep all
+    const float t2 = (2.0f * __logf(fmaxf(255.0f * ro, 1.0f))) * 1.002f + 1e-3f;
+    const float inv_a = 1.0f / a, inv_c = 1.0f / c;
+    unsigned int m = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        // rectangle of the patch's pixel centres, relative to the splat centre
+        const float X0 = tile_x0 + 8.0f * (w & 1) + 0.5f - u, X1 = X0 + 7.0f;
+        const float Y0 = tile_y0 + 4.0f * (w >> 1) + 0.5f - v, Y1 = Y0 + 3.0f;
+        float best;
+        if (X0 <= 0.0f && X1 >= 0.0f && Y0 <= 0.0f && Y1 >= 0.0f) {
+            best = 0.0f;
+        } else {
+            const float ya = fminf(fmaxf(-b * X0 * inv_c, Y0), Y1);
+            const float yb = fminf(fmaxf(-b * X1 * inv_c, Y0), Y1);
+            const float xa = fminf(fmaxf(-b * Y0 * inv_a, X0), X1);
+            const float xb = fminf(fmaxf(-b * Y1 * inv_a, X0), X1);
+            best = fminf(fminf(quad_form(a, b, c, X0, ya), quad_form(a, b, c, X1, yb)),
+                         fminf(quad_form(a, b, c, xa, Y0), quad_form(a, b, c, xb, Y1)));
+        }
+        if (!(best > t2)) m |= 1u << w;  // NaN keeps the patch
+    }
+    return m;
+}
+#endif
+
 static inline int num_sms() {
     static int n = 0;
     if (n == 0) {
