@@ -83,10 +83,10 @@ __device__ __forceinline__ void warp_transpose_reduce16(float (&v)[16], int lane
 template <bool EXACT_EXP>
 __global__ void __launch_bounds__(GSB_TILE_PIXELS)
 blend_backward_kernel(const BlendBwdParams p) {
-    __shared__ float4 s_r0[GSB_TILE_PIXELS];
-    __shared__ float4 s_r1[GSB_TILE_PIXELS];
-    __shared__ float4 s_r2[GSB_TILE_PIXELS];
+    __shared__ float4 s_rec[3 * GSB_TILE_PIXELS];  // [0]: u v a b  [1]: c rescale opacity depth  [2]: r g b radius
     __shared__ int s_off[GSB_TILE_PIXELS];
+    float4 *const s_r0 = s_rec, *const s_r1 = s_rec + GSB_TILE_PIXELS, *const s_r2 = s_rec + 2 * GSB_TILE_PIXELS;
+    constexpr int PLANE = GSB_TILE_PIXELS * 16;
     __shared__ unsigned int s_bits[8][8];  // [consumer warp patch][loader warp]
     __shared__ int s_max_last;
 
@@ -105,6 +105,7 @@ blend_backward_kernel(const BlendBwdParams p) {
     float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f;
     const float g0 = p.grad_image[3 * pix], g1 = p.grad_image[3 * pix + 1], g2 = p.grad_image[3 * pix + 2];
     float mag0 = 0.0f, mag1 = 0.0f;
+    const unsigned int sa = smem_u32(s_rec);
 
     // deepest effective splat of this warp's patch and of the whole tile (GPCR:609-610: nothing at or
     // behind a pixel's last effective offset contributes to it)
@@ -155,8 +156,9 @@ blend_backward_kernel(const BlendBwdParams p) {
                     for (int k = 0; k < 16; ++k) v[k] = 0.0f;
                     bool contributes = false;
                     if (idx < last) {
-                        const float4 r0 = s_r0[j];  // u v a b
-                        const float4 r1 = s_r1[j];  // c rescale opacity depth
+                        const unsigned int ja = sa + j * 16;
+                        const float4 r0 = lds128<0>(ja);      // u v a b
+                        const float4 r1 = lds128<PLANE>(ja);  // c rescale opacity depth
                         const float d0 = px - r0.x, d1 = py - r0.y;
                         const float q0 = r0.z * d0 + r0.w * d1;  // conic @ d   (UT:337-339)
                         const float q1 = r0.w * d0 + r1.x * d1;
@@ -168,7 +170,7 @@ blend_backward_kernel(const BlendBwdParams p) {
                         if (prod_alpha >= 1.0f / 255.0f) {  // GPCR:634
                             contributes = true;
                             const float alpha = fminf(prod_alpha, 0.99f);
-                            const float4 r2 = s_r2[j];
+                            const float4 r2 = lds128<2 * PLANE>(ja);
                             const float inv = EXACT_EXP ? 1.0f / (1.0f - alpha) : rcp_approx(1.0f - alpha);
                             T = T * inv;                               // GPCR:643
                             const float aT = alpha * T;                // d pixel / d colour (GPCR:649)

@@ -35,9 +35,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
 template <bool RGB_ONLY, bool EXACT_EXP>
 __global__ void __launch_bounds__(GSB_TILE_PIXELS, 5)
 blend_forward_kernel(const BlendFwdParams p) {
-    __shared__ float4 s_r0[GSB_TILE_PIXELS];
-    __shared__ float4 s_r1[GSB_TILE_PIXELS];
-    __shared__ float4 s_r2[GSB_TILE_PIXELS];
+    __shared__ float4 s_rec[3 * GSB_TILE_PIXELS];  // [0]: u v a b  [1]: c rescale opacity depth  [2]: r g b radius
+    float4 *const s_r0 = s_rec, *const s_r1 = s_rec + GSB_TILE_PIXELS, *const s_r2 = s_rec + 2 * GSB_TILE_PIXELS;
+    constexpr int PLANE = GSB_TILE_PIXELS * 16;  // bytes between the three record planes
     __shared__ unsigned int s_bits[8][8];  // [consumer warp patch][loader warp] -> splats that can reach it
 
     const int tile = blockIdx.x;
@@ -50,12 +50,14 @@ blend_forward_kernel(const BlendFwdParams p) {
     const float tile_x0 = (float)(tu * GSB_TILE_WIDTH), tile_y0 = (float)(tv * GSB_TILE_HEIGHT);
     const int start = p.tile_start[tile], end = p.tile_end[tile];
 
-    float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, D = 0.0f, Wt = 0.0f;
+    // T is the working transmittance: it is forced to 0 once the pixel has saturated, which makes every
+    // later splat fail the T(1-a) >= 1e-4 test without a separate flag; Tlive keeps the value to output.
+    float T = 1.0f, Tlive = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, D = 0.0f, Wt = 0.0f;
     int last = start, cnt = 0;
-    bool done = false;
+    const unsigned int sa = smem_u32(s_rec);
 
     for (int base = start; base < end; base += GSB_TILE_PIXELS) {
-        if (__syncthreads_and(done)) break;  // barrier (smem reuse) + tile-level early exit
+        if (__syncthreads_and(T == 0.0f)) break;  // barrier (smem reuse) + tile-level early exit
         const int idx = base + tid;
         unsigned int mask = 0;
         if (idx < end) {
@@ -81,16 +83,16 @@ blend_forward_kernel(const BlendFwdParams p) {
             if (lane == 0) s_bits[w][warp] = bits;
         }
         __syncthreads();
-        if (__all_sync(0xffffffffu, done)) continue;  // whole patch saturated: only help with loads
+        if (__all_sync(0xffffffffu, T == 0.0f)) continue;  // whole patch saturated: only help with loads
 #pragma unroll 1
         for (int lw = 0; lw < 8; ++lw) {
             unsigned int bits = s_bits[warp][lw];
             while (bits) {
                 const int j = lw * 32 + __ffs(bits) - 1;
                 bits &= bits - 1;
-                if (done) continue;
-                const float4 r0 = s_r0[j];  // u v a b
-                const float4 r1 = s_r1[j];  // c rescale opacity depth
+                const unsigned int ja = sa + j * 16;
+                const float4 r0 = lds128<0>(ja);      // u v a b      (fast: u v A B)
+                const float4 r1 = lds128<PLANE>(ja);  // c rescale opacity depth (fast: C ro - depth)
                 const float dx = px - r0.x, dy = py - r0.y;
                 float alpha;
                 if (EXACT_EXP) {  // the reference's op order (UT:275-284)
@@ -99,24 +101,34 @@ blend_forward_kernel(const BlendFwdParams p) {
                 } else {
                     alpha = ex2_approx(dx * (r0.z * dx + r0.w * dy) + r1.x * dy * dy) * r1.y;
                 }
-                if (alpha < 1.0f / 255.0f) continue;   // GPCR:451
-                alpha = fminf(alpha, 0.99f);           // GPCR:453
-                const float nT = T * (1.0f - alpha);
-                if (nT < 0.0001f) {                     // GPCR:457-460: saturated, splat not blended
-                    done = true;
-                    continue;
+                if (!(alpha < 1.0f / 255.0f)) {             // GPCR:451 (same comparison as the reference)
+                    alpha = fminf(alpha, 0.99f);            // GPCR:453
+                    const float nT = T * (1.0f - alpha);
+                    if (nT >= 0.0001f) {
+                        last = base + j + 1;
+                        const float4 r2 = lds128<2 * PLANE>(ja);
+                        const float wgt = alpha * T;
+                        if (EXACT_EXP) {
+                            C0 += r2.x * alpha * T;
+                            C1 += r2.y * alpha * T;
+                            C2 += r2.z * alpha * T;
+                            if (!RGB_ONLY) D += r1.w * alpha * T;
+                        } else {
+                            C0 = fmaf(r2.x, wgt, C0);
+                            C1 = fmaf(r2.y, wgt, C1);
+                            C2 = fmaf(r2.z, wgt, C2);
+                            if (!RGB_ONLY) D = fmaf(r1.w, wgt, D);
+                        }
+                        if (!RGB_ONLY) {
+                            Wt += wgt;
+                            cnt += 1;
+                        }
+                        T = nT;
+                        Tlive = nT;
+                    } else {
+                        T = 0.0f;  // GPCR:457-460: saturated; this splat is NOT blended
+                    }
                 }
-                last = base + j + 1;
-                const float4 r2 = s_r2[j];
-                C0 += r2.x * alpha * T;
-                C1 += r2.y * alpha * T;
-                C2 += r2.z * alpha * T;
-                if (!RGB_ONLY) {
-                    D += r1.w * alpha * T;
-                    Wt += alpha * T;
-                    cnt += 1;
-                }
-                T = nT;
             }
         }
     }
@@ -126,7 +138,7 @@ blend_forward_kernel(const BlendFwdParams p) {
     p.image[3 * pix + 2] = C2;
     if (!RGB_ONLY) {
         p.depth[pix] = D / fmaxf(Wt, 1e-6f);  // GPCR:479-480
-        p.acc_alpha[pix] = 1.0f - T;
+        p.acc_alpha[pix] = 1.0f - Tlive;
         p.last_effective[pix] = last;
         p.valid_count[pix] = cnt;
     }

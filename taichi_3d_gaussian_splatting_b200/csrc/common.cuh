@@ -89,6 +89,24 @@ constexpr int SCAN_BLOCK_THREADS = 256;
 // conservative (t2 padded by 0.2 % + 1e-3; degenerate or NaN conics keep every patch), so it never
 // changes a result -- it only lets a warp skip splats none of its 32 pixels can see.
 #ifdef __CUDACC__
+// 128-bit shared-memory load from an explicit shared-space address (keeps the address arithmetic of the
+// blend inner loops to one IMAD instead of a generic->shared window computation per access).
+template <int BYTE_OFFSET>
+__device__ __forceinline__ float4 lds128(unsigned int saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(saddr), "n"(BYTE_OFFSET));
+    return v;
+}
+// Shared-space address of a __shared__ object, made opaque so that the compiler keeps it in a register
+// instead of re-deriving it (S2R SR_CgaCtaId + LEA chain on sm_100) inside the inner loops.
+__device__ __forceinline__ unsigned int smem_u32(const void *p) {
+    unsigned int a = (unsigned int)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+
 __device__ __forceinline__ float quad_form(float a, float b, float c, float dx, float dy) {
     return a * dx * dx + 2.0f * b * dx * dy + c * dy * dy;
 }
