@@ -64,6 +64,7 @@ typedef struct GsbWorkspaceLayout {
     int64_t tile_end;          /* int32[T]  tile_points_end */
     int64_t poses;             /* float[num_objects][20]: T_camera_pointcloud 3x4, camera centre, pad */
     int64_t point_id;          /* int32[N]  point_id_in_camera_list (first M valid), GPCR:864 */
+    int64_t point_offset;      /* int32[N]  inverse map: in-camera offset of point id, -1 if outside the frustum */
     int64_t num_tiles;         /* int32[N]  num_overlap_tiles, GPCR:904-911 */
     int64_t records;           /* float[N][12]: u v a b | c rescale opacity depth | r g b radius */
     int64_t point_in_camera;   /* float[N][3] GPCR:877 */
@@ -99,6 +100,13 @@ typedef struct GsbForwardArgs {
     int32_t *pixel_offset_of_last_effective_point; /* (H,W) */
     int32_t *pixel_valid_point_count;   /* (H,W) */
     void *stream;
+    /* Optional early read-back: if both are non-NULL, gsb200_forward copies counters[0..3] = {M, K, overflow, -}
+     * to the PINNED HOST buffer right after the per-point stage and records the event (a cudaEvent_t) behind
+     * the copy; the remaining stages are enqueued regardless.  The host can wait on the event (it fires after
+     * ~the preprocess kernel, long before the frame ends), learn M and K and whether the key buffers overflowed,
+     * and return to its caller with the rest of the frame still in flight. */
+    int64_t *host_counters;
+    void *host_counters_event;
 } GsbForwardArgs;
 
 typedef struct GsbBackwardArgs {
@@ -124,7 +132,7 @@ typedef struct GsbBackwardArgs {
     float *accum;                       /* (>=M,12) zero-initialised by this call:
                                            guv.x guv.y gcov00 gcov01 gcov11 gr gg gb glogit magnitude n_pixels(as f32) pad */
     int64_t accum_rows;
-    float *grad_pointcloud;             /* (N,3) fully written (zeros for points outside the frustum) */
+    float *grad_pointcloud;             /* (N,3) fully written by the per-point kernel (zeros outside the frustum) */
     float *grad_pointcloud_features;    /* (N,56) fully written, band-masked and factor-scaled */
     float *magnitude_grad_viewspace_on_image; /* (H,W,2) */
     void *stream;

@@ -53,15 +53,23 @@ def _require(t: torch.Tensor, name: str, dtype: torch.dtype, shape_tail=None) ->
 
 
 class _PinnedCounters:
-    """One pinned int64[4] read-back buffer + event per device (M, K, overflow flag)."""
-    _cache = {}
+    """Per-device pool of (pinned int64[4] read-back buffer, CUDA event) pairs, one per frame in flight."""
+    _free = {}
 
     @classmethod
-    def get(cls, device: torch.device):
+    def acquire(cls, device: torch.device):
         key = device.index if device.index is not None else torch.cuda.current_device()
-        if key not in cls._cache:
-            cls._cache[key] = (torch.zeros(8, dtype=torch.int64).pin_memory(), torch.cuda.Event())
-        return cls._cache[key]
+        pool = cls._free.setdefault(key, [])
+        if pool:
+            return pool.pop()
+        event = torch.cuda.Event()
+        event.record()  # materialises the underlying cudaEvent_t so that its handle can cross the C ABI
+        return torch.zeros(4, dtype=torch.int64).pin_memory(), event
+
+    @classmethod
+    def release(cls, device: torch.device, item) -> None:
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        cls._free.setdefault(key, []).append(item)
 
 
 class Frame:
@@ -224,6 +232,7 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
         self._flags = (_lib.GSB_FLAG_EXACT_EXP if exact_exp else 0) | (_lib.GSB_FLAG_FORCE_KEY64 if force_key64 else 0)
         self._key_capacity = int(initial_key_capacity) if initial_key_capacity else 0
         self.last_frame: Optional[Frame] = None
+        self._layout_cache = {}
         _lib.load()  # fail loudly at construction time if the CUDA library is missing
         outer = self
 
@@ -257,6 +266,17 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
     # ------------------------------------------------------------------ forward plumbing
     def _default_key_capacity(self, num_points: int) -> int:
         return max(1 << 20, 8 * num_points)
+
+    def _layout(self, N, n_obj, key_capacity, H, W):
+        key = (N, n_obj, key_capacity, H, W, self.config.far_plane, self.config.depth_to_sort_key_scale, self._flags)
+        cached = self._layout_cache.get(key)
+        if cached is None:
+            if len(self._layout_cache) > 64:
+                self._layout_cache.clear()
+            cached = _lib.workspace_layout(N, n_obj, key_capacity, H, W, self.config.far_plane,
+                                           self.config.depth_to_sort_key_scale, self._flags)
+            self._layout_cache[key] = cached
+        return cached
 
     def _run_forward(self, pointcloud, pointcloud_features, point_invalid_mask, point_object_id,
                      q_pointcloud_camera, t_pointcloud_camera, camera_info):
@@ -297,12 +317,12 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
                 acc_alpha = torch.empty((H, W), dtype=torch.float32, device=device)
                 last_effective = torch.empty((H, W), dtype=torch.int32, device=device)
                 valid_count = torch.empty((H, W), dtype=torch.int32, device=device)
-            pinned, event = _PinnedCounters.get(device)
+            readback = _PinnedCounters.acquire(device)
+            pinned, event = readback
             retry_flag = 0
             while True:
                 key_capacity = self._key_capacity
-                layout = _lib.workspace_layout(N, n_obj, key_capacity, H, W, cfg.far_plane,
-                                               cfg.depth_to_sort_key_scale, self._flags)
+                layout = self._layout(N, n_obj, key_capacity, H, W)
                 ws = torch.empty((layout.total_bytes,), dtype=torch.uint8, device=device)
                 args = _lib.GsbForwardArgs(
                     num_points=N, pointcloud=_ptr(pointcloud), pointcloud_features=_ptr(pointcloud_features),
@@ -315,13 +335,14 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
                     key_capacity=key_capacity, rasterized_image=_ptr(image), rasterized_depth=_ptr(depth),
                     pixel_accumulated_alpha=_ptr(acc_alpha),
                     pixel_offset_of_last_effective_point=_ptr(last_effective),
-                    pixel_valid_point_count=_ptr(valid_count), stream=stream.cuda_stream)
+                    pixel_valid_point_count=_ptr(valid_count), stream=stream.cuda_stream,
+                    host_counters=pinned.data_ptr(), host_counters_event=event.cuda_event)
+                # The whole frame is enqueued by this one call; the library copies {M, K, overflow} to pinned
+                # host memory right after the per-point stage and records `event` behind that copy.
                 _lib.check(lib.gsb200_forward(ctypes.byref(args)), "gsb200_forward")
                 frame = Frame(ws, layout, N, key_capacity, H, W, self._flags)
-                # one read-back at the END of the frame (the reference syncs twice in the middle,
-                # GPCR:864 and GPCR:916-931): M, K and the key-capacity overflow flag.
-                pinned[:8].copy_(frame.counters, non_blocking=True)
-                event.record(stream)
+                # ONE host wait per frame (the reference syncs twice, GPCR:864 and GPCR:916-931), and it ends
+                # when the first kernel is done: sort + blend are still in flight when we return.
                 event.synchronize()
                 frame.num_points_in_camera = int(pinned[0])
                 frame.num_keys = int(pinned[1])
@@ -331,6 +352,7 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
                 # normalised the quaternions in place; the re-run must not normalise them a second time.
                 self._key_capacity = int(frame.num_keys * 1.25) + 4096
                 retry_flag = _lib.GSB_FLAG_Q_ALREADY_NORMALISED
+            _PinnedCounters.release(device, readback)
         self.last_frame = frame
         return (image, depth, acc_alpha, last_effective, valid_count), frame, {"camera_intrinsics": K}
 

@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgsb200.so")
+LIB_PATH = os.environ.get("GSB200_LIB_PATH", os.path.join(_HERE, "libgsb200.so"))  # override: tuning experiments only
 
 GSB_FLAG_EXACT_EXP = 1
 GSB_FLAG_FORCE_KEY64 = 2
@@ -21,7 +21,7 @@ class GsbWorkspaceLayout(ctypes.Structure):
     _fields_ = [
         ("total_bytes", c_i64), ("zero_bytes", c_i64), ("counters", c_i64), ("tickets", c_i64),
         ("scan_state", c_i64), ("sort_hist", c_i64), ("sort_state", c_i64), ("tile_start", c_i64),
-        ("tile_end", c_i64), ("poses", c_i64), ("point_id", c_i64), ("num_tiles", c_i64),
+        ("tile_end", c_i64), ("poses", c_i64), ("point_id", c_i64), ("point_offset", c_i64), ("num_tiles", c_i64),
         ("records", c_i64), ("point_in_camera", c_i64), ("keys_a", c_i64), ("keys_b", c_i64),
         ("vals_a", c_i64), ("vals_b", c_i64), ("key_bytes", c_i32), ("tile_bits", c_i32),
         ("depth_bits", c_i32), ("sort_passes", c_i32), ("key_capacity_padded", c_i64),
@@ -39,7 +39,7 @@ class GsbForwardArgs(ctypes.Structure):
         ("workspace_bytes", c_i64), ("key_capacity", c_i64), ("rasterized_image", c_vp),
         ("rasterized_depth", c_vp), ("pixel_accumulated_alpha", c_vp),
         ("pixel_offset_of_last_effective_point", c_vp), ("pixel_valid_point_count", c_vp),
-        ("stream", c_vp),
+        ("stream", c_vp), ("host_counters", c_vp), ("host_counters_event", c_vp),
     ]
 
 

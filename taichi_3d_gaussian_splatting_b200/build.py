@@ -13,8 +13,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libgsb200.so")
-OBJ_DIR = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, os.environ.get("GSB200_LIB_NAME", "libgsb200.so"))
+EXTRA_DEFINES = os.environ.get("GSB200_DEFINES", "").split()  # e.g. "-DGSB_SORT_ITEMS=8" (tuning experiments)
+OBJ_DIR = os.path.join(HERE, "build" + ("_" + os.environ["GSB200_LIB_NAME"] if "GSB200_LIB_NAME" in os.environ else ""))
 STAMP = os.path.join(OBJ_DIR, "sources.sha1")
 
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -41,6 +42,7 @@ def _source_hash() -> str:
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
     files.append(os.path.join(os.path.dirname(HERE), "include", "gsb200.h"))
     files.append(os.path.abspath(__file__))
+    h.update(" ".join(EXTRA_DEFINES).encode())
     for f in files:
         with open(f, "rb") as fh:
             h.update(f.encode())
@@ -61,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src, extra in SOURCES.items():
         obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *ARCH_FLAGS, *COMMON, *ccbin, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *ARCH_FLAGS, *COMMON, *ccbin, *extra, *EXTRA_DEFINES, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

@@ -81,6 +81,7 @@ static int compute_layout(int64_t N, int32_t n_obj, int64_t key_capacity, int32_
     L->zero_bytes = off;
     L->poses = take((int64_t)(n_obj > 0 ? n_obj : 1) * sizeof(PoseBlock));
     L->point_id = take(N * 4);
+    L->point_offset = take(N * 4);
     L->num_tiles = take(N * 4);
     L->records = take(N * GSB_RECORD_FLOATS * 4);
     L->point_in_camera = take(N * 3 * 4);
@@ -116,6 +117,7 @@ int resolve_workspace(void *base, int64_t bytes, int64_t N, int32_t n_obj, int64
     ws->tile_end = reinterpret_cast<int *>(b + L.tile_end);
     ws->poses = reinterpret_cast<PoseBlock *>(b + L.poses);
     ws->point_id = reinterpret_cast<int *>(b + L.point_id);
+    ws->point_offset = reinterpret_cast<int *>(b + L.point_offset);
     ws->num_tiles = reinterpret_cast<int *>(b + L.num_tiles);
     ws->records = reinterpret_cast<float4 *>(b + L.records);
     ws->point_in_camera = reinterpret_cast<float *>(b + L.point_in_camera);
@@ -229,6 +231,10 @@ int gsb200_forward(const GsbForwardArgs *a) {
     cudaStream_t st = static_cast<cudaStream_t>(a->stream);
     GSB_CUDA_CHECK(cudaMemsetAsync(a->workspace, 0, (size_t)ws.layout.zero_bytes, st));
     if ((rc = launch_preprocess(*a, ws, st)) != GSB_OK) return rc;
+    if (a->host_counters && a->host_counters_event) {
+        GSB_CUDA_CHECK(cudaMemcpyAsync(a->host_counters, ws.counters, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        GSB_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(a->host_counters_event), st));
+    }
     if ((rc = launch_sort(ws, a->key_capacity, st)) != GSB_OK) return rc;
     const int T = (a->camera_height / GSB_TILE_HEIGHT) * (a->camera_width / GSB_TILE_WIDTH);
     if ((rc = launch_tile_ranges(ws, a->key_capacity, T, st)) != GSB_OK) return rc;
@@ -260,11 +266,6 @@ int gsb200_backward(const GsbBackwardArgs *a) {
     cudaStream_t st = static_cast<cudaStream_t>(a->stream);
     if (a->accum_rows > 0)
         GSB_CUDA_CHECK(cudaMemsetAsync(a->accum, 0, (size_t)a->accum_rows * GSB_ACCUM_FLOATS * 4, st));
-    if (a->num_points > 0) {
-        GSB_CUDA_CHECK(cudaMemsetAsync(a->grad_pointcloud, 0, (size_t)a->num_points * 3 * 4, st));
-        GSB_CUDA_CHECK(cudaMemsetAsync(a->grad_pointcloud_features, 0,
-                                       (size_t)a->num_points * GSB_FEATURE_DIM * 4, st));
-    }
     if ((rc = launch_blend_backward(*a, ws, st)) != GSB_OK) return rc;
     return launch_backward_points(*a, ws, st);
 }
@@ -337,11 +338,6 @@ int gsb200_backward_timed(const GsbBackwardArgs *a, float *stage_ms_out) {
     t.mark();
     if (a->accum_rows > 0)
         GSB_CUDA_CHECK(cudaMemsetAsync(a->accum, 0, (size_t)a->accum_rows * GSB_ACCUM_FLOATS * 4, st));
-    if (a->num_points > 0) {
-        GSB_CUDA_CHECK(cudaMemsetAsync(a->grad_pointcloud, 0, (size_t)a->num_points * 3 * 4, st));
-        GSB_CUDA_CHECK(cudaMemsetAsync(a->grad_pointcloud_features, 0,
-                                       (size_t)a->num_points * GSB_FEATURE_DIM * 4, st));
-    }
     t.mark();
     if ((rc = launch_blend_backward(*a, ws, st)) != GSB_OK) return rc;
     t.mark();

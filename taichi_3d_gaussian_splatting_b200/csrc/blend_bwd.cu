@@ -83,11 +83,11 @@ __device__ __forceinline__ void warp_transpose_reduce16(float (&v)[16], int lane
 template <bool EXACT_EXP>
 __global__ void __launch_bounds__(GSB_TILE_PIXELS)
 blend_backward_kernel(const BlendBwdParams p) {
-    __shared__ float4 s_rec[3 * GSB_TILE_PIXELS];  // [0]: u v a b  [1]: c rescale opacity depth  [2]: r g b radius
-    __shared__ int s_off[GSB_TILE_PIXELS];
-    float4 *const s_r0 = s_rec, *const s_r1 = s_rec + GSB_TILE_PIXELS, *const s_r2 = s_rec + 2 * GSB_TILE_PIXELS;
+    // double-buffered staging area: [buf][plane][splat]; planes: u v a b | c rescale opacity depth | r g b radius
+    __shared__ float4 s_rec[2 * 3 * GSB_TILE_PIXELS];
+    __shared__ int s_off[2][GSB_TILE_PIXELS];
     constexpr int PLANE = GSB_TILE_PIXELS * 16;
-    __shared__ unsigned int s_bits[8][8];  // [consumer warp patch][loader warp]
+    __shared__ unsigned int s_bits[2][8][8];  // [buf][consumer warp patch][loader warp]
     __shared__ int s_max_last;
 
     const int tile = blockIdx.x;
@@ -118,10 +118,12 @@ blend_backward_kernel(const BlendBwdParams p) {
     __syncthreads();
     const int end = min(p.tile_end[tile], s_max_last);
 
-    for (int block_end = end; block_end > start; block_end -= GSB_TILE_PIXELS) {
+    // One barrier per batch (double-buffered staging, see blend_fwd.cu).
+    int buf = 0;
+    for (int block_end = end; block_end > start; block_end -= GSB_TILE_PIXELS, buf ^= 1) {
         const int block_start = max(block_end - GSB_TILE_PIXELS, start);
-        const int nb = block_end - block_start;
-        __syncthreads();  // every warp is done with the previous batch before smem is reused
+        float4 *const s_r0 = s_rec + buf * 3 * GSB_TILE_PIXELS;
+        float4 *const s_r1 = s_r0 + GSB_TILE_PIXELS, *const s_r2 = s_r0 + 2 * GSB_TILE_PIXELS;
         {
             const int idx = block_end - 1 - tid;  // element j <-> sorted index block_end-1-j
             unsigned int mask = 0;
@@ -132,20 +134,21 @@ blend_backward_kernel(const BlendBwdParams p) {
                 s_r0[tid] = r0;
                 s_r1[tid] = r1;
                 s_r2[tid] = __ldg(rec + 2);
-                s_off[tid] = o;
+                s_off[buf][tid] = o;
                 mask = splat_patch_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y * r1.z, tile_x0, tile_y0);
             }
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
                 const unsigned int bits = __ballot_sync(0xffffffffu, (mask >> w) & 1u);
-                if (lane == 0) s_bits[w][warp] = bits;
+                if (lane == 0) s_bits[buf][w][warp] = bits;
             }
         }
         __syncthreads();
+        const unsigned int sb = sa + buf * (3 * PLANE);
         if (block_start < warp_last) {  // otherwise every splat of this batch is behind the whole patch
 #pragma unroll 1
             for (int lw = 0; lw < 8; ++lw) {
-                unsigned int bits = s_bits[warp][lw];
+                unsigned int bits = s_bits[buf][warp][lw];
                 while (bits) {
                     const int j = lw * 32 + __ffs(bits) - 1;
                     bits &= bits - 1;
@@ -156,7 +159,7 @@ blend_backward_kernel(const BlendBwdParams p) {
                     for (int k = 0; k < 16; ++k) v[k] = 0.0f;
                     bool contributes = false;
                     if (idx < last) {
-                        const unsigned int ja = sa + j * 16;
+                        const unsigned int ja = sb + j * 16;
                         const float4 r0 = lds128<0>(ja);      // u v a b
                         const float4 r1 = lds128<PLANE>(ja);  // c rescale opacity depth
                         const float d0 = px - r0.x, d1 = py - r0.y;
@@ -203,7 +206,7 @@ blend_backward_kernel(const BlendBwdParams p) {
                         warp_transpose_reduce16(v, lane);
                         const int k = (lane >> 1) & 15;
                         if ((lane & 1) == 0 && k < 11)
-                            atomicAdd(p.accum + (size_t)s_off[j] * GSB_ACCUM_FLOATS + k, v[0]);
+                            atomicAdd(p.accum + (size_t)s_off[buf][j] * GSB_ACCUM_FLOATS + k, v[0]);
                     }
                 }
             }
@@ -240,8 +243,8 @@ int launch_blend_backward(const GsbBackwardArgs &a, const Workspace &ws, cudaStr
 
 // ------------------------------------------------------------------ loop B + P4
 struct PointsBwdParams {
-    const long long *counters;
-    const int *point_id;
+    long long N;
+    const int *point_offset;
     const float4 *records;
     const float *point_in_camera;
     const float *accum;
@@ -259,10 +262,19 @@ struct PointsBwdParams {
 
 __global__ void __launch_bounds__(128)
 backward_points_kernel(const PointsBwdParams p) {
-    const long long M = p.counters[CNT_M];
+    // One thread per scene row: rows outside the frustum get their zeros here (no separate memset of the
+    // dense (N,3)/(N,56) gradients), rows inside get the chain rule.
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < M; o += stride) {
-        const int id = p.point_id[o];
+    for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < p.N; id += stride) {
+        const int o = p.point_offset[id];
+        if (o < 0) {
+            float *gxz = p.grad_xyz + 3 * (size_t)id;
+            gxz[0] = 0.0f; gxz[1] = 0.0f; gxz[2] = 0.0f;
+            float4 *gz = reinterpret_cast<float4 *>(p.grad_feat + (size_t)GSB_FEATURE_DIM * id);
+#pragma unroll
+            for (int k = 0; k < GSB_FEATURE_DIM / 4; ++k) gz[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            continue;
+        }
         const float4 *accp = reinterpret_cast<const float4 *>(p.accum + (size_t)o * GSB_ACCUM_FLOATS);
         const float4 a0 = accp[0], a1 = accp[1], a2 = accp[2];
         // a0 = guv.x guv.y g00 g01 | a1 = g11 gr gg gb | a2 = glogit mag n pad
@@ -391,8 +403,8 @@ backward_points_kernel(const PointsBwdParams p) {
 int launch_backward_points(const GsbBackwardArgs &a, const Workspace &ws, cudaStream_t stream) {
     if (a.num_points <= 0) return GSB_OK;
     PointsBwdParams p;
-    p.counters = ws.counters;
-    p.point_id = ws.point_id;
+    p.N = a.num_points;
+    p.point_offset = ws.point_offset;
     p.records = ws.records;
     p.point_in_camera = ws.point_in_camera;
     p.accum = a.accum;
@@ -411,7 +423,7 @@ int launch_backward_points(const GsbBackwardArgs &a, const Workspace &ws, cudaSt
     p.h_f = a.grad_high_order_color_factor;
     p.grad_xyz = a.grad_pointcloud;
     p.grad_feat = a.grad_pointcloud_features;
-    long long blocks = (a.accum_rows + 127) / 128;
+    long long blocks = (a.num_points + 127) / 128;
     const long long cap = 16LL * num_sms();
     if (blocks > cap) blocks = cap;
     if (blocks <= 0) return GSB_OK;

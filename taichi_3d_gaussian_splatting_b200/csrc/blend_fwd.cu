@@ -35,10 +35,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
 template <bool RGB_ONLY, bool EXACT_EXP>
 __global__ void __launch_bounds__(GSB_TILE_PIXELS, 5)
 blend_forward_kernel(const BlendFwdParams p) {
-    __shared__ float4 s_rec[3 * GSB_TILE_PIXELS];  // [0]: u v a b  [1]: c rescale opacity depth  [2]: r g b radius
-    float4 *const s_r0 = s_rec, *const s_r1 = s_rec + GSB_TILE_PIXELS, *const s_r2 = s_rec + 2 * GSB_TILE_PIXELS;
+    // double-buffered staging area: [buf][plane][splat]; planes: u v a b | c rescale opacity depth | r g b radius
+    __shared__ float4 s_rec[2 * 3 * GSB_TILE_PIXELS];
     constexpr int PLANE = GSB_TILE_PIXELS * 16;  // bytes between the three record planes
-    __shared__ unsigned int s_bits[8][8];  // [consumer warp patch][loader warp] -> splats that can reach it
+    __shared__ unsigned int s_bits[2][8][8];  // [buf][consumer warp patch][loader warp] -> splats that can reach it
 
     const int tile = blockIdx.x;
     const int tu = tile % p.tiles_x, tv = tile / p.tiles_x;
@@ -56,8 +56,12 @@ blend_forward_kernel(const BlendFwdParams p) {
     int last = start, cnt = 0;
     const unsigned int sa = smem_u32(s_rec);
 
-    for (int base = start; base < end; base += GSB_TILE_PIXELS) {
-        if (__syncthreads_and(T == 0.0f)) break;  // barrier (smem reuse) + tile-level early exit
+    // One barrier per batch: batch k is staged into buffer k&1 while slower warps may still be blending
+    // batch k-1 from the other buffer; passing barrier k implies everybody is done with batch k-1.
+    int buf = 0;
+    for (int base = start; base < end; base += GSB_TILE_PIXELS, buf ^= 1) {
+        float4 *const s_r0 = s_rec + buf * 3 * GSB_TILE_PIXELS;
+        float4 *const s_r1 = s_r0 + GSB_TILE_PIXELS, *const s_r2 = s_r0 + 2 * GSB_TILE_PIXELS;
         const int idx = base + tid;
         unsigned int mask = 0;
         if (idx < end) {
@@ -80,17 +84,18 @@ blend_forward_kernel(const BlendFwdParams p) {
 #pragma unroll
         for (int w = 0; w < 8; ++w) {
             const unsigned int bits = __ballot_sync(0xffffffffu, (mask >> w) & 1u);
-            if (lane == 0) s_bits[w][warp] = bits;
+            if (lane == 0) s_bits[buf][w][warp] = bits;
         }
-        __syncthreads();
+        if (__syncthreads_and(T == 0.0f)) break;  // staging visible + tile-level early exit
         if (__all_sync(0xffffffffu, T == 0.0f)) continue;  // whole patch saturated: only help with loads
+        const unsigned int sb = sa + buf * (3 * PLANE);
 #pragma unroll 1
         for (int lw = 0; lw < 8; ++lw) {
-            unsigned int bits = s_bits[warp][lw];
+            unsigned int bits = s_bits[buf][warp][lw];
             while (bits) {
                 const int j = lw * 32 + __ffs(bits) - 1;
                 bits &= bits - 1;
-                const unsigned int ja = sa + j * 16;
+                const unsigned int ja = sb + j * 16;
                 const float4 r0 = lds128<0>(ja);      // u v a b      (fast: u v A B)
                 const float4 r1 = lds128<PLANE>(ja);  // c rescale opacity depth (fast: C ro - depth)
                 const float dx = px - r0.x, dy = py - r0.y;

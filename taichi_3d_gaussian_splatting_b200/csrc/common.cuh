@@ -46,6 +46,7 @@ struct Workspace {
     int *tile_end;
     PoseBlock *poses;
     int *point_id;
+    int *point_offset;
     int *num_tiles;
     float4 *records;        // 3 float4 per in-camera point
     float *point_in_camera; // 3 floats per in-camera point
@@ -74,8 +75,14 @@ int sort_pairs_device(const void *keys_in, const int *vals_in, void *keys_out, i
                       unsigned int *tickets /*8, zeroed*/, void *tmp_keys, int *tmp_vals,
                       long long *sel_out, cudaStream_t stream);
 
+#ifndef GSB_SORT_ITEMS
+#define GSB_SORT_ITEMS 16
+#endif
+#ifndef GSB_SORT_MIN_BLOCKS
+#define GSB_SORT_MIN_BLOCKS 2
+#endif
 constexpr int SORT_BLOCK_THREADS = 256;
-constexpr int SORT_ITEMS_PER_THREAD = 16;
+constexpr int SORT_ITEMS_PER_THREAD = GSB_SORT_ITEMS;
 constexpr int SORT_TILE = SORT_BLOCK_THREADS * SORT_ITEMS_PER_THREAD;  // 4096 keys per CTA
 constexpr int SCAN_BLOCK_THREADS = 256;
 

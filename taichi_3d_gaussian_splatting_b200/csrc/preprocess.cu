@@ -120,6 +120,7 @@ struct PreParams {
     unsigned int *tickets;
     unsigned long long *scan_state;
     int *point_id;
+    int *point_offset;
     int *num_tiles;
     float4 *records;
     float *point_in_camera;
@@ -140,8 +141,11 @@ __device__ __forceinline__ void bounding_box(float u, float v, float radii, int 
     d = min(max((int)floorf(max_v / (float)GSB_TILE_HEIGHT) + 1, c + 1), th);
 }
 
+#ifndef GSB_PRE_MIN_BLOCKS
+#define GSB_PRE_MIN_BLOCKS 2
+#endif
 template <typename KeyT>
-__global__ void __launch_bounds__(SCAN_BLOCK_THREADS)
+__global__ void __launch_bounds__(SCAN_BLOCK_THREADS, GSB_PRE_MIN_BLOCKS)
 preprocess_kernel(const PreParams p) {
     __shared__ unsigned int s_ticket;
     __shared__ unsigned long long s_warp_sums[SCAN_BLOCK_THREADS / 32];
@@ -333,12 +337,16 @@ preprocess_kernel(const PreParams p) {
         }
     }
     __syncthreads();
-    if (!in) return;
+    if (!in) {
+        if (i < p.N) p.point_offset[i] = -1;
+        return;
+    }
     const unsigned long long excl = s_block_exclusive + warp_prefix + (incl - mine);
     const long long off = (long long)(excl >> CNT_SHIFT);
     const long long key_base = (long long)(excl & ((1ull << CNT_SHIFT) - 1));
 
     p.point_id[off] = (int)i;
+    p.point_offset[i] = (int)off;
     p.num_tiles[off] = ntiles;
     p.records[3 * off] = r0;
     p.records[3 * off + 1] = r1;
@@ -392,6 +400,7 @@ int launch_preprocess(const GsbForwardArgs &a, const Workspace &ws, cudaStream_t
     p.tickets = ws.tickets;
     p.scan_state = ws.scan_state;
     p.point_id = ws.point_id;
+    p.point_offset = ws.point_offset;
     p.num_tiles = ws.num_tiles;
     p.records = ws.records;
     p.point_in_camera = ws.point_in_camera;

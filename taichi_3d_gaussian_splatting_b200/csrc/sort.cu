@@ -99,7 +99,7 @@ struct PassSmem {
 };
 
 template <typename KeyT>
-__global__ void __launch_bounds__(SORT_BLOCK_THREADS)
+__global__ void __launch_bounds__(SORT_BLOCK_THREADS, GSB_SORT_MIN_BLOCKS)
 onesweep_pass_kernel(const KeyT *__restrict__ keys_in, const int *__restrict__ vals_in,
                      KeyT *__restrict__ keys_out, int *__restrict__ vals_out,
                      const long long *__restrict__ n_dev, long long capacity, int shift,
