@@ -244,21 +244,40 @@ def run_b200(args):
     K_host = scene.camera_info.camera_intrinsics.detach().cpu().pin_memory()
     h2d = target_host.numel() * 4 + q_host.numel() * 4 + t_host.numel() * 4 + K_host.numel() * 4
 
-    def step_e2e():
-        scene.point_cloud.grad = None
-        scene.point_cloud_features.grad = None
-        target = target_host.to(device, non_blocking=True)
-        inp = make_input(q_host.to(device, non_blocking=True), t_host.to(device, non_blocking=True),
-                         K_host.to(device, non_blocking=True))
-        image, _, _ = op(inp)
-        loss = (image - target).abs().mean()
-        loss.backward()
-        exchange_grads()
-        return float(loss.item())  # D2H read of the step's result
+    # The step's host inputs are uploaded on a copy stream into double-buffered device slots, one step
+    # ahead (what a DataLoader with pin_memory + non_blocking does); every step's copy is issued and
+    # completed inside the timed region.
+    copy_stream = torch.cuda.Stream(device=device)
+    slots = [dict(target=torch.empty((H, W, 3), dtype=torch.float32, device=device),
+                  q=torch.empty_like(scene.q_pointcloud_camera), t=torch.empty_like(scene.t_pointcloud_camera),
+                  K=torch.empty((3, 3), dtype=torch.float32, device=device), ready=torch.cuda.Event())
+             for _ in range(2)]
 
-    for _ in range(3):
-        step_e2e()
-    e2e_ms = timed(step_e2e, steps) / steps
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            slot["target"].copy_(target_host, non_blocking=True)
+            slot["q"].copy_(q_host, non_blocking=True)
+            slot["t"].copy_(t_host, non_blocking=True)
+            slot["K"].copy_(K_host, non_blocking=True)
+            slot["ready"].record(copy_stream)
+
+    def run_e2e(k):
+        upload(slots[0])
+        for i in range(k):
+            if i + 1 < k:
+                upload(slots[(i + 1) % 2])  # overlaps with this step's compute
+            slot = slots[i % 2]
+            torch.cuda.current_stream().wait_event(slot["ready"])
+            scene.point_cloud.grad = None
+            scene.point_cloud_features.grad = None
+            image, _, _ = op(make_input(slot["q"], slot["t"], slot["K"]))
+            loss = (image - slot["target"]).abs().mean()
+            loss.backward()
+            exchange_grads()
+            float(loss.item())  # D2H read of the step's result (also orders slot reuse)
+
+    run_e2e(3)
+    e2e_ms = timed(lambda: run_e2e(steps), 1) / steps
     e2e_value = world * H * W / (e2e_ms * 1e-3) / 1e6
 
     # ---- forward-only numbers (inference: torch.no_grad, full outputs and rgb_only)
@@ -337,7 +356,7 @@ def run_b200(args):
                    "l2": "inputs larger than L2 (scene 236 MB + 200 MB workspace per frame vs 126 MB L2)"},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(e2e_ms, 4),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "what": "pinned host target image + pose + intrinsics -> device, forward, L1 loss, backward, loss.item()"},
+                "what": "per step: pinned host target image + pose + intrinsics -> device (copy stream, one step ahead), forward, L1 loss, backward, loss.item()"},
         "forward_only": {"Mpix_s": round(world * H * W / (fwd_ms * 1e-3) / 1e6, 2), "ms": round(fwd_ms, 4),
                          "rgb_only_Mpix_s": round(world * H * W / (fwd_rgb_ms * 1e-3) / 1e6, 2),
                          "rgb_only_ms": round(fwd_rgb_ms, 4)},

@@ -58,8 +58,8 @@ typedef struct GsbWorkspaceLayout {
                                   [2]=overflow (K > key_capacity), [3]=sorted-buffer selector (0=a,1=b) */
     int64_t tickets;           /* uint32[16] dynamic block tickets */
     int64_t scan_state;        /* uint64[ceil(N/256)+1] decoupled look-back state of the compaction scan */
-    int64_t sort_hist;         /* uint32[8][256] global digit histograms */
-    int64_t sort_state;        /* uint32[passes][sort_blocks][256] onesweep look-back state */
+    int64_t sort_hist;         /* uint32[8][1024] global digit histograms */
+    int64_t sort_state;        /* uint32[passes][sort_blocks][2^radix_bits] onesweep look-back state */
     int64_t tile_start;        /* int32[T]  GPCR:952-957 tile_points_start */
     int64_t tile_end;          /* int32[T]  tile_points_end */
     int64_t poses;             /* float[num_objects][20]: T_camera_pointcloud 3x4, camera centre, pad */
@@ -74,6 +74,8 @@ typedef struct GsbWorkspaceLayout {
     int32_t tile_bits, depth_bits, sort_passes;
     int64_t key_capacity_padded;
     int32_t sort_blocks, scan_blocks;
+    int32_t radix_bits;        /* 8 or 10: digit width of the key sort */
+    int32_t reserved;
 } GsbWorkspaceLayout;
 
 /* Inputs of GaussianPointCloudRasterisationInput (GPCR:788-804) + config (GPCR:776-786). */

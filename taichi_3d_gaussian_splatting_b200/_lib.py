@@ -25,7 +25,7 @@ class GsbWorkspaceLayout(ctypes.Structure):
         ("records", c_i64), ("point_in_camera", c_i64), ("keys_a", c_i64), ("keys_b", c_i64),
         ("vals_a", c_i64), ("vals_b", c_i64), ("key_bytes", c_i32), ("tile_bits", c_i32),
         ("depth_bits", c_i32), ("sort_passes", c_i32), ("key_capacity_padded", c_i64),
-        ("sort_blocks", c_i32), ("scan_blocks", c_i32),
+        ("sort_blocks", c_i32), ("scan_blocks", c_i32), ("radix_bits", c_i32), ("reserved", c_i32),
     ]
 
 

@@ -59,7 +59,8 @@ static int compute_layout(int64_t N, int32_t n_obj, int64_t key_capacity, int32_
     } else {
         L->key_bytes = 4;
     }
-    L->sort_passes = (L->tile_bits + L->depth_bits + 7) / 8;
+    L->radix_bits = sort_radix_bits(L->tile_bits + L->depth_bits);
+    L->sort_passes = (L->tile_bits + L->depth_bits + L->radix_bits - 1) / L->radix_bits;
     if (L->sort_passes < 1) L->sort_passes = 1;
     L->key_capacity_padded = align_up(key_capacity > 0 ? key_capacity : 1, SORT_TILE);
     L->sort_blocks = (int32_t)(L->key_capacity_padded / SORT_TILE);
@@ -74,8 +75,8 @@ static int compute_layout(int64_t N, int32_t n_obj, int64_t key_capacity, int32_
     L->counters = take(8 * sizeof(int64_t));
     L->tickets = take(16 * sizeof(uint32_t));
     L->scan_state = take((int64_t)(L->scan_blocks + 1) * 8);
-    L->sort_hist = take(8 * 256 * 4);
-    L->sort_state = take((int64_t)L->sort_passes * L->sort_blocks * 256 * 4);
+    L->sort_hist = take(8 * 1024 * 4);
+    L->sort_state = take((int64_t)L->sort_passes * L->sort_blocks * (1 << L->radix_bits) * 4);
     L->tile_start = take(T * 4);
     L->tile_end = take(T * 4);
     L->zero_bytes = off;
@@ -362,8 +363,8 @@ int64_t gsb200_sort_temp_bytes(int64_t n, int32_t key_bytes) {
     int64_t off = 0;
     off += 256;                                      // n_dev
     off += 256;                                      // tickets
-    off += 8 * 256 * 4;                              // hist
-    off += align_up(8 * blocks * 256 * 4, 256);      // state (up to 8 passes)
+    off += 8 * 1024 * 4;                             // hist (up to 8 passes of up to 1024 bins)
+    off += align_up(8 * blocks * 1024 * 4, 256);     // look-back state (up to 8 passes x 1024 digits)
     off += align_up(padded * key_bytes, 256);        // tmp keys
     off += align_up(padded * 4, 256);                // tmp vals
     return off;
@@ -396,11 +397,11 @@ int gsb200_sort_pairs(const void *keys_in, const int32_t *vals_in, void *keys_ou
     long long *n_dev = reinterpret_cast<long long *>(b);
     unsigned int *tickets = reinterpret_cast<unsigned int *>(b + 256);
     unsigned int *hist = reinterpret_cast<unsigned int *>(b + 512);
-    unsigned int *state = reinterpret_cast<unsigned int *>(b + 512 + 8 * 256 * 4);
-    const int64_t state_bytes = align_up(8 * blocks * 256 * 4, 256);
-    void *tmp_keys = b + 512 + 8 * 256 * 4 + state_bytes;
+    unsigned int *state = reinterpret_cast<unsigned int *>(b + 512 + 8 * 1024 * 4);
+    const int64_t state_bytes = align_up(8 * blocks * 1024 * 4, 256);
+    void *tmp_keys = b + 512 + 8 * 1024 * 4 + state_bytes;
     int *tmp_vals = reinterpret_cast<int *>(static_cast<char *>(tmp_keys) + align_up(padded * key_bytes, 256));
-    GSB_CUDA_CHECK(cudaMemsetAsync(b, 0, (size_t)(512 + 8 * 256 * 4 + state_bytes), st));
+    GSB_CUDA_CHECK(cudaMemsetAsync(b, 0, (size_t)(512 + 8 * 1024 * 4 + state_bytes), st));
     const long long n_host = n;
     GSB_CUDA_CHECK(cudaMemcpyAsync(n_dev, &n_host, sizeof(n_host), cudaMemcpyHostToDevice, st));
     return sort_pairs_device(keys_in, vals_in, keys_out, vals_out, n_dev, padded, key_bytes, end_bit, hist,

@@ -69,6 +69,7 @@ int launch_blend_forward(const GsbForwardArgs &a, const Workspace &ws, cudaStrea
 int launch_blend_backward(const GsbBackwardArgs &a, const Workspace &ws, cudaStream_t stream);
 int launch_backward_points(const GsbBackwardArgs &a, const Workspace &ws, cudaStream_t stream);
 
+int sort_radix_bits(int bits);
 int sort_pairs_device(const void *keys_in, const int *vals_in, void *keys_out, int *vals_out,
                       const long long *n_dev, int64_t n_capacity, int key_bytes, int end_bit,
                       unsigned int *hist /*8*256, zeroed*/, unsigned int *state /*zeroed*/,

@@ -142,7 +142,7 @@ __device__ __forceinline__ void bounding_box(float u, float v, float radii, int 
 }
 
 #ifndef GSB_PRE_MIN_BLOCKS
-#define GSB_PRE_MIN_BLOCKS 2
+#define GSB_PRE_MIN_BLOCKS 4
 #endif
 template <typename KeyT>
 __global__ void __launch_bounds__(SCAN_BLOCK_THREADS, GSB_PRE_MIN_BLOCKS)
@@ -187,13 +187,8 @@ preprocess_kernel(const PreParams p) {
         if (in) {
             float4 *frow = reinterpret_cast<float4 *>(p.features + (size_t)GSB_FEATURE_DIM * i);
             float4 qv = frow[0];  // plain load: this row's q is rewritten below
-            float f[GSB_FEATURE_DIM - 4];
-#pragma unroll
-            for (int k = 1; k < GSB_FEATURE_DIM / 4; ++k) {
-                float4 t4 = __ldg(reinterpret_cast<const float4 *>(frow) + k);
-                f[4 * (k - 1)] = t4.x; f[4 * (k - 1) + 1] = t4.y;
-                f[4 * (k - 1) + 2] = t4.z; f[4 * (k - 1) + 3] = t4.w;
-            }
+            const float4 sl = __ldg(reinterpret_cast<const float4 *>(frow) + 1);  // s0 s1 s2 logit
+            const float f[4] = {sl.x, sl.y, sl.z, sl.w};
             // GPCR:196-205: q <- q / |q| (invlen * q), written back in place
             if (!p.skip_q_normalise) {
                 float qn = sqrtf(((qv.x * qv.x + qv.y * qv.y) + qv.z * qv.z) + qv.w * qv.w);
@@ -263,13 +258,21 @@ preprocess_kernel(const PreParams p) {
             sh[13] = 0.45704579946446572f * dx * (1.0f - 5.0f * dz * dz);
             sh[14] = 1.4453057213202769f * dz * (dx * dx - dy * dy);
             sh[15] = 0.59004358992664352f * dx * (-dx * dx + 3.0f * dy * dy);
+            // SH coefficients are streamed 16 B at a time right where they are consumed (keeps ~50 registers
+            // free; the dot product order k = 0..15 is the oracle's)
             float col[3];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                const float *cf = f + 4 + 16 * ch;
-                float acc = cf[0] * sh[0];
+                float acc = 0.0f;
 #pragma unroll
-                for (int k = 1; k < 16; ++k) acc = acc + cf[k] * sh[k];
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const float4 c4 = __ldg(reinterpret_cast<const float4 *>(frow) + 2 + 4 * ch + k4);
+                    if (k4 == 0) acc = c4.x * sh[0];
+                    else acc = acc + c4.x * sh[4 * k4];
+                    acc = acc + c4.y * sh[4 * k4 + 1];
+                    acc = acc + c4.z * sh[4 * k4 + 2];
+                    acc = acc + c4.w * sh[4 * k4 + 3];
+                }
                 col[ch] = sigmoid_cr(acc);
             }
             bounding_box(u, v, radius, p.W, p.H, min_tu, max_tu, min_tv, max_tv);

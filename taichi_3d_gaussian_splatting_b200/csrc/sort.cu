@@ -14,11 +14,18 @@
 
 namespace gsb {
 
-constexpr int RADIX_BITS = 8;
-constexpr int RADIX = 1 << RADIX_BITS;
 constexpr unsigned int SS_AGGREGATE = 1u << 30;
 constexpr unsigned int SS_INCLUSIVE = 2u << 30;
 constexpr unsigned int SS_VALUE_MASK = (1u << 30) - 1;
+constexpr int MAX_RADIX = 1024;  // 8-bit or 10-bit digits; 10 bits when that saves a pass (e.g. 30-bit keys: 3 vs 4)
+
+// Digit width for a key of `bits` live bits.  The kernels are templated on 8- and 10-bit digits; measured on
+// B200 (C3, 30-bit keys, K = 4.0e6) three 10-bit passes cost 244 us against 199 us for four 8-bit passes
+// (1024-bin ranking + 4 KB of look-back state per CTA outweigh the saved pass), so 8 bits are always used.
+int sort_radix_bits(int bits) {
+    (void)bits;
+    return 8;
+}
 
 __device__ __forceinline__ unsigned int ld_u32_volatile(const unsigned int *p) {
     return *reinterpret_cast<const volatile unsigned int *>(p);
@@ -63,10 +70,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int 
 }
 
 // ------------------------------------------------------------------ histograms of all passes
-template <typename KeyT>
+template <typename KeyT, int RBITS>
 __global__ void __launch_bounds__(256)
 sort_histogram_kernel(const KeyT *__restrict__ keys, const long long *__restrict__ n_dev,
                       long long capacity, int passes, unsigned int *__restrict__ hist) {
+    constexpr int RADIX = 1 << RBITS;
     __shared__ unsigned int s_hist[8 * RADIX];
     for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
@@ -76,7 +84,7 @@ sort_histogram_kernel(const KeyT *__restrict__ keys, const long long *__restrict
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const KeyT k = keys[i];
         for (int p = 0; p < passes; ++p)
-            atomicAdd(&s_hist[p * RADIX + (int)((k >> (p * RADIX_BITS)) & (RADIX - 1))], 1u);
+            atomicAdd(&s_hist[p * RADIX + (int)((k >> (p * RBITS)) & (RADIX - 1))], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x) {
@@ -86,11 +94,12 @@ sort_histogram_kernel(const KeyT *__restrict__ keys, const long long *__restrict
 }
 
 // ------------------------------------------------------------------ one radix pass
-template <typename KeyT>
+template <typename KeyT, int RBITS>
 struct PassSmem {
+    static constexpr int RADIX = 1 << RBITS;
     alignas(128) KeyT keys[SORT_TILE];  // TMA destination, later the block-sorted key staging area
     int vals[SORT_TILE];                // block-sorted payload staging area
-    unsigned int warp_cnt[SORT_BLOCK_THREADS / 32][RADIX];
+    unsigned short warp_cnt[SORT_BLOCK_THREADS / 32][RADIX];  // per-warp digit counters (<= 512 each)
     unsigned int digit_start[RADIX];    // exclusive start of each digit inside the block-sorted tile
     unsigned int global_base[RADIX];    // destination of local position p with digit d: global_base[d] + p
     unsigned int scan_tmp[SORT_BLOCK_THREADS / 32];
@@ -98,16 +107,37 @@ struct PassSmem {
     unsigned int ticket;
 };
 
-template <typename KeyT>
+// exclusive block scan of one value per thread (256 threads); returns the exclusive prefix of `v`
+template <typename S>
+__device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, S &s, int lane, int warp) {
+    unsigned int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    __syncthreads();  // scan_tmp free
+    if (lane == 31) s.scan_tmp[warp] = incl;
+    __syncthreads();
+    unsigned int wprefix = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_BLOCK_THREADS / 32; ++w)
+        if (w < warp) wprefix += s.scan_tmp[w];
+    return wprefix + incl - v;
+}
+
+template <typename KeyT, int RBITS>
 __global__ void __launch_bounds__(SORT_BLOCK_THREADS, GSB_SORT_MIN_BLOCKS)
 onesweep_pass_kernel(const KeyT *__restrict__ keys_in, const int *__restrict__ vals_in,
                      KeyT *__restrict__ keys_out, int *__restrict__ vals_out,
                      const long long *__restrict__ n_dev, long long capacity, int shift,
-                     const unsigned int *__restrict__ hist /* this pass, 256 bins */,
-                     unsigned int *__restrict__ state /* this pass: [blocks][256] */,
+                     const unsigned int *__restrict__ hist /* this pass, RADIX bins */,
+                     unsigned int *__restrict__ state /* this pass: [blocks][RADIX] */,
                      unsigned int *__restrict__ ticket_ctr) {
+    constexpr int RADIX = 1 << RBITS;
+    constexpr int DPT = RADIX / SORT_BLOCK_THREADS;  // digits owned by a thread: [tid*DPT, tid*DPT+DPT)
     extern __shared__ unsigned char smem_raw[];
-    PassSmem<KeyT> &s = *reinterpret_cast<PassSmem<KeyT> *>(
+    PassSmem<KeyT, RBITS> &s = *reinterpret_cast<PassSmem<KeyT, RBITS> *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -115,8 +145,10 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, const int *__restrict__ v
         s.ticket = atomicAdd(ticket_ctr, 1u);
         mbar_init(&s.mbar, 1);
     }
-    for (int i = tid; i < (SORT_BLOCK_THREADS / 32) * RADIX; i += SORT_BLOCK_THREADS)
-        (&s.warp_cnt[0][0])[i] = 0;
+    {
+        unsigned int *z = reinterpret_cast<unsigned int *>(&s.warp_cnt[0][0]);
+        for (int i = tid; i < (SORT_BLOCK_THREADS / 32) * RADIX / 2; i += SORT_BLOCK_THREADS) z[i] = 0;
+    }
     __syncthreads();
     const unsigned int blk = s.ticket;
     long long n = *n_dev;
@@ -160,75 +192,56 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, const int *__restrict__ v
         if (valid) prev = s.warp_cnt[warp][d];
         ranks[j] = (unsigned short)(prev + __popc(peers & lt_mask));
         __syncwarp();
-        if (valid && (peers & lt_mask) == 0) s.warp_cnt[warp][d] = prev + __popc(peers);
+        if (valid && (peers & lt_mask) == 0) s.warp_cnt[warp][d] = (unsigned short)(prev + __popc(peers));
         __syncwarp();
     }
     __syncthreads();
 
-    // per-digit totals, warp-exclusive bases, block-exclusive digit starts
-    unsigned int my_count = 0;
-    {
+    // per-digit totals (thread t owns digits t*DPT..), warp-exclusive bases; publish the aggregates at once
+    unsigned int cnt[DPT], excl[DPT];
+    unsigned int *my_state = state + (size_t)blk * RADIX + tid * DPT;
+    unsigned int tsum = 0;
+#pragma unroll
+    for (int k = 0; k < DPT; ++k) {
+        const int d = tid * DPT + k;
+        unsigned int c = 0;
 #pragma unroll
         for (int w = 0; w < SORT_BLOCK_THREADS / 32; ++w) {
-            const unsigned int c = s.warp_cnt[w][tid];
-            s.warp_cnt[w][tid] = my_count;
-            my_count += c;
+            const unsigned int x = s.warp_cnt[w][d];
+            s.warp_cnt[w][d] = (unsigned short)c;
+            c += x;
         }
-        unsigned int incl = my_count;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned int o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += o;
-        }
-        if (lane == 31) s.scan_tmp[warp] = incl;
-        __syncthreads();
-        unsigned int wprefix = 0;
-#pragma unroll
-        for (int w = 0; w < SORT_BLOCK_THREADS / 32; ++w)
-            if (w < warp) wprefix += s.scan_tmp[w];
-        const unsigned int dstart = wprefix + incl - my_count;
-        s.digit_start[tid] = dstart;
-
-        // global exclusive prefix of this digit over all digits (from the pass histogram)
-        unsigned int h = hist[tid];
-        unsigned int hincl = h;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned int o = __shfl_up_sync(0xffffffffu, hincl, d);
-            if (lane >= d) hincl += o;
-        }
-        __syncthreads();  // scan_tmp reuse
-        if (lane == 31) s.scan_tmp[warp] = hincl;
-        __syncthreads();
-        unsigned int hprefix = 0;
-#pragma unroll
-        for (int w = 0; w < SORT_BLOCK_THREADS / 32; ++w)
-            if (w < warp) hprefix += s.scan_tmp[w];
-        const unsigned int digit_global = hprefix + hincl - h;
-
-        // (c) decoupled look-back over preceding CTAs for digit `tid`
-        unsigned int *my_state = state + (size_t)blk * RADIX + tid;
-        unsigned int exclusive = 0;
-        if (blk == 0) {
-            st_u32_volatile(my_state, SS_INCLUSIVE | my_count);
-        } else {
-            st_u32_volatile(my_state, SS_AGGREGATE | my_count);
-            long long look = (long long)blk - 1;
-            while (true) {
-                const unsigned int *ps = state + (size_t)look * RADIX + tid;
-                unsigned int w = ld_u32_volatile(ps);
-                while ((w >> 30) == 0) w = ld_u32_volatile(ps);
-                exclusive += w & SS_VALUE_MASK;
-                if ((w >> 30) == 2) break;
-                --look;
-            }
-            st_u32_volatile(my_state, SS_INCLUSIVE | (exclusive + my_count));
-        }
-        s.global_base[tid] = digit_global + exclusive - dstart;
+        cnt[k] = c;
+        tsum += c;
+        st_u32_volatile(my_state + k, (blk == 0 ? SS_INCLUSIVE : SS_AGGREGATE) | c);
     }
-    __syncthreads();
+    {   // block-exclusive digit starts
+        unsigned int run = block_exclusive_scan(tsum, s, lane, warp);
+#pragma unroll
+        for (int k = 0; k < DPT; ++k) {
+            s.digit_start[tid * DPT + k] = run;
+            run += cnt[k];
+        }
+    }
+    unsigned int dglobal[DPT];
+    {   // global exclusive prefix of each digit over all digits (from the pass histogram)
+        unsigned int h[DPT], hs = 0;
+#pragma unroll
+        for (int k = 0; k < DPT; ++k) {
+            h[k] = hist[tid * DPT + k];
+            hs += h[k];
+        }
+        unsigned int run = block_exclusive_scan(hs, s, lane, warp);
+#pragma unroll
+        for (int k = 0; k < DPT; ++k) {
+            dglobal[k] = run;
+            run += h[k];
+        }
+    }
+    __syncthreads();  // digit_start and the warp bases are visible
 
-    // block-sorted staging in shared memory (the TMA buffer is dead: all keys are in registers)
+    // block-sorted staging in shared memory (the TMA buffer is dead: all keys are in registers).  This needs
+    // only block-local offsets, so it runs BEFORE the look-back and gives the predecessors time to publish.
 #pragma unroll
     for (int j = 0; j < SORT_ITEMS_PER_THREAD; ++j) {
         const int idx = wbase + j * 32 + lane;
@@ -239,7 +252,48 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, const int *__restrict__ v
             s.vals[pos] = vals[j];
         }
     }
+
+    // (c) decoupled look-back over preceding CTAs for this thread's digits, four predecessors in flight per round
+#pragma unroll
+    for (int k = 0; k < DPT; ++k) excl[k] = 0;
+    if (blk != 0) {
+        bool done[DPT];
+#pragma unroll
+        for (int k = 0; k < DPT; ++k) done[k] = false;
+        long long look = (long long)blk - 1;
+        bool all_done = false;
+        while (!all_done) {
+            unsigned int w[4][DPT];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int k = 0; k < DPT; ++k)
+                    w[r][k] = (look - r >= 0) ? ld_u32_volatile(state + (size_t)(look - r) * RADIX + tid * DPT + k)
+                                              : SS_INCLUSIVE;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                for (int k = 0; k < DPT; ++k) {
+                    if (done[k]) continue;
+                    while ((w[r][k] >> 30) == 0)
+                        w[r][k] = ld_u32_volatile(state + (size_t)(look - r) * RADIX + tid * DPT + k);
+                    excl[k] += w[r][k] & SS_VALUE_MASK;
+                    if ((w[r][k] >> 30) == 2) done[k] = true;
+                }
+            }
+            all_done = true;
+#pragma unroll
+            for (int k = 0; k < DPT; ++k) all_done = all_done && done[k];
+            look -= 4;
+        }
+#pragma unroll
+        for (int k = 0; k < DPT; ++k) st_u32_volatile(my_state + k, SS_INCLUSIVE | (excl[k] + cnt[k]));
+    }
+#pragma unroll
+    for (int k = 0; k < DPT; ++k)
+        s.global_base[tid * DPT + k] = dglobal[k] + excl[k] - s.digit_start[tid * DPT + k];
     __syncthreads();
+
     // (d) scatter: consecutive local positions of one digit go to consecutive global addresses
 #pragma unroll
     for (int j = 0; j < SORT_ITEMS_PER_THREAD; ++j) {
@@ -254,23 +308,24 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, const int *__restrict__ v
     }
 }
 
-template <typename KeyT>
+template <typename KeyT, int RBITS>
 static int sort_pairs_typed(const KeyT *keys_in, const int *vals_in, KeyT *keys_out, int *vals_out,
                             const long long *n_dev, int64_t capacity, int end_bit, unsigned int *hist,
                             unsigned int *state, unsigned int *tickets, KeyT *tmp_keys, int *tmp_vals,
-                            long long *sel_out, cudaStream_t stream) {
-    const int passes = (end_bit + RADIX_BITS - 1) / RADIX_BITS;
+                            cudaStream_t stream) {
+    constexpr int RADIX = 1 << RBITS;
+    const int passes = (end_bit + RBITS - 1) / RBITS;
     const int blocks = (int)((capacity + SORT_TILE - 1) / SORT_TILE);
     if (blocks == 0 || passes == 0) return GSB_OK;
-    const size_t smem = sizeof(PassSmem<KeyT>) + 128;
+    const size_t smem = sizeof(PassSmem<KeyT, RBITS>) + 128;
     static bool attr_set = false;
     if (!attr_set) {
-        GSB_CUDA_CHECK(cudaFuncSetAttribute(onesweep_pass_kernel<KeyT>,
+        GSB_CUDA_CHECK(cudaFuncSetAttribute(onesweep_pass_kernel<KeyT, RBITS>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     int hist_blocks = blocks < 4 * num_sms() ? blocks : 4 * num_sms();
-    sort_histogram_kernel<KeyT><<<hist_blocks, 256, 0, stream>>>(keys_in, n_dev, capacity, passes, hist);
+    sort_histogram_kernel<KeyT, RBITS><<<hist_blocks, 256, 0, stream>>>(keys_in, n_dev, capacity, passes, hist);
     GSB_CUDA_CHECK(cudaGetLastError());
     // ping-pong: pass p reads src, writes dst.  We arrange that the LAST pass writes keys_out.
     const KeyT *src_k = keys_in;
@@ -279,14 +334,13 @@ static int sort_pairs_typed(const KeyT *keys_in, const int *vals_in, KeyT *keys_
         const bool last_to_out = ((passes - 1 - p) % 2) == 0;
         KeyT *dst_k = last_to_out ? keys_out : tmp_keys;
         int *dst_v = last_to_out ? vals_out : tmp_vals;
-        onesweep_pass_kernel<KeyT><<<blocks, SORT_BLOCK_THREADS, smem, stream>>>(
-            src_k, src_v, dst_k, dst_v, n_dev, capacity, p * RADIX_BITS, hist + p * RADIX,
+        onesweep_pass_kernel<KeyT, RBITS><<<blocks, SORT_BLOCK_THREADS, smem, stream>>>(
+            src_k, src_v, dst_k, dst_v, n_dev, capacity, p * RBITS, hist + p * RADIX,
             state + (size_t)p * blocks * RADIX, tickets + p);
         GSB_CUDA_CHECK(cudaGetLastError());
         src_k = dst_k;
         src_v = dst_v;
     }
-    (void)sel_out;
     return GSB_OK;
 }
 
@@ -298,16 +352,22 @@ int sort_pairs_device(const void *keys_in, const int *vals_in, void *keys_out, i
                       const long long *n_dev, int64_t n_capacity, int key_bytes, int end_bit,
                       unsigned int *hist, unsigned int *state, unsigned int *tickets, void *tmp_keys,
                       int *tmp_vals, long long *sel_out, cudaStream_t stream) {
+    (void)sel_out;
+    const int rbits = sort_radix_bits(end_bit);
+    typedef unsigned int u32;
+    typedef unsigned long long u64;
+    if (key_bytes == 4 && rbits == 8)
+        return sort_pairs_typed<u32, 8>((const u32 *)keys_in, vals_in, (u32 *)keys_out, vals_out, n_dev, n_capacity,
+                                        end_bit, hist, state, tickets, (u32 *)tmp_keys, tmp_vals, stream);
     if (key_bytes == 4)
-        return sort_pairs_typed<unsigned int>((const unsigned int *)keys_in, vals_in,
-                                              (unsigned int *)keys_out, vals_out, n_dev, n_capacity,
-                                              end_bit, hist, state, tickets, (unsigned int *)tmp_keys,
-                                              tmp_vals, sel_out, stream);
+        return sort_pairs_typed<u32, 10>((const u32 *)keys_in, vals_in, (u32 *)keys_out, vals_out, n_dev, n_capacity,
+                                         end_bit, hist, state, tickets, (u32 *)tmp_keys, tmp_vals, stream);
+    if (key_bytes == 8 && rbits == 8)
+        return sort_pairs_typed<u64, 8>((const u64 *)keys_in, vals_in, (u64 *)keys_out, vals_out, n_dev, n_capacity,
+                                        end_bit, hist, state, tickets, (u64 *)tmp_keys, tmp_vals, stream);
     if (key_bytes == 8)
-        return sort_pairs_typed<unsigned long long>(
-            (const unsigned long long *)keys_in, vals_in, (unsigned long long *)keys_out, vals_out, n_dev,
-            n_capacity, end_bit, hist, state, tickets, (unsigned long long *)tmp_keys, tmp_vals, sel_out,
-            stream);
+        return sort_pairs_typed<u64, 10>((const u64 *)keys_in, vals_in, (u64 *)keys_out, vals_out, n_dev, n_capacity,
+                                         end_bit, hist, state, tickets, (u64 *)tmp_keys, tmp_vals, stream);
     set_error("sort: key_bytes must be 4 or 8, got %d", key_bytes);
     return GSB_EINVAL;
 }
