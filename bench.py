@@ -293,6 +293,39 @@ def run_b200(args):
     fwd_ms = timed(fwd_only(op), steps) / steps
     fwd_rgb_ms = timed(fwd_only(op_rgb), steps) / steps
 
+    # ---- BASELINE config 2 (Truck-scale, 4.3e5 Gaussians, 976x544, fwd+bwd) as a side number
+    def side_config(name, k=10):
+        c = dict(CONFIGS[name])
+        sc2 = make_scene(**c).to(device)
+        sc2.point_cloud.requires_grad_(True)
+        sc2.point_cloud_features.requires_grad_(True)
+        inp2 = Input(point_cloud=sc2.point_cloud, point_cloud_features=sc2.point_cloud_features,
+                     point_object_id=sc2.point_object_id, point_invalid_mask=sc2.point_invalid_mask,
+                     camera_info=sc2.camera_info, q_pointcloud_camera=sc2.q_pointcloud_camera,
+                     t_pointcloud_camera=sc2.t_pointcloud_camera, color_max_sh_band=3)
+        g2 = torch.randn((c["height"], c["width"], 3), device=device)
+        op2 = GPCR(GPCR.GaussianPointCloudRasterisationConfig())
+
+        def st():
+            sc2.point_cloud.grad = None
+            sc2.point_cloud_features.grad = None
+            im, _, _ = op2(inp2)
+            im.backward(g2)
+
+        def fw():
+            with torch.no_grad():
+                op2(inp2)
+        for _ in range(3):
+            st()
+        ms = timed(st, k) / k
+        fms = timed(fw, k) / k
+        px = c["height"] * c["width"]
+        return {"fwd_bwd_ms": round(ms, 4), "fwd_bwd_Mpix_s": round(world * px / (ms * 1e-3) / 1e6, 1),
+                "fwd_ms": round(fms, 4), "fwd_Mpix_s": round(world * px / (fms * 1e-3) / 1e6, 1),
+                "N": c["num_points"], "HxW": f"{c['height']}x{c['width']}",
+                "M": op2.last_frame.num_points_in_camera, "K": op2.last_frame.num_keys}
+    side = {"C2": side_config("C2")} if args.workload == "C3" else {}
+
     # ---- per-kernel device times (CUDA events recorded inside the library on the launching stream)
     stage_ms = profiling.stage_times(op, dev_input, grad_image, iters=min(steps, 10))
 
@@ -360,6 +393,7 @@ def run_b200(args):
         "forward_only": {"Mpix_s": round(world * H * W / (fwd_ms * 1e-3) / 1e6, 2), "ms": round(fwd_ms, 4),
                          "rgb_only_Mpix_s": round(world * H * W / (fwd_rgb_ms * 1e-3) / 1e6, 2),
                          "rgb_only_ms": round(fwd_rgb_ms, 4)},
+        "other_configs": side,
         "gpu_launches": launches_per_step * steps,
         "clocks": clocks,
         "roofline": roofline,

@@ -258,6 +258,11 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
             def backward(ctx, grad_rasterized_image, grad_rasterized_depth, grad_pixel_valid_point_count):
                 grad_pointcloud = grad_pointcloud_features = None
                 if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:  # GPCR:1028
+                    if outer.config.rgb_only:
+                        # the reference leaves accumulated alpha / last-effective offsets uninitialised in
+                        # this mode (GPCR:478-484), so its backward is undefined; refuse instead
+                        raise RuntimeError("rgb_only=True is an inference-only mode: backward needs the "
+                                           "auxiliary per-pixel outputs")
                     grad_pointcloud, grad_pointcloud_features = outer._run_backward(ctx, grad_rasterized_image)
                 return grad_pointcloud, grad_pointcloud_features, None, None, None, None, None, None
 

@@ -4,6 +4,8 @@ rasteriser, a drop-in for the hot path of wanmeihuali/taichi_3d_gaussian_splatti
 ``torch.distributed``); every kernel is hand-written CUDA behind the C ABI in ``include/gsb200.h``.
 """
 from .Camera import CameraInfo, CameraView  # noqa: F401
+from .densification import GaussianPointAdaptiveController  # noqa: F401
+from .loss import LossFunction  # noqa: F401
 from .GaussianPointCloudRasterisation import (  # noqa: F401
     BOUNDARY_TILES,
     TILE_HEIGHT,
@@ -12,5 +14,6 @@ from .GaussianPointCloudRasterisation import (  # noqa: F401
     find_tile_start_and_end,
 )
 
-__all__ = ["CameraInfo", "CameraView", "GaussianPointCloudRasterisation", "find_tile_start_and_end",
+__all__ = ["CameraInfo", "CameraView", "GaussianPointCloudRasterisation", "GaussianPointAdaptiveController",
+           "LossFunction", "find_tile_start_and_end",
            "TILE_WIDTH", "TILE_HEIGHT", "BOUNDARY_TILES"]

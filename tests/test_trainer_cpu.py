@@ -1,0 +1,111 @@
+"""CPU tests of the §8(f) rows around the operator: SSIM restatement, densification controller logic, and
+the trainer loop driven by the ORACLE rasteriser (the CUDA operator cannot run here)."""
+import numpy as np
+import torch
+
+from taichi_3d_gaussian_splatting_b200 import GaussianPointAdaptiveController as Controller
+from taichi_3d_gaussian_splatting_b200 import GaussianPointCloudRasterisation as GPCR
+from taichi_3d_gaussian_splatting_b200.loss import LossFunction, ssim
+from taichi_3d_gaussian_splatting_b200.trainer import (GaussianPointCloudTrainer, downsample_image_and_camera_info)
+
+from oracle_module import OracleRasterisationModule
+from trainer_helpers import H, W, hidden_scene, initial_scene, render_views, train_config
+
+
+def _ssim_dense_f64(x, y):
+    """Independent SSIM: non-separable 11x11 window, explicit loops over output pixels, float64."""
+    x, y = x.double().numpy(), y.double().numpy()
+    k = np.arange(11) - 5
+    g = np.exp(-k ** 2 / (2 * 1.5 ** 2))
+    g /= g.sum()
+    w2 = np.outer(g, g)
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    vals = []
+    for c in range(x.shape[0]):
+        acc = []
+        for i in range(x.shape[1] - 10):
+            for j in range(x.shape[2] - 10):
+                a, b = x[c, i:i + 11, j:j + 11], y[c, i:i + 11, j:j + 11]
+                mu1, mu2 = (w2 * a).sum(), (w2 * b).sum()
+                s1, s2 = (w2 * a * a).sum() - mu1 ** 2, (w2 * b * b).sum() - mu2 ** 2
+                s12 = (w2 * a * b).sum() - mu1 * mu2
+                acc.append((2 * mu1 * mu2 + C1) * (2 * s12 + C2) / ((mu1 ** 2 + mu2 ** 2 + C1) * (s1 + s2 + C2)))
+        vals.append(np.mean(acc))
+    return float(np.mean(vals))
+
+
+def test_ssim_matches_dense_reference_and_basic_properties():
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand((1, 3, 24, 30), generator=g)
+    y = (x + 0.1 * torch.randn(x.shape, generator=g)).clamp(0, 1)
+    assert abs(float(ssim(x, x)) - 1.0) < 1e-6
+    assert abs(float(ssim(x, y)) - float(ssim(y, x))) < 1e-6
+    assert abs(float(ssim(x, y)) - _ssim_dense_f64(x[0], y[0])) < 1e-5
+    loss, l1, ld = LossFunction(LossFunction.LossFunctionConfig(enable_regularization=False))(x[0], y[0])
+    assert abs(float(loss) - (0.8 * float(l1) + 0.2 * float(ld))) < 1e-6 and abs(float(ld) - (1 - float(ssim(x, y)))) < 1e-6
+
+
+def test_downsample_crops_to_multiples_of_16():
+    from taichi_3d_gaussian_splatting_b200 import CameraInfo
+    K = torch.tensor([[600.0, 0, 488], [0, 600.0, 272], [0, 0, 1]])
+    img, cam = downsample_image_and_camera_info(torch.rand(3, 544, 976), CameraInfo(K, 544, 976, 0), 4)
+    assert (cam.camera_height, cam.camera_width) == (128, 240) and img.shape == (3, 128, 240)
+    assert torch.allclose(cam.camera_intrinsics, torch.tensor([[150.0, 0, 122], [0, 150.0, 68], [0, 0, 1]]))
+
+
+def _hook_input(ids, n_pixels, mag, depth=None):
+    m = len(ids)
+    return GPCR.BackwardValidPointHookInput(
+        point_id_in_camera_list=torch.tensor(ids, dtype=torch.int32), grad_point_in_camera=torch.ones(m, 3) * 0.01,
+        grad_pointfeatures_in_camera=torch.zeros(m, 56), grad_viewspace=torch.zeros(m, 2),
+        magnitude_grad_viewspace=torch.tensor(mag, dtype=torch.float32), magnitude_grad_viewspace_on_image=torch.zeros(16, 16, 2),
+        num_overlap_tiles=torch.ones(m, dtype=torch.int32), num_affected_pixels=torch.tensor(n_pixels, dtype=torch.int32),
+        point_depth=torch.full((m,), 5.0) if depth is None else torch.tensor(depth), point_uv_in_camera=torch.zeros(m, 2))
+
+
+def test_controller_densify_prune_and_reset():
+    n = 10
+    pc = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3)
+    feat = torch.zeros(n, 56)
+    feat[:, 3] = 1.0
+    feat[:, 7] = torch.tensor([1.0, 1.0, -3.0, 1.0, 1.0, 0, 0, 0, 0, 0])  # point 2 is transparent
+    mask = torch.tensor([0, 0, 0, 0, 0, 1, 1, 1, 1, 1], dtype=torch.int8)
+    cfg = Controller.GaussianPointAdaptiveControllerConfig(
+        num_iterations_warm_up=0, num_iterations_densify=1, transparent_alpha_threshold=-2.0,
+        densification_view_space_position_gradients_threshold=1e-3, under_reconstructed_num_pixels_threshold=100,
+        num_iterations_reset_alpha=1, reset_alpha_value=0.2, iteration_start_remove_floater=10 ** 9)
+    ctl = Controller(cfg, Controller.GaussianPointAdaptiveControllerMaintainedParameters(
+        pointcloud=pc, pointcloud_features=feat, point_invalid_mask=mask, point_object_id=torch.zeros(n, dtype=torch.int32)),
+        generator=torch.Generator().manual_seed(0))
+    # points 0 (large, over-reconstructed -> split) and 1 (small -> clone) have big view-space gradients
+    ctl.update(_hook_input([0, 1, 2, 3], [500, 10, 5, 50], [0.5, 0.2, 0.9, 1e-6]))
+    info = ctl.densify_point_info
+    assert info.densify_point_id.tolist() == [0, 1] and info.transparent_point_id.tolist() == [2]
+    assert np.allclose(info.densify_size_reduction_factor.reshape(-1).tolist(), [np.log(1.6), 0.0])
+    before = pc.clone()
+    ctl.refinement()
+    assert mask.tolist() == [0, 0, 0, 0, 0, 0, 1, 1, 1, 1]  # point 2 pruned then re-used, slot 5 filled
+    assert torch.allclose(feat[0, 4:7], torch.full((3,), -float(np.log(1.6)))) and torch.allclose(feat[2, 4:7], feat[0, 4:7])
+    assert torch.allclose(feat[5, 4:7], torch.zeros(3)) and torch.allclose(feat[1, 4:7], torch.zeros(3))  # clone keeps size
+    assert not torch.allclose(pc[0], before[0]) and not torch.allclose(pc[2], before[0])  # both halves of a split are re-sampled
+    assert torch.allclose(pc[5], before[1] + 0.01 * cfg.under_reconstructed_move_factor)  # clone moved along the mean xyz gradient
+    assert float(feat[:, 7].max()) <= 0.2 + 1e-6  # alpha reset
+    assert int(ctl.accumulated_num_in_camera.sum()) == 0  # accumulators cleared
+
+
+def test_trainer_loop_with_oracle_reduces_loss_and_densifies():
+    """Mirrors the reference's 'loss must go down' integration tests
+    (tests/GaussianPointCloudRasterisation_test.py:284-351, tests/GaussianPointAdaptiveController_test.py:14-95)
+    on the trainer harness, with the oracle as rasteriser."""
+    hidden = hidden_scene(n=250)
+    views = render_views(OracleRasterisationModule(GPCR.GaussianPointCloudRasterisationConfig()), hidden)
+    scene = initial_scene(hidden)
+    trainer = GaussianPointCloudTrainer(train_config(100, densify=True), scene, views,
+                                        rasterisation_factory=OracleRasterisationModule,
+                                        generator=torch.Generator().manual_seed(1))
+    psnr0 = trainer.validation()
+    hist = trainer.train(log_interval=1)
+    psnr1 = trainer.validation()
+    assert psnr1 > psnr0 + 2.0, (psnr0, psnr1)
+    assert np.mean([h["loss"] for h in hist[-8:]]) < 0.8 * np.mean([h["loss"] for h in hist[:8]])
+    assert hist[-1]["num_valid_points"] > hist[0]["num_valid_points"]  # densification added points
