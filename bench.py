@@ -293,6 +293,41 @@ def run_b200(args):
     fwd_ms = timed(fwd_only(op), steps) / steps
     fwd_rgb_ms = timed(fwd_only(op_rgb), steps) / steps
 
+    # ---- inference e2e through the C ABI with HOST buffers (gsb200_render_host): pose + intrinsics H2D,
+    #      forward (rgb_only), image D2H into pinned memory, every frame
+    def render_host_e2e(k):
+        import ctypes
+        from taichi_3d_gaussian_splatting_b200 import _lib
+        lib = _lib.load()
+        fr = op_rgb.last_frame
+        ws = torch.empty(fr.layout.total_bytes, dtype=torch.uint8, device=device)
+        img_dev = torch.empty((H, W, 3), device=device)
+        aux_f = torch.empty((H, W), device=device)
+        aux_i = torch.empty((H, W), dtype=torch.int32, device=device)
+        cfgr = op_rgb.config
+        a = _lib.GsbForwardArgs(
+            num_points=N, pointcloud=scene.point_cloud.data_ptr(), pointcloud_features=scene.point_cloud_features.data_ptr(),
+            point_invalid_mask=scene.point_invalid_mask.data_ptr(), point_object_id=scene.point_object_id.data_ptr(),
+            num_objects=1, camera_height=H, camera_width=W, near_plane=cfgr.near_plane, far_plane=cfgr.far_plane,
+            depth_to_sort_key_scale=cfgr.depth_to_sort_key_scale, rgb_only=1, flags=fr.flags, workspace=ws.data_ptr(),
+            workspace_bytes=fr.layout.total_bytes, key_capacity=fr.key_capacity, rasterized_image=img_dev.data_ptr(),
+            rasterized_depth=aux_f.data_ptr(), pixel_accumulated_alpha=aux_f.data_ptr(),
+            pixel_offset_of_last_effective_point=aux_i.data_ptr(), pixel_valid_point_count=aux_i.data_ptr(),
+            stream=torch.cuda.current_stream(device).cuda_stream)
+        staging = torch.empty(32, device=device)
+        image_host = torch.empty((H, W, 3)).pin_memory()
+
+        def one():
+            _lib.check(lib.gsb200_render_host(ctypes.byref(a), q_host.data_ptr(), t_host.data_ptr(), K_host.data_ptr(),
+                                              staging.data_ptr(), image_host.data_ptr(), None), "gsb200_render_host")
+        for _ in range(3):
+            one()
+        ms = timed(one, k) / k
+        return {"ms": round(ms, 4), "Mpix_s": round(world * H * W / (ms * 1e-3) / 1e6, 1),
+                "h2d_bytes_per_frame": 64, "d2h_bytes_per_frame": H * W * 3 * 4,
+                "what": "gsb200_render_host: host pose/intrinsics in, forward (rgb_only), image to pinned host memory"}
+    render_host = render_host_e2e(steps)
+
     # ---- BASELINE config 2 (Truck-scale, 4.3e5 Gaussians, 976x544, fwd+bwd) as a side number
     def side_config(name, k=10):
         c = dict(CONFIGS[name])
@@ -400,6 +435,7 @@ def run_b200(args):
         "forward_only": {"Mpix_s": round(world * H * W / (fwd_ms * 1e-3) / 1e6, 2), "ms": round(fwd_ms, 4),
                          "rgb_only_Mpix_s": round(world * H * W / (fwd_rgb_ms * 1e-3) / 1e6, 2),
                          "rgb_only_ms": round(fwd_rgb_ms, 4)},
+        "forward_e2e_c_abi": render_host,
         "other_configs": side,
         "gpu_launches": launches_per_step * steps,
         "clocks": clocks,

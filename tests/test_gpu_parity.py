@@ -302,3 +302,45 @@ def test_c2_full_size_statistical_parity_and_properties():
     image2, _, _ = run_forward(op, sc, band=3)
     image2.backward(2.0 * grad_image.cuda())
     assert np.allclose(n(sc.point_cloud.grad), 2.0 * gx, rtol=1e-3, atol=1e-4 * np.abs(gx).max())
+
+
+def test_render_host_c_abi_entry_point():
+    """gsb200_render_host: scene resident on the device, pose + intrinsics from HOST memory, image back in HOST
+    memory (the render-loop body of gaussian_point_render.py:106-121) -- must equal the operator's image."""
+    import ctypes
+    from taichi_3d_gaussian_splatting_b200 import _lib
+    scene = _small_scene(81)
+    sc = cuda_scene(scene)
+    op = make_op(exact_exp=True)
+    image, depth, count = run_forward(op, sc)
+    frame = op.last_frame
+    H, W, N = frame.height, frame.width, sc.point_cloud.shape[0]
+    lib = _lib.load()
+    ws = torch.empty(frame.layout.total_bytes, dtype=torch.uint8, device="cuda")
+    out = [torch.empty((H, W, 3), device="cuda"), torch.empty((H, W), device="cuda"), torch.empty((H, W), device="cuda"),
+           torch.empty((H, W), dtype=torch.int32, device="cuda"), torch.empty((H, W), dtype=torch.int32, device="cuda")]
+    cfg = op.config
+    args = _lib.GsbForwardArgs(
+        num_points=N, pointcloud=sc.point_cloud.data_ptr(), pointcloud_features=sc.point_cloud_features.data_ptr(),
+        point_invalid_mask=sc.point_invalid_mask.data_ptr(), point_object_id=sc.point_object_id.data_ptr(), num_objects=1,
+        camera_height=H, camera_width=W, near_plane=cfg.near_plane, far_plane=cfg.far_plane,
+        depth_to_sort_key_scale=cfg.depth_to_sort_key_scale, rgb_only=0, flags=frame.flags, workspace=ws.data_ptr(),
+        workspace_bytes=frame.layout.total_bytes, key_capacity=frame.key_capacity, rasterized_image=out[0].data_ptr(),
+        rasterized_depth=out[1].data_ptr(), pixel_accumulated_alpha=out[2].data_ptr(),
+        pixel_offset_of_last_effective_point=out[3].data_ptr(), pixel_valid_point_count=out[4].data_ptr(),
+        stream=torch.cuda.current_stream().cuda_stream)
+    q_host = scene.q_pointcloud_camera.clone().pin_memory()
+    t_host = scene.t_pointcloud_camera.clone().pin_memory()
+    K_host = scene.camera_info.camera_intrinsics.clone().pin_memory()
+    staging = torch.empty(32, device="cuda")
+    image_host = torch.empty((H, W, 3)).pin_memory()
+    counters = torch.zeros(4, dtype=torch.int64).pin_memory()
+    rc = lib.gsb200_render_host(ctypes.byref(args), q_host.data_ptr(), t_host.data_ptr(), K_host.data_ptr(),
+                                staging.data_ptr(), image_host.data_ptr(), counters.data_ptr())
+    _lib.check(rc, "gsb200_render_host")
+    # the first forward already normalised q in place; normalising again may move q by an ulp
+    assert torch.allclose(image_host, image.cpu(), atol=1e-5)
+    assert counters[0].item() == frame.num_points_in_camera and counters[1].item() == frame.num_keys and counters[2].item() == 0
+    # error convention: bad arguments return a negative code and a message, never throw
+    assert lib.gsb200_render_host(None, None, None, None, None, None, None) < 0
+    assert b"null" in lib.gsb200_last_error()
