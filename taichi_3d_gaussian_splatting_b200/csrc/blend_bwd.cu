@@ -80,8 +80,14 @@ __device__ __forceinline__ void warp_transpose_reduce16(float (&v)[16], int lane
 }
 
 
+#ifndef GSB_BWD_BRANCHFREE
+#define GSB_BWD_BRANCHFREE 1
+#endif
+#ifndef GSB_BWD_MIN_BLOCKS
+#define GSB_BWD_MIN_BLOCKS 4
+#endif
 template <bool EXACT_EXP>
-__global__ void __launch_bounds__(GSB_TILE_PIXELS)
+__global__ void __launch_bounds__(GSB_TILE_PIXELS, GSB_BWD_MIN_BLOCKS)
 blend_backward_kernel(const BlendBwdParams p) {
     // double-buffered staging area: [buf][plane][splat]; planes: u v a b | c rescale opacity depth | r g b radius
     __shared__ float4 s_rec[2 * 3 * GSB_TILE_PIXELS];
@@ -155,9 +161,59 @@ blend_backward_kernel(const BlendBwdParams p) {
                     const int idx = block_end - 1 - j;
                     if (idx >= warp_last) continue;  // warp-uniform
                     float v[16];
+                    bool contributes;
+#if GSB_BWD_BRANCHFREE
+                    // Branch-free: every lane evaluates the splat; lanes that do not contribute (behind their
+                    // last effective splat, or alpha < 1/255) get zero weights, so all partials vanish and the
+                    // pixel state is left untouched by predicated selects.
+                    {
+                        const unsigned int ja = sb + j * 16;
+                        const float4 r0 = lds128<0>(ja);          // u v a b
+                        const float4 r1 = lds128<PLANE>(ja);      // c rescale opacity depth
+                        const float4 r2 = lds128<2 * PLANE>(ja);  // r g b radius
+                        const float d0 = px - r0.x, d1 = py - r0.y;
+                        const float q0 = r0.z * d0 + r0.w * d1;
+                        const float q1 = r0.w * d0 + r1.x * d1;
+                        float gp;
+                        if (EXACT_EXP) gp = expf(-0.5f * (d0 * q0 + d1 * q1)) * r1.y;
+                        else gp = ex2_approx_b(-0.72134752044448170368f * (d0 * q0 + d1 * q1)) * r1.y;
+                        const float opa = r1.z;
+                        const float prod_alpha = gp * opa;
+                        contributes = (idx < last) && (prod_alpha >= 1.0f / 255.0f);
+                        const float alpha = fminf(prod_alpha, 0.99f);
+                        const float inv = EXACT_EXP ? 1.0f / (1.0f - alpha) : rcp_approx(1.0f - alpha);
+                        const float Tn = T * inv;
+                        const float aT = contributes ? alpha * Tn : 0.0f;
+                        const float a_grad = contributes ? (r2.x * Tn - w0 * inv) * g0 + (r2.y * Tn - w1 * inv) * g1 +
+                                                               (r2.z * Tn - w2 * inv) * g2
+                                                         : 0.0f;
+                        T = contributes ? Tn : T;
+                        w0 = fmaf(r2.x, aT, w0);
+                        w1 = fmaf(r2.y, aT, w1);
+                        w2 = fmaf(r2.z, aT, w2);
+                        const float G = a_grad * opa * gp;
+                        const float vs0 = G * q0, vs1 = G * q1;
+                        mag0 += fabsf(vs0);
+                        mag1 += fabsf(vs1);
+                        const float hq0 = 0.5f * G * q0;
+                        v[0] = vs0;
+                        v[1] = vs1;
+                        v[2] = hq0 * q0;
+                        v[3] = hq0 * q1;
+                        v[4] = 0.5f * G * q1 * q1;
+                        v[5] = aT * g0;
+                        v[6] = aT * g1;
+                        v[7] = aT * g2;
+                        v[8] = a_grad * gp * (1.0f - opa) * opa;
+                        v[9] = EXACT_EXP ? sqrtf(vs0 * vs0 + vs1 * vs1) : sqrt_approx(vs0 * vs0 + vs1 * vs1);
+                        v[10] = contributes ? 1.0f : 0.0f;
+#pragma unroll
+                        for (int k = 11; k < 16; ++k) v[k] = 0.0f;
+                    }
+#else
 #pragma unroll
                     for (int k = 0; k < 16; ++k) v[k] = 0.0f;
-                    bool contributes = false;
+                    contributes = false;
                     if (idx < last) {
                         const unsigned int ja = sb + j * 16;
                         const float4 r0 = lds128<0>(ja);      // u v a b
@@ -201,6 +257,7 @@ blend_backward_kernel(const BlendBwdParams p) {
                             v[10] = 1.0f;                              // affected-pixel count
                         }
                     }
+#endif
                     if (__any_sync(0xffffffffu, contributes)) {
                         // 11 partials of this (warp, splat) -> 11 lanes -> one RED.ADD.F32 row update
                         warp_transpose_reduce16(v, lane);
@@ -260,7 +317,10 @@ struct PointsBwdParams {
     float *grad_feat;
 };
 
-__global__ void __launch_bounds__(128)
+#ifndef GSB_POINTS_THREADS
+#define GSB_POINTS_THREADS 256
+#endif
+__global__ void __launch_bounds__(GSB_POINTS_THREADS)
 backward_points_kernel(const PointsBwdParams p) {
     // One thread per scene row: rows outside the frustum get their zeros here (no separate memset of the
     // dense (N,3)/(N,56) gradients), rows inside get the chain rule.
@@ -423,11 +483,11 @@ int launch_backward_points(const GsbBackwardArgs &a, const Workspace &ws, cudaSt
     p.h_f = a.grad_high_order_color_factor;
     p.grad_xyz = a.grad_pointcloud;
     p.grad_feat = a.grad_pointcloud_features;
-    long long blocks = (a.num_points + 127) / 128;
+    long long blocks = (a.num_points + GSB_POINTS_THREADS - 1) / GSB_POINTS_THREADS;
     const long long cap = 16LL * num_sms();
     if (blocks > cap) blocks = cap;
     if (blocks <= 0) return GSB_OK;
-    backward_points_kernel<<<(int)blocks, 128, 0, stream>>>(p);
+    backward_points_kernel<<<(int)blocks, GSB_POINTS_THREADS, 0, stream>>>(p);
     GSB_CUDA_CHECK(cudaGetLastError());
     return GSB_OK;
 }

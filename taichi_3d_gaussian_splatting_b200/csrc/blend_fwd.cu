@@ -32,8 +32,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+#ifndef GSB_FWD_MIN_BLOCKS
+#define GSB_FWD_MIN_BLOCKS 5
+#endif
 template <bool RGB_ONLY, bool EXACT_EXP>
-__global__ void __launch_bounds__(GSB_TILE_PIXELS, 5)
+__global__ void __launch_bounds__(GSB_TILE_PIXELS, GSB_FWD_MIN_BLOCKS)
 blend_forward_kernel(const BlendFwdParams p) {
     // double-buffered staging area: [buf][plane][splat]; planes: u v a b | c rescale opacity depth | r g b radius
     __shared__ float4 s_rec[2 * 3 * GSB_TILE_PIXELS];

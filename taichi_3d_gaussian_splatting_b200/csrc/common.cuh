@@ -80,12 +80,15 @@ int sort_pairs_device(const void *keys_in, const int *vals_in, void *keys_out, i
 #define GSB_SORT_ITEMS 16
 #endif
 #ifndef GSB_SORT_MIN_BLOCKS
-#define GSB_SORT_MIN_BLOCKS 2
+#define GSB_SORT_MIN_BLOCKS 3
 #endif
 constexpr int SORT_BLOCK_THREADS = 256;
 constexpr int SORT_ITEMS_PER_THREAD = GSB_SORT_ITEMS;
 constexpr int SORT_TILE = SORT_BLOCK_THREADS * SORT_ITEMS_PER_THREAD;  // 4096 keys per CTA
-constexpr int SCAN_BLOCK_THREADS = 256;
+#ifndef GSB_SCAN_THREADS
+#define GSB_SCAN_THREADS 256
+#endif
+constexpr int SCAN_BLOCK_THREADS = GSB_SCAN_THREADS;
 
 // ---- per-warp culling shared by the forward and backward blend kernels.
 // A CTA renders a 16x16 tile with 8 warps; warp w owns the 8x4 pixel patch at ((w & 1) * 8, (w >> 1) * 4).

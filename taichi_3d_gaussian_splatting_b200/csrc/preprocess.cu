@@ -142,7 +142,7 @@ __device__ __forceinline__ void bounding_box(float u, float v, float radii, int 
 }
 
 #ifndef GSB_PRE_MIN_BLOCKS
-#define GSB_PRE_MIN_BLOCKS 4
+#define GSB_PRE_MIN_BLOCKS 5
 #endif
 template <typename KeyT>
 __global__ void __launch_bounds__(SCAN_BLOCK_THREADS, GSB_PRE_MIN_BLOCKS)

@@ -17,7 +17,10 @@ namespace gsb {
 constexpr unsigned int SS_AGGREGATE = 1u << 30;
 constexpr unsigned int SS_INCLUSIVE = 2u << 30;
 constexpr unsigned int SS_VALUE_MASK = (1u << 30) - 1;
-constexpr int MAX_RADIX = 1024;  // 8-bit or 10-bit digits; 10 bits when that saves a pass (e.g. 30-bit keys: 3 vs 4)
+#ifndef GSB_SORT_LOOKBACK
+#define GSB_SORT_LOOKBACK 4
+#endif
+constexpr int LOOKBACK = GSB_SORT_LOOKBACK;  // predecessors whose state is fetched per look-back round
 
 // Digit width for a key of `bits` live bits.  The kernels are templated on 8- and 10-bit digits; measured on
 // B200 (C3, 30-bit keys, K = 4.0e6) three 10-bit passes cost 244 us against 199 us for four 8-bit passes
@@ -263,15 +266,15 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, const int *__restrict__ v
         long long look = (long long)blk - 1;
         bool all_done = false;
         while (!all_done) {
-            unsigned int w[4][DPT];
+            unsigned int w[LOOKBACK][DPT];
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
+            for (int r = 0; r < LOOKBACK; ++r)
 #pragma unroll
                 for (int k = 0; k < DPT; ++k)
                     w[r][k] = (look - r >= 0) ? ld_u32_volatile(state + (size_t)(look - r) * RADIX + tid * DPT + k)
                                               : SS_INCLUSIVE;
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
+            for (int r = 0; r < LOOKBACK; ++r) {
 #pragma unroll
                 for (int k = 0; k < DPT; ++k) {
                     if (done[k]) continue;
@@ -284,7 +287,7 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, const int *__restrict__ v
             all_done = true;
 #pragma unroll
             for (int k = 0; k < DPT; ++k) all_done = all_done && done[k];
-            look -= 4;
+            look -= LOOKBACK;
         }
 #pragma unroll
         for (int k = 0; k < DPT; ++k) st_u32_volatile(my_state + k, SS_INCLUSIVE | (excl[k] + cnt[k]));
