@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -231,7 +231,6 @@ def run_b200(args):
         sampler.start()
         time.sleep(0.15)
     total_ms = timed(step_resident, steps)
-    clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / steps
     value = world * H * W / (ms_per_step * 1e-3) / 1e6
     frame = op.last_frame
@@ -360,6 +359,9 @@ def run_b200(args):
                 "N": c["num_points"], "HxW": f"{c['height']}x{c['width']}",
                 "M": op2.last_frame.num_points_in_camera, "K": op2.last_frame.num_keys}
     side = {"C2": side_config("C2")} if args.workload == "C3" else {}
+
+    # clocks were sampled from the start of the headline region to here (all timed regions of this run)
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel device times (CUDA events recorded inside the library on the launching stream)
     stage_ms = profiling.stage_times(op, dev_input, grad_image, iters=min(steps, 10))

@@ -143,110 +143,108 @@ class GaussianPointAdaptiveController:
                 self.reset_alpha()
             self.input_data = None
 
-    # GaussianPointAdaptiveController.py:170-270
-    def _find_densify_points(self, input_data):
-        cfg = self.config
-        mp = self.maintained_parameters
-        pointcloud, features = mp.pointcloud, mp.pointcloud_features
-        point_id_list = torch.arange(pointcloud.shape[0], device=pointcloud.device)
-        ids_in_camera = input_data.point_id_in_camera_list.long()
-        num_affected_pixels = input_data.num_affected_pixels
-        point_depth = input_data.point_depth
-        average_num_affect_pixels = self.accumulated_num_pixels / self.accumulated_num_in_camera
-        average_num_affect_pixels[torch.isnan(average_num_affect_pixels)] = 0
+    # ---- selection (reference: GaussianPointAdaptiveController.py:170-270, without the debug plot)
+    @staticmethod
+    def _safe_div(num: torch.Tensor, den: torch.Tensor) -> torch.Tensor:
+        """num / den with 0/0 -> 0 (the reference overwrites NaNs after the division)."""
+        out = num / den
+        return torch.where(torch.isnan(out), torch.zeros_like(out), out)
 
-        floater_mask = torch.zeros_like(point_id_list, dtype=torch.bool)
-        floater_mask_in_camera = torch.zeros_like(ids_in_camera, dtype=torch.bool)
-        floater_point_id = torch.empty(0, dtype=torch.int64, device=pointcloud.device)
+    def _removal_masks(self, hook, ids):
+        """(floater mask over all points, floater mask over in-camera points, floater ids, transparent mask)."""
+        cfg, mp = self.config, self.maintained_parameters
+        n = mp.pointcloud.shape[0]
+        dev = mp.pointcloud.device
+        alive = mp.point_invalid_mask == 0
+        floaters_all = torch.zeros(n, dtype=torch.bool, device=dev)
+        floaters_cam = torch.zeros(ids.shape[0], dtype=torch.bool, device=dev)
+        floater_ids = torch.empty(0, dtype=torch.int64, device=dev)
         if self.iteration_counter > cfg.iteration_start_remove_floater:
-            floater_mask_in_camera = (num_affected_pixels > cfg.floater_near_camrea_num_pixels_threshold) & \
-                (point_depth < cfg.floater_depth_threshold)
-            floater_point_id = ids_in_camera[floater_mask_in_camera]
-            floater_mask[floater_point_id] = True
-            floater_mask = floater_mask & (mp.point_invalid_mask == 0)
+            floaters_cam = (hook.num_affected_pixels > cfg.floater_near_camrea_num_pixels_threshold) & \
+                (hook.point_depth < cfg.floater_depth_threshold)
+            floater_ids = ids[floaters_cam]
+            floaters_all[floater_ids] = True
+            floaters_all &= alive
+        broken = torch.isnan(mp.pointcloud_features).any(dim=1)
+        transparent = ((mp.pointcloud_features[:, 7] < cfg.transparent_alpha_threshold) | broken) & alive & ~floaters_all
+        return floaters_all, floaters_cam, floater_ids, transparent
 
-        point_alpha = features[:, 7]
-        nan_mask = torch.isnan(features).any(dim=1)
-        transparent_point_mask = ((point_alpha < cfg.transparent_alpha_threshold) | nan_mask) & \
-            (mp.point_invalid_mask == 0) & (~floater_mask)
-        transparent_point_id = point_id_list[transparent_point_mask]
-        will_be_remove_mask = floater_mask | transparent_point_mask
+    def _find_densify_points(self, hook):
+        cfg, mp = self.config, self.maintained_parameters
+        n = mp.pointcloud.shape[0]
+        dev = mp.pointcloud.device
+        ids = hook.point_id_in_camera_list.long()
+        floaters_all, floaters_cam, floater_ids, transparent = self._removal_masks(hook, ids)
+        doomed = floaters_all | transparent
+        doomed_cam = floaters_cam | transparent[ids]
 
-        in_camera_will_be_remove_mask = floater_mask_in_camera | transparent_point_mask[ids_in_camera]
-        grad_viewspace_norm = input_data.magnitude_grad_viewspace
-        in_camera_to_densify_mask = grad_viewspace_norm > cfg.densification_view_space_position_gradients_threshold
-        in_camera_to_densify_mask &= ~in_camera_will_be_remove_mask
-        in_camera_to_densify_mask |= (grad_viewspace_norm / num_affected_pixels >
-                                      cfg.densification_view_avg_space_position_gradients_threshold)
-        in_camera_to_densify_mask &= ~in_camera_will_be_remove_mask
+        # this frame: large view-space gradient, or large gradient per covered pixel
+        mag = hook.magnitude_grad_viewspace
+        pick_cam = (mag > cfg.densification_view_space_position_gradients_threshold) & ~doomed_cam
+        pick_cam |= (mag / hook.num_affected_pixels) > cfg.densification_view_avg_space_position_gradients_threshold
+        pick_cam &= ~doomed_cam
+        picked = torch.zeros(n, dtype=torch.bool, device=dev)
+        picked[ids[pick_cam]] = True
 
-        single_frame_mask = torch.zeros_like(point_id_list, dtype=torch.bool)
-        single_frame_mask[ids_in_camera[in_camera_to_densify_mask]] = True
+        # since the last refinement: the same statistics averaged over the frames a point was seen in
+        seen = self.accumulated_num_in_camera
+        mean_pixels = self._safe_div(self.accumulated_num_pixels, seen)
+        picked |= self._safe_div(self.accumulated_view_space_position_gradients, seen) > \
+            cfg.densification_multi_frame_view_space_position_gradients_threshold
+        picked |= (self._safe_div(self.accumulated_view_space_position_gradients_avg, seen) / mean_pixels) > \
+            cfg.densification_multi_frame_view_pixel_avg_space_position_gradients_threshold
+        picked |= (self.accumulated_position_gradients_norm / seen) > \
+            cfg.densification_multi_frame_position_gradients_threshold
+        picked &= ~doomed
+        chosen = torch.nonzero(picked).reshape(-1)
 
-        mf_view = self.accumulated_view_space_position_gradients / self.accumulated_num_in_camera
-        mf_view[torch.isnan(mf_view)] = 0
-        multi_frame_mask = mf_view > cfg.densification_multi_frame_view_space_position_gradients_threshold
-        mf_avg = self.accumulated_view_space_position_gradients_avg / self.accumulated_num_in_camera
-        mf_avg[torch.isnan(mf_avg)] = 0
-        multi_frame_mask |= (mf_avg / average_num_affect_pixels >
-                             cfg.densification_multi_frame_view_pixel_avg_space_position_gradients_threshold)
-        mf_pos = self.accumulated_position_gradients_norm / self.accumulated_num_in_camera
-        multi_frame_mask |= mf_pos > cfg.densification_multi_frame_position_gradients_threshold
-        to_densify_mask = (single_frame_mask | multi_frame_mask) & (~will_be_remove_mask)
-        densify_point_id = point_id_list[to_densify_mask]
-
-        position_before = pointcloud[densify_point_id].detach().clone()
-        grad_position = self.accumulated_position_gradients[densify_point_id] / \
-            self.accumulated_num_in_camera[densify_point_id].unsqueeze(-1)
-        grad_position[torch.isnan(grad_position)] = 0
-        reduction = torch.zeros_like(densify_point_id, dtype=torch.float32)
-        over_reconstructed = self.accumulated_num_pixels[to_densify_mask] > cfg.under_reconstructed_num_pixels_threshold
-        reduction[over_reconstructed] = float(np.log(cfg.gaussian_split_factor_phi))
+        mean_grad = self._safe_div(self.accumulated_position_gradients[chosen], seen[chosen].unsqueeze(-1))
+        shrink = torch.zeros(chosen.shape[0], dtype=torch.float32, device=dev)
+        # "over-reconstructed" (covers many pixels) -> split: both halves shrink by phi; otherwise clone
+        shrink[self.accumulated_num_pixels[picked] > cfg.under_reconstructed_num_pixels_threshold] = \
+            float(np.log(cfg.gaussian_split_factor_phi))
         self.densify_point_info = GaussianPointAdaptiveController.GaussianPointAdaptiveControllerDensifyPointInfo(
-            floater_point_id=floater_point_id, transparent_point_id=transparent_point_id,
-            densify_point_id=densify_point_id, densify_point_position_before_optimization=position_before,
-            densify_size_reduction_factor=reduction.unsqueeze(-1), densify_point_grad_position=grad_position)
+            floater_point_id=floater_ids, transparent_point_id=torch.nonzero(transparent).reshape(-1),
+            densify_point_id=chosen, densify_point_position_before_optimization=mp.pointcloud[chosen].detach().clone(),
+            densify_size_reduction_factor=shrink.unsqueeze(-1), densify_point_grad_position=mean_grad)
 
-    # GaussianPointAdaptiveController.py:290-353
+    # ---- application (reference: GaussianPointAdaptiveController.py:290-353)
     def _add_densify_points(self):
         assert self.densify_point_info is not None
         cfg, mp, info = self.config, self.maintained_parameters, self.densify_point_info
-        valid_before = int(mp.point_invalid_mask.shape[0] - mp.point_invalid_mask.sum())
-        num_transparent = info.transparent_point_id.shape[0]
-        mp.point_invalid_mask[info.transparent_point_id] = 1
-        num_floaters = info.floater_point_id.shape[0]
-        mp.point_invalid_mask[info.floater_point_id] = 1
-        num_densify = info.densify_point_id.shape[0]
-        to_fill = torch.where(mp.point_invalid_mask == 1)[0][:num_densify]
-        n_fill = 0
-        if num_densify > 0:
-            n_fill = min(num_densify, to_fill.shape[0])
-            src = info.densify_point_id[:n_fill]
-            mp.pointcloud[to_fill] = info.densify_point_position_before_optimization[:n_fill]
-            mp.pointcloud_features[to_fill] = mp.pointcloud_features[src]
-            mp.point_object_id[to_fill] = mp.point_object_id[src]
-            mp.pointcloud_features[to_fill, 4:7] -= info.densify_size_reduction_factor[:n_fill]
-            over = (info.densify_size_reduction_factor[:n_fill] > 1e-6).reshape(-1)
-            under = ~over
-            mp.pointcloud_features[src, 4:7] -= info.densify_size_reduction_factor[:n_fill]
+        xyz, feat, invalid = mp.pointcloud, mp.pointcloud_features, mp.point_invalid_mask
+        alive_before = int((invalid == 0).sum())
+        invalid[info.transparent_point_id] = 1
+        invalid[info.floater_point_id] = 1
+        wanted = info.densify_point_id.shape[0]
+        slots = torch.nonzero(invalid == 1).reshape(-1)[:wanted]  # freed + spare rows, lowest ids first
+        filled = slots.shape[0]
+        if filled > 0:
+            src = info.densify_point_id[:filled]
+            shrink = info.densify_size_reduction_factor[:filled]
+            # the copy starts from the source's position BEFORE this optimiser step, so the pair differs
+            xyz[slots] = info.densify_point_position_before_optimization[:filled]
+            feat[slots] = feat[src]
+            mp.point_object_id[slots] = mp.point_object_id[src]
+            feat[slots, 4:7] -= shrink
+            feat[src, 4:7] -= shrink
+            split = (shrink > 1e-6).reshape(-1)
             if cfg.enable_ellipsoid_offset:
-                offset = compute_ellipsoid_offset(mp.pointcloud[src], mp.pointcloud_features[src])
-                mp.pointcloud[to_fill] += offset
-                mp.pointcloud[src] -= offset
+                shift = compute_ellipsoid_offset(xyz[src], feat[src])
+                xyz[slots] += shift
+                xyz[src] -= shift
             if cfg.enable_sample_from_point:
-                over_src, over_dst = src[over], to_fill[over]
-                mp.pointcloud[over_dst] = sample_from_point(mp.pointcloud[over_src], mp.pointcloud_features[over_src],
-                                                            self.generator)
-                mp.pointcloud[over_src] = sample_from_point(mp.pointcloud[over_src], mp.pointcloud_features[over_src],
-                                                            self.generator)
-                mp.pointcloud[to_fill[under]] += info.densify_point_grad_position[:n_fill][under] * \
+                s_src, s_dst = src[split], slots[split]
+                xyz[s_dst] = sample_from_point(xyz[s_src], feat[s_src], self.generator)
+                xyz[s_src] = sample_from_point(xyz[s_src], feat[s_src], self.generator)
+                xyz[slots[~split]] += info.densify_point_grad_position[:filled][~split] * \
                     cfg.under_reconstructed_move_factor
-            mp.point_invalid_mask[to_fill] = 0
-        valid_after = int(mp.point_invalid_mask.shape[0] - mp.point_invalid_mask.sum())
-        assert valid_after == valid_before - num_transparent - num_floaters + n_fill
+            invalid[slots] = 0
+        alive_after = int((invalid == 0).sum())
+        assert alive_after == alive_before - info.transparent_point_id.shape[0] - info.floater_point_id.shape[0] + filled
         if self.verbose:
-            print(f"total valid points: {valid_before} -> {valid_after}, densify {num_densify} (filled {n_fill}), "
-                  f"transparent {num_transparent}, floaters {num_floaters}")
+            print(f"valid points {alive_before} -> {alive_after}: {wanted} candidates, {filled} placed, "
+                  f"{info.transparent_point_id.shape[0]} transparent, {info.floater_point_id.shape[0]} floaters removed")
         self.densify_point_info = None
 
     # GaussianPointAdaptiveController.py:355-358
