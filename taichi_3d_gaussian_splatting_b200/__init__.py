@@ -6,6 +6,7 @@ rasteriser, a drop-in for the hot path of wanmeihuali/taichi_3d_gaussian_splatti
 from .Camera import CameraInfo, CameraView  # noqa: F401
 from .densification import GaussianPointAdaptiveController  # noqa: F401
 from .loss import LossFunction  # noqa: F401
+from .scene_io import GaussianPointCloudScene  # noqa: F401
 from .GaussianPointCloudRasterisation import (  # noqa: F401
     BOUNDARY_TILES,
     TILE_HEIGHT,
@@ -15,5 +16,5 @@ from .GaussianPointCloudRasterisation import (  # noqa: F401
 )
 
 __all__ = ["CameraInfo", "CameraView", "GaussianPointCloudRasterisation", "GaussianPointAdaptiveController",
-           "LossFunction", "find_tile_start_and_end",
+           "LossFunction", "GaussianPointCloudScene", "find_tile_start_and_end",
            "TILE_WIDTH", "TILE_HEIGHT", "BOUNDARY_TILES"]
