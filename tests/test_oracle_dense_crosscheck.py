@@ -99,3 +99,42 @@ def test_oracle_offscreen_bbox_quirk():
                                          r.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(5),
                                          ctypes.c_int(64), ctypes.c_int(64))
     assert n.tolist() == [1, 1, 0, 0, 1]
+
+
+def test_oracle_empty_and_degenerate_inputs():
+    """Edge cases the reference handles implicitly (GPCR:915-918, 934, 959, 980): no points, no point in the
+    frustum, K == 0 -> zero image (the reference returns uninitialised memory there; we define zeros)."""
+    from oracle import OracleRasterisation
+    o = OracleRasterisation()
+    K = np.array([[50.0, 0, 16], [0, 50.0, 16], [0, 0, 1]], np.float32)
+    q, t = np.array([[0, 0, 0, 1]], np.float32), np.zeros((1, 3), np.float32)
+    f = o.forward(np.zeros((0, 3), np.float32), np.zeros((0, 56), np.float32), np.zeros(0, np.int8),
+                  np.zeros(0, np.int32), K, 32, 32, q, t)
+    assert f.image.shape == (32, 32, 3) and not f.image.any() and f.point_id_in_camera_list.shape == (0,)
+    xyz = np.array([[0, 0, -5.0], [100.0, 0, 5.0]], np.float32)  # behind the camera / far outside the margin
+    feat = np.zeros((2, 56), np.float32)
+    feat[:, 3] = 1
+    f = o.forward(xyz, feat, np.zeros(2, np.int8), np.zeros(2, np.int32), K, 32, 32, q, t)
+    assert f.point_id_in_camera_list.shape == (0,) and not f.image.any() and not f.tile_points_end.any()
+    b = o.backward(f, np.ones((32, 32, 3), np.float32), xyz, feat, np.zeros(2, np.int32), K, t, 3)
+    assert not b.grad_pointcloud.any() and not b.grad_pointcloud_features.any()
+
+
+def test_oracle_splat_covering_every_tile_and_frustum_borders():
+    from oracle import OracleRasterisation
+    o = OracleRasterisation(near_plane=0.8, far_plane=10.0)
+    K = np.array([[40.0, 0, 32], [0, 40.0, 32], [0, 0, 1]], np.float32)
+    q, t = np.array([[0, 0, 0, 1]], np.float32), np.zeros((1, 3), np.float32)
+    # point 0: huge splat at the centre -> all 16 tiles; points 1-4 sit exactly on the strict depth limits
+    # (near < z < far) and on the +-48 px margin (-48 <= u < W + 48)
+    xyz = np.array([[0, 0, 2.0], [0, 0, 0.8], [0, 0, 10.0], [-4.0, 0.4, 2.0], [4.0, 0, 2.0]], np.float32)
+    feat = np.zeros((5, 56), np.float32)
+    feat[:, 3] = 1
+    feat[0, 4:7] = 2.0
+    feat[1:, 4:7] = -3.0
+    f = o.forward(xyz, feat, np.zeros(5, np.int8), np.zeros(5, np.int32), K, 64, 64, q, t)
+    # u = 32 + 40 * x / z: x = -4 -> u = -48 (inside, >=), x = +4 -> u = 112 = W + 48 (outside, strict <)
+    assert f.point_id_in_camera_list.tolist() == [0, 3]
+    assert f.num_overlap_tiles[0] == 16 and (f.tile_points_end - f.tile_points_start >= 1).all()
+    assert f.num_overlap_tiles[1] == 1  # left of the image: still gets tile column 0 (GPCR:81-103 quirk)
+    assert f.pixel_valid_point_count.min() >= 1
