@@ -157,6 +157,7 @@ def run_b200(args):
     import torch.distributed as dist
     from taichi_3d_gaussian_splatting_b200 import GaussianPointCloudRasterisation as GPCR
     from taichi_3d_gaussian_splatting_b200 import profiling
+    from taichi_3d_gaussian_splatting_b200.parallel import exchange_gradients
     from taichi_3d_gaussian_splatting_b200.synthetic import C4_YAWS, CONFIGS, make_scene
 
     rank = int(os.environ.get("RANK", "0"))
@@ -193,9 +194,9 @@ def run_b200(args):
                            scene.camera_info.camera_intrinsics)
 
     def exchange_grads():
-        if world > 1:  # the training-time exchange step: dense (N,3)+(N,56) gradient sum over NVLink
-            dist.all_reduce(scene.point_cloud.grad)
-            dist.all_reduce(scene.point_cloud_features.grad)
+        if world > 1:  # the training-time exchange step: dense (N,3)+(N,56) gradient sum over NVLink (one all-reduce)
+            exchange_gradients([scene.point_cloud.grad, scene.point_cloud_features.grad],
+                               fused_buffer=op.last_gradient_buffer)
 
     def step_resident():
         scene.point_cloud.grad = None

@@ -232,6 +232,7 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
         self._flags = (_lib.GSB_FLAG_EXACT_EXP if exact_exp else 0) | (_lib.GSB_FLAG_FORCE_KEY64 if force_key64 else 0)
         self._key_capacity = int(initial_key_capacity) if initial_key_capacity else 0
         self.last_frame: Optional[Frame] = None
+        self.last_gradient_buffer: Optional[torch.Tensor] = None  # flat storage behind the latest backward's grads
         self._layout_cache = {}
         _lib.load()  # fail loudly at construction time if the CUDA library is missing
         outer = self
@@ -379,8 +380,15 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
             grad_image = grad_rasterized_image.contiguous()
             if grad_image.dtype != torch.float32:
                 grad_image = grad_image.float()
-            grad_pointcloud = torch.empty_like(pointcloud)
-            grad_pointcloud_features = torch.empty_like(pointcloud_features)
+            # both dense gradients live in ONE allocation (xyz rows, pad to 16 B, feature rows) so that a
+            # view-parallel trainer can sum them over ranks with a single collective (parallel.py)
+            off = (3 * N + 3) // 4 * 4
+            flat = torch.empty((off + 56 * N,), dtype=torch.float32, device=device)
+            if off > 3 * N:
+                flat[3 * N:off].zero_()
+            grad_pointcloud = flat[:3 * N].view(N, 3)
+            grad_pointcloud_features = flat[off:off + 56 * N].view(N, 56)
+            self.last_gradient_buffer = flat
             accum = torch.empty((max(M, 1), _ACCUM_FLOATS), dtype=torch.float32, device=device)
             magnitude_on_image = torch.empty((H, W, 2), dtype=torch.float32, device=device)
             t_pc = t_pointcloud_camera.contiguous()

@@ -19,9 +19,21 @@ def shard_views(num_views: int, rank: int, world_size: int) -> List[int]:
     return list(range(rank, num_views, world_size))
 
 
+def _aliases(buffer: torch.Tensor, grads) -> bool:
+    """True if every gradient tensor is a view into ``buffer``'s allocation (then one collective covers all)."""
+    lo = buffer.data_ptr()
+    hi = lo + buffer.numel() * buffer.element_size()
+    return all(g is None or (g.is_contiguous() and lo <= g.data_ptr() and
+                             g.data_ptr() + g.numel() * g.element_size() <= hi) for g in grads)
+
+
 def exchange_gradients(grads: Iterable[Optional[torch.Tensor]], group=None, average: bool = False,
-                       async_op: bool = False):
+                       async_op: bool = False, fused_buffer: Optional[torch.Tensor] = None):
     """Sum (or average) the dense gradient tensors over all ranks, in place.
+
+    ``fused_buffer``: the operator's ``last_gradient_buffer``; when the gradients are views into it (autograd
+    hands the operator's outputs to ``.grad`` without copying) the exchange is ONE all-reduce instead of one
+    per tensor.
 
     Returns the list of work handles when ``async_op`` (so the exchange can overlap the next view's
     forward on another stream), else ``None``.  A no-op when torch.distributed is not initialised or
@@ -30,6 +42,9 @@ def exchange_gradients(grads: Iterable[Optional[torch.Tensor]], group=None, aver
         return [] if async_op else None
     handles = []
     world = dist.get_world_size(group)
+    grads = list(grads)
+    if fused_buffer is not None and _aliases(fused_buffer, grads):
+        grads = [fused_buffer]
     for g in grads:
         if g is None:
             continue

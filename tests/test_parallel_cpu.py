@@ -33,10 +33,15 @@ def _worker(rank, world, port, out_dir):
     exchange_gradients([g_xyz, None, g_feat])
     g_avg = torch.full((4,), float(rank))
     exchange_gradients([g_avg], average=True)
+    flat = torch.arange(20, dtype=torch.float32) * (rank + 1)  # two views into one allocation -> one collective
+    va, vb = flat[:6].view(2, 3), flat[8:20].view(3, 4)
+    exchange_gradients([va, vb], fused_buffer=flat)
+    other = torch.ones(4) * (rank + 1)  # not a view of `flat`: falls back to per-tensor exchange
+    exchange_gradients([va, other], fused_buffer=flat)
     handles = exchange_gradients([torch.ones(3)], async_op=True)
     for h in handles:
         h.wait()
-    torch.save({"xyz": g_xyz, "feat": g_feat, "avg": g_avg, "views": shard_views(8, rank, world)},
+    torch.save({"xyz": g_xyz, "feat": g_feat, "avg": g_avg, "views": shard_views(8, rank, world), "flat": flat, "other": other},
                os.path.join(out_dir, f"rank{rank}.pt"))
     dist.destroy_process_group()
 
@@ -51,6 +56,9 @@ def test_gradient_exchange_world2_gloo(tmp_path):
         assert torch.equal(o["xyz"], torch.full((n, 3), 3.0))  # 1 + 2
         assert torch.equal(o["feat"], torch.arange(n * 56, dtype=torch.float32).reshape(n, 56) * 3)
         assert torch.allclose(o["avg"], torch.full((4,), 0.5))
+        expect = torch.arange(20, dtype=torch.float32) * 3
+        expect[:6] *= 2  # `va` went through the second (per-tensor) exchange: both ranks held x3, sum = x6
+        assert torch.equal(o["flat"], expect) and torch.equal(o["other"], torch.full((4,), 3.0))
     assert sorted(outs[0]["views"] + outs[1]["views"]) == list(range(8))
 
 
