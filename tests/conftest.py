@@ -12,6 +12,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """A clean checkout has no built artefacts (they are git-ignored): build the CUDA library (nvcc cross-compiles
+    without a GPU) and the oracle before collection, exactly what ``__graft_entry__.build()`` does.  The product
+    package itself never builds implicitly."""
+    from taichi_3d_gaussian_splatting_b200 import build as _build
+    if not os.path.exists(_build.LIB):
+        _build.build()
+    from oracle import build_oracle
+    build_oracle()
+
+
 def pytest_collection_modifyitems(config, items):
     try:
         import torch
