@@ -236,6 +236,7 @@ def run_b200(args):
     value = world * H * W / (ms_per_step * 1e-3) / 1e6
     frame = op.last_frame
     M, Kk = frame.num_points_in_camera, frame.num_keys
+    K_ref = int(frame.num_overlap_tiles.sum())  # pairs of the reference's 3-sigma squares (before the reach filter)
 
     # ---- e2e: per-step inputs in pinned HOST memory (target image, pose, intrinsics), loss scalar back
     target_host = torch.rand((H, W, 3), dtype=torch.float32).pin_memory()
@@ -429,7 +430,8 @@ def run_b200(args):
         "warmup": warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: N={N} Gaussians, {W}x{H}, SH deg {cfg['sh_degree']}, fwd+bwd, "
-                               f"1 view per GPU per step, M={M} in frustum, K={Kk} (tile,splat) pairs",
+                               f"1 view per GPU per step, M={M} in frustum, K={Kk} (tile,splat) pairs sorted and blended "
+                               f"(of {K_ref} in the reference's 3-sigma squares; the rest cannot reach alpha>=1/255)",
                    "parallelism": f"view-parallel x{world}" + (" + NCCL all-reduce of dense grads" if world > 1 else ""),
                    "l2": "inputs larger than L2 (scene 236 MB + 200 MB workspace per frame vs 126 MB L2)"},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(e2e_ms, 4),

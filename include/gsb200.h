@@ -45,6 +45,9 @@ enum {
 /* flags */
 #define GSB_FLAG_EXACT_EXP 1u    /* blend kernels use expf instead of ex2.approx */
 #define GSB_FLAG_FORCE_KEY64 2u  /* always sort (tile<<32 | depth) 64-bit keys like GPCR:158-170 */
+#define GSB_FLAG_KEEP_ALL_TILE_PAIRS 8u   /* emit a key for every tile of the reference's 3-sigma square (GPCR:81-172) instead of
+                                            only those where the splat can reach alpha >= 1/255 on some pixel; outputs are
+                                            identical either way, this only makes the sorted list equal to the reference's */
 #define GSB_FLAG_Q_ALREADY_NORMALISED 4u /* forward only: take q as stored and do not rewrite it.  Used when a
                                             frame is re-run after a key-capacity overflow, so that the second
                                             pass is bit-identical to the first (normalising twice is not). */
@@ -54,7 +57,7 @@ enum {
 typedef struct GsbWorkspaceLayout {
     int64_t total_bytes;
     int64_t zero_bytes;        /* [0, zero_bytes) is memset to 0 at the start of every forward */
-    int64_t counters;          /* int64[8]: [0]=M in-frustum points, [1]=K (tile,splat) pairs needed,
+    int64_t counters;          /* int64[8]: [0]=M in-frustum points, [1]=K (tile,splat) pairs emitted/needed,
                                   [2]=overflow (K > key_capacity), [3]=sorted-buffer selector (0=a,1=b) */
     int64_t tickets;           /* uint32[16] dynamic block tickets */
     int64_t scan_state;        /* uint64[ceil(N/256)+1] decoupled look-back state of the compaction scan */

@@ -15,4 +15,4 @@ inp = GPCR.GaussianPointCloudRasterisationInput(
     t_pointcloud_camera=scene.t_pointcloud_camera, color_max_sh_band=3)
 g = torch.randn((cfg["height"], cfg["width"], 3), generator=torch.Generator().manual_seed(1)).cuda()
 t = profiling.stage_times(op, inp, g, iters=10)
-print(os.environ.get("GSB200_LIB_PATH", "default"), name, {k: round(v * 1e3, 1) for k, v in t.items()}, "sum_us", round(sum(t.values()) * 1e3, 1))
+print(os.environ.get("GSB200_LIB_PATH", "default"), name, "K", op.last_frame.num_keys, {k: round(v * 1e3, 1) for k, v in t.items()}, "sum_us", round(sum(t.values()) * 1e3, 1))

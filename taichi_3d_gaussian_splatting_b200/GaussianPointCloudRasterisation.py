@@ -221,15 +221,19 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
         exact_exp: bool = False,
         force_key64: bool = False,
         initial_key_capacity: Optional[int] = None,
+        keep_all_tile_pairs: bool = False,
     ):
         """``exact_exp``: blend kernels use ``expf`` instead of ``ex2.approx`` (parity debugging).
         ``force_key64``: sort the reference's 64-bit ``tile << 32 | depth`` keys even when the live
         bits fit 32.  ``initial_key_capacity``: first guess for the number of (tile, splat) pairs;
-        the buffers grow automatically when a frame needs more."""
+        the buffers grow automatically when a frame needs more.  ``keep_all_tile_pairs``: emit a sort key for
+        every tile of the reference's 3-sigma square instead of only the tiles the splat can actually reach with
+        alpha >= 1/255 (same outputs, ~1.5x more keys; used by tests that compare the sorted list itself)."""
         super().__init__()
         self.config = config
         self.backward_valid_point_hook = backward_valid_point_hook
-        self._flags = (_lib.GSB_FLAG_EXACT_EXP if exact_exp else 0) | (_lib.GSB_FLAG_FORCE_KEY64 if force_key64 else 0)
+        self._flags = (_lib.GSB_FLAG_EXACT_EXP if exact_exp else 0) | (_lib.GSB_FLAG_FORCE_KEY64 if force_key64 else 0) | \
+            (_lib.GSB_FLAG_KEEP_ALL_TILE_PAIRS if keep_all_tile_pairs else 0)
         self._key_capacity = int(initial_key_capacity) if initial_key_capacity else 0
         self.last_frame: Optional[Frame] = None
         self.last_gradient_buffer: Optional[torch.Tensor] = None  # flat storage behind the latest backward's grads

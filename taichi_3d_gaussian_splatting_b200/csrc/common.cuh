@@ -118,38 +118,63 @@ __device__ __forceinline__ unsigned int smem_u32(const void *p) {
     return a;
 }
 
-__device__ __forceinline__ float quad_form(float a, float b, float c, float dx, float dy) {
-    return a * dx * dx + 2.0f * b * dx * dy + c * dy * dy;
+// Reach test of one splat: can alpha = exp(-q/2) * ro reach 1/255 anywhere in a rectangle of pixel centres?
+// q(d) = d^T conic d <= t2 = 2 ln(255 ro) (padded by 0.2 % + 1e-3).  `mode`: 0 = never (ro too small),
+// 1 = test rectangles with rect_reachable(), 2 = always (NaN / degenerate conic: keep the reference behaviour).
+// The arithmetic uses explicit FMAs and approximate reciprocals: it only has to be conservative, not exact.
+struct SplatReach {
+    float a, b2, c;        // conic a, 2b, c
+    float nb_ic, nb_ia;    // -b / c, -b / a  (1-D minimisers along vertical / horizontal edges)
+    float t2;
+    int mode;
+};
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float quad_form(const SplatReach &r, float dx, float dy) {
+    return fmaf(dx, fmaf(r.b2, dy, r.a * dx), r.c * dy * dy);
+}
+__device__ __forceinline__ SplatReach make_splat_reach(float a, float b, float c, float rescale_times_opacity) {
+    SplatReach r;
+    r.a = a; r.b2 = 2.0f * b; r.c = c;
+    const float ro = rescale_times_opacity;
+    r.nb_ic = -b * rcp_fast(c);
+    r.nb_ia = -b * rcp_fast(a);
+    r.t2 = fmaf(2.0f * 1.002f, __logf(fmaxf(255.0f * ro, 1.0f)), 1e-3f);
+    const float det = a * c - b * b;
+    if (!(ro == ro) || !(det > 0.0f) || !(a > 0.0f) || !(c > 0.0f)) r.mode = 2;
+    else if (ro < (1.0f / 255.0f) * 0.999f) r.mode = 0;  // exp(.) <= 1: can never reach 1/255
+    else r.mode = 1;
+    return r;
+}
+// Rectangle [X0,X1] x [Y0,Y1] is given RELATIVE to the splat centre.  Minimum of the convex quadratic over the
+// rectangle: 0 if the centre is inside, otherwise attained on one of the four edges (clamped 1-D minimisation).
+__device__ __forceinline__ bool rect_reachable(const SplatReach &r, float X0, float X1, float Y0, float Y1) {
+    if (X0 <= 0.0f && X1 >= 0.0f && Y0 <= 0.0f && Y1 >= 0.0f) return true;
+    const float ya = fminf(fmaxf(r.nb_ic * X0, Y0), Y1);
+    const float yb = fminf(fmaxf(r.nb_ic * X1, Y0), Y1);
+    const float xa = fminf(fmaxf(r.nb_ia * Y0, X0), X1);
+    const float xb = fminf(fmaxf(r.nb_ia * Y1, X0), X1);
+    const float best = fminf(fminf(quad_form(r, X0, ya), quad_form(r, X1, yb)),
+                             fminf(quad_form(r, xa, Y0), quad_form(r, xb, Y1)));
+    return !(best > r.t2);  // NaN keeps the rectangle
 }
 
 __device__ __forceinline__ unsigned int splat_patch_mask(float u, float v, float a, float b, float c,
                                                          float rescale_times_opacity, float tile_x0,
                                                          float tile_y0) {
-    const float ro = rescale_times_opacity;
-    if (!(ro == ro)) return 0xFFu;                 // NaN opacity: keep the reference behaviour
-    if (ro < (1.0f / 255.0f) * 0.999f) return 0u;  // can never reach 1/255 (exp(.) <= 1)
-    const float det = a * c - b * b;
-    if (!(det > 0.0f) || !(a > 0.0f) || !(c > 0.0f)) return 0xFFu;  // NaN / degenerate conic: keep all
-    const float t2 = (2.0f * __logf(fmaxf(255.0f * ro, 1.0f))) * 1.002f + 1e-3f;
-    const float inv_a = 1.0f / a, inv_c = 1.0f / c;
+    const SplatReach r = make_splat_reach(a, b, c, rescale_times_opacity);
+    if (r.mode == 0) return 0u;
+    if (r.mode == 2) return 0xFFu;
     unsigned int m = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
         // rectangle of the patch's pixel centres, relative to the splat centre
-        const float X0 = tile_x0 + 8.0f * (w & 1) + 0.5f - u, X1 = X0 + 7.0f;
-        const float Y0 = tile_y0 + 4.0f * (w >> 1) + 0.5f - v, Y1 = Y0 + 3.0f;
-        float best;
-        if (X0 <= 0.0f && X1 >= 0.0f && Y0 <= 0.0f && Y1 >= 0.0f) {
-            best = 0.0f;
-        } else {
-            const float ya = fminf(fmaxf(-b * X0 * inv_c, Y0), Y1);
-            const float yb = fminf(fmaxf(-b * X1 * inv_c, Y0), Y1);
-            const float xa = fminf(fmaxf(-b * Y0 * inv_a, X0), X1);
-            const float xb = fminf(fmaxf(-b * Y1 * inv_a, X0), X1);
-            best = fminf(fminf(quad_form(a, b, c, X0, ya), quad_form(a, b, c, X1, yb)),
-                         fminf(quad_form(a, b, c, xa, Y0), quad_form(a, b, c, xb, Y1)));
-        }
-        if (!(best > t2)) m |= 1u << w;  // NaN keeps the patch
+        const float X0 = tile_x0 + 8.0f * (w & 1) + 0.5f - u;
+        const float Y0 = tile_y0 + 4.0f * (w >> 1) + 0.5f - v;
+        if (rect_reachable(r, X0, X0 + 7.0f, Y0, Y0 + 3.0f)) m |= 1u << w;
     }
     return m;
 }

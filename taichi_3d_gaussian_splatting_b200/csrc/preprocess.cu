@@ -113,6 +113,7 @@ struct PreParams {
     float near_plane, far_plane, depth_scale;
     int depth_bits;
     int skip_q_normalise;
+    int filter_tiles;
     long long key_capacity;
     int num_blocks;
     // outputs
@@ -144,6 +145,18 @@ __device__ __forceinline__ void bounding_box(float u, float v, float radii, int 
 #ifndef GSB_PRE_MIN_BLOCKS
 #define GSB_PRE_MIN_BLOCKS 5
 #endif
+#ifndef GSB_FILTER_MAX_TILES
+#define GSB_FILTER_MAX_TILES 16
+#endif
+constexpr int FILTER_MAX_TILES = GSB_FILTER_MAX_TILES;  // <= 64 (bit mask)
+
+// pixel centres of tile (tu, tv) relative to the splat centre
+__device__ __forceinline__ bool tile_reachable(const SplatReach &r, float u, float v, int tu, int tv) {
+    const float X0 = (float)(tu * GSB_TILE_WIDTH) + 0.5f - u;
+    const float Y0 = (float)(tv * GSB_TILE_HEIGHT) + 0.5f - v;
+    return rect_reachable(r, X0, X0 + (float)(GSB_TILE_WIDTH - 1), Y0, Y0 + (float)(GSB_TILE_HEIGHT - 1));
+}
+
 template <typename KeyT>
 __global__ void __launch_bounds__(SCAN_BLOCK_THREADS, GSB_PRE_MIN_BLOCKS)
 preprocess_kernel(const PreParams p) {
@@ -159,7 +172,10 @@ preprocess_kernel(const PreParams p) {
     const long long i = (long long)blk * SCAN_BLOCK_THREADS + tid;
 
     bool in = false;
-    int ntiles = 0, min_tu = 0, max_tu = 0, min_tv = 0, max_tv = 0;
+    int ntiles = 0, nkeys = 0, min_tu = 0, max_tu = 0, min_tv = 0, max_tv = 0;
+    unsigned long long keep_mask = 0;
+    SplatReach reach;
+    reach.mode = 2;
     float4 r0 = make_float4(0, 0, 0, 0), r1 = r0, r2 = r0;
     float pc[3] = {0, 0, 0};
 
@@ -277,6 +293,27 @@ preprocess_kernel(const PreParams p) {
             }
             bounding_box(u, v, radius, p.W, p.H, min_tu, max_tu, min_tv, max_tv);
             ntiles = (max_tu - min_tu) * (max_tv - min_tv);
+            // Of the tiles in the reference's 3-sigma square, keep only those where alpha can reach 1/255 on
+            // some pixel centre (conservative reach test, common.cuh): a dropped (tile, splat) pair is one the
+            // blend would have skipped on all 256 pixels, so no output changes; ~1/3 of the pairs go away.
+            reach = make_splat_reach(inv_det * c11, inv_det * (-c01), inv_det * c00, rescale * opacity);
+            if (p.filter_tiles && reach.mode != 2) {
+                // Only the first FILTER_MAX_TILES tiles of a splat are tested (the rest are kept): one lane with a
+                // huge splat would otherwise stall its warp in this loop; splats that small carry most pairs.
+                int idx = 0;
+                for (int tu = min_tu; tu < max_tu && idx < FILTER_MAX_TILES; ++tu)
+                    for (int tv = min_tv; tv < max_tv && idx < FILTER_MAX_TILES; ++tv, ++idx) {
+                        const bool keep = reach.mode == 1 && tile_reachable(reach, u, v, tu, tv);
+                        if (keep) {
+                            ++nkeys;
+                            keep_mask |= 1ull << idx;
+                        }
+                    }
+                if (ntiles > FILTER_MAX_TILES) nkeys += ntiles - FILTER_MAX_TILES;
+            } else {
+                nkeys = ntiles;
+                keep_mask = ~0ull;
+            }
             r0 = make_float4(u, v, inv_det * c11, inv_det * (-c01));
             r1 = make_float4(inv_det * c00, rescale, opacity, pc[2]);
             r2 = make_float4(col[0], col[1], col[2], radius);
@@ -284,7 +321,7 @@ preprocess_kernel(const PreParams p) {
     }
 
     // ---- block-level exclusive scan of the packed pair (count << 36 | tiles)
-    const unsigned long long mine = ((unsigned long long)(in ? 1 : 0) << CNT_SHIFT) | (unsigned long long)ntiles;
+    const unsigned long long mine = ((unsigned long long)(in ? 1 : 0) << CNT_SHIFT) | (unsigned long long)nkeys;
     unsigned long long incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -363,13 +400,17 @@ preprocess_kernel(const PreParams p) {
     KeyT *keys = reinterpret_cast<KeyT *>(p.keys);
     const int tiles_x = p.W / GSB_TILE_WIDTH;
     long long pos = key_base;
+    int idx = 0;
     for (int tu = min_tu; tu < max_tu; ++tu)
-        for (int tv = min_tv; tv < max_tv; ++tv, ++pos) {
+        for (int tv = min_tv; tv < max_tv; ++tv, ++idx) {
+            const bool keep = idx >= FILTER_MAX_TILES || ((keep_mask >> idx) & 1ull) != 0;
+            if (!keep) continue;
             if (pos < p.key_capacity) {
                 const KeyT tile = (KeyT)(tu + tv * tiles_x);
                 keys[pos] = (tile << p.depth_bits) | (KeyT)(unsigned int)depth_key;
                 p.vals[pos] = (int)off;
             }
+            ++pos;
         }
 }
 
@@ -397,6 +438,7 @@ int launch_preprocess(const GsbForwardArgs &a, const Workspace &ws, cudaStream_t
     p.depth_scale = a.depth_to_sort_key_scale;
     p.depth_bits = L.depth_bits;
     p.skip_q_normalise = (a.flags & GSB_FLAG_Q_ALREADY_NORMALISED) ? 1 : 0;
+    p.filter_tiles = (a.flags & GSB_FLAG_KEEP_ALL_TILE_PAIRS) ? 0 : 1;
     p.key_capacity = a.key_capacity;
     p.num_blocks = L.scan_blocks;
     p.counters = ws.counters;

@@ -8,9 +8,9 @@ Config = GPCR.GaussianPointCloudRasterisationConfig
 Input = GPCR.GaussianPointCloudRasterisationInput
 
 
-def make_op(hook=None, exact_exp=False, force_key64=False, initial_key_capacity=None, **cfg):
-    return GPCR(Config(**cfg), backward_valid_point_hook=hook, exact_exp=exact_exp,
-                force_key64=force_key64, initial_key_capacity=initial_key_capacity)
+def make_op(hook=None, exact_exp=False, force_key64=False, initial_key_capacity=None, keep_all_tile_pairs=False, **cfg):
+    return GPCR(Config(**cfg), backward_valid_point_hook=hook, exact_exp=exact_exp, force_key64=force_key64,
+                initial_key_capacity=initial_key_capacity, keep_all_tile_pairs=keep_all_tile_pairs)
 
 
 def cuda_scene(scene, requires_grad=False):

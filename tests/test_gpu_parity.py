@@ -27,9 +27,8 @@ def _small_scene(seed, npts=3000, h=64, w=96, sigma=0.06, yaw=7.0, sh_degree=3):
     return sc
 
 
-def _check_stages(frame, fwd, exact_floats=True):
+def _check_stages(frame, fwd, exact_floats=True, max_tiles=None):
     assert frame.num_points_in_camera == fwd.point_id_in_camera_list.shape[0]
-    assert frame.num_keys == fwd.point_offset_with_sort_key.shape[0]
     assert (n(frame.point_id_in_camera_list) == fwd.point_id_in_camera_list).all()
     assert (n(frame.num_overlap_tiles) == fwd.num_overlap_tiles).all()
     pairs = [(frame.point_uv, fwd.point_uv), (frame.point_in_camera, fwd.point_in_camera),
@@ -42,25 +41,71 @@ def _check_stages(frame, fwd, exact_floats=True):
             assert np.array_equal(got, exp), f"max abs diff {np.abs(got - exp).max()}"
         else:
             assert np.allclose(got, exp, rtol=1e-5, atol=1e-5)
-    # sorted (key, value) arrays bit-exact vs the oracle's stable sort
     L = frame.layout
     okeys = fwd.point_in_camera_sort_key
     packed = ((okeys >> 32) << L.depth_bits) | (okeys & 0xFFFFFFFF)
-    assert (n(frame.sorted_keys) == packed).all()
-    assert (n(frame.point_offset_with_sort_key) == fwd.point_offset_with_sort_key).all()
-    assert (n(frame.tile_points_start) == fwd.tile_points_start).all()
-    assert (n(frame.tile_points_end) == fwd.tile_points_end).all()
+    if frame.flags & 8:  # GSB_FLAG_KEEP_ALL_TILE_PAIRS: the sorted list IS the reference's list
+        assert frame.num_keys == fwd.point_offset_with_sort_key.shape[0]
+        assert (n(frame.sorted_keys) == packed).all()
+        assert (n(frame.point_offset_with_sort_key) == fwd.point_offset_with_sort_key).all()
+        assert (n(frame.tile_points_start) == fwd.tile_points_start).all()
+        assert (n(frame.tile_points_end) == fwd.tile_points_end).all()
+    else:
+        _check_filtered_lists(frame, fwd, packed, max_tiles)
 
 
+def _check_filtered_lists(frame, fwd, packed, max_tiles=None):
+    """Default mode: only (tile, splat) pairs that can reach alpha >= 1/255 on some pixel get a key.  Per tile the
+    emitted list must be a SUBSEQUENCE of the reference's list (same relative order, same keys), and every dropped
+    pair must be one that contributes to no pixel of the tile in the oracle's arithmetic."""
+    mk, mv = n(frame.sorted_keys), n(frame.point_offset_with_sort_key)
+    ms, me = n(frame.tile_points_start), n(frame.tile_points_end)
+    W, H = frame.width, frame.height
+    tiles_x = W // 16
+    assert frame.num_keys == mk.shape[0] <= packed.shape[0]
+    assert (np.diff(mk) >= 0).all()
+    tiles = np.arange(ms.shape[0])
+    if max_tiles is not None and tiles.shape[0] > max_tiles:
+        tiles = np.random.default_rng(0).choice(tiles, max_tiles, replace=False)
+    ys, xs = np.meshgrid(np.arange(16), np.arange(16), indexing="ij")
+    dropped_total = 0
+    for t in tiles:
+        os_, oe = fwd.tile_points_start[t], fwd.tile_points_end[t]
+        ref_vals, ref_keys = fwd.point_offset_with_sort_key[os_:oe], packed[os_:oe]
+        got_vals, got_keys = mv[ms[t]:me[t]], mk[ms[t]:me[t]]
+        # subsequence: walk the reference list once
+        keep = np.zeros(ref_vals.shape[0], bool)
+        j = 0
+        for i in range(ref_vals.shape[0]):
+            if j < got_vals.shape[0] and ref_vals[i] == got_vals[j] and ref_keys[i] == got_keys[j]:
+                keep[i] = True
+                j += 1
+        assert j == got_vals.shape[0], f"tile {t}: emitted list is not a subsequence of the reference list"
+        drop = ref_vals[~keep]
+        if drop.shape[0] == 0:
+            continue
+        dropped_total += drop.shape[0]
+        px = (t % tiles_x) * 16 + xs.reshape(-1) + 0.5
+        py = (t // tiles_x) * 16 + ys.reshape(-1) + 0.5
+        uv, cr = fwd.point_uv[drop], fwd.point_uv_conic_and_rescale[drop]
+        dx, dy = px[None, :] - uv[:, 0:1], py[None, :] - uv[:, 1:2]
+        power = -0.5 * (dx * dx * cr[:, 0:1] + dy * dy * cr[:, 2:3]) - dx * dy * cr[:, 1:2]
+        alpha = np.exp(power) * cr[:, 3:4] * fwd.point_alpha_after_activation[drop][:, None]
+        assert alpha.max() < 1.0 / 255.0, f"tile {t}: dropped a pair with alpha {alpha.max()}"
+    return dropped_total
+
+
+@pytest.mark.parametrize("keep_all", [False, True])
 @pytest.mark.parametrize("exact_exp", [True, False])
 @pytest.mark.parametrize("force_key64", [False, True])
-def test_c1_forward_backward_vs_oracle(exact_exp, force_key64):
+def test_c1_forward_backward_vs_oracle(exact_exp, force_key64, keep_all):
     """BASELINE config 1 (correctness gate): 1e4 Gaussians, 256x256, SH deg 0."""
     scene = make_scene(**CONFIGS["C1"])
     o, fwd, feats_n = oracle_forward(scene)
     sc = cuda_scene(scene, requires_grad=True)
     captured = {}
-    op = make_op(hook=lambda h: captured.setdefault("hook", h), exact_exp=exact_exp, force_key64=force_key64)
+    op = make_op(hook=lambda h: captured.setdefault("hook", h), exact_exp=exact_exp, force_key64=force_key64,
+                 keep_all_tile_pairs=keep_all)
     image, depth, count = run_forward(op, sc, band=0)
     frame = op.last_frame
     assert frame.layout.key_bytes == (8 if force_key64 else 4)
@@ -196,7 +241,7 @@ def test_key_capacity_overflow_regrows():
     _, fwd, _ = oracle_forward(scene)
     op = make_op(initial_key_capacity=64, exact_exp=True)
     image, _, _ = run_forward(op, cuda_scene(scene))
-    assert op.last_frame.key_capacity >= fwd.point_offset_with_sort_key.shape[0] > 64
+    assert op.last_frame.key_capacity >= op.last_frame.num_keys > 64
     _check_stages(op.last_frame, fwd)
     assert np.abs(n(image) - fwd.image).max() <= 1e-4
 
@@ -273,14 +318,15 @@ def test_c2_full_size_statistical_parity_and_properties():
     op = make_op()
     image, depth, count = run_forward(op, sc, band=3)
     frame = op.last_frame
-    _check_stages(frame, fwd)
+    _check_stages(frame, fwd, max_tiles=150)
     # size-independent properties
     keys = frame.sorted_keys
     assert bool((keys[1:] >= keys[:-1]).all())
     same = keys[1:] == keys[:-1]
     vals = frame.point_offset_with_sort_key
     assert bool((vals[1:][same] > vals[:-1][same]).all())  # stability: ties keep ascending offset
-    assert int(frame.num_overlap_tiles.sum()) == frame.num_keys
+    assert frame.num_keys <= int(frame.num_overlap_tiles.sum()) == fwd.point_offset_with_sort_key.shape[0]
+    assert frame.num_keys < 0.8 * fwd.point_offset_with_sort_key.shape[0]  # about a third of the pairs can never contribute
     assert bool(torch.isfinite(image).all()) and float(image.min()) >= 0.0
     d = np.abs(n(image) - fwd.image)
     assert (d > 1e-4).sum() <= 40 and d.max() <= 5e-3
@@ -344,3 +390,22 @@ def test_render_host_c_abi_entry_point():
     # error convention: bad arguments return a negative code and a message, never throw
     assert lib.gsb200_render_host(None, None, None, None, None, None, None) < 0
     assert b"null" in lib.gsb200_last_error()
+
+
+def test_filtered_and_unfiltered_key_lists_render_identically():
+    """Dropping the (tile, splat) pairs that cannot reach alpha >= 1/255 must not change a single bit of the image,
+    depth, accumulated alpha or pixel counts; gradients agree up to the order of the atomic sums."""
+    scene = _small_scene(91, npts=4000, sigma=0.08)
+    out = {}
+    for keep_all in (False, True):
+        sc = cuda_scene(scene, requires_grad=True)
+        op = make_op(keep_all_tile_pairs=keep_all)
+        image, depth, count = run_forward(op, sc)
+        image.backward(torch.ones_like(image))
+        out[keep_all] = (image.detach().clone(), depth.clone(), count.clone(), sc.point_cloud.grad.clone(),
+                         sc.point_cloud_features.grad.clone(), op.last_frame.num_keys)
+    a, b = out[False], out[True]
+    assert a[5] < b[5]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    assert torch.allclose(a[3], b[3], rtol=1e-4, atol=1e-5 * float(b[3].abs().max()))
+    assert torch.allclose(a[4], b[4], rtol=1e-4, atol=1e-5 * float(b[4].abs().max()))
