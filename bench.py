@@ -351,10 +351,10 @@ def run_b200(args):
         def fw():
             with torch.no_grad():
                 op2(inp2)
-        for _ in range(3):
+        for _ in range(5):
             st()
-        ms = timed(st, k) / k
-        fms = timed(fw, k) / k
+        ms = min(timed(st, k), timed(st, k)) / k   # side number: best of two short runs
+        fms = min(timed(fw, k), timed(fw, k)) / k
         px = c["height"] * c["width"]
         return {"fwd_bwd_ms": round(ms, 4), "fwd_bwd_Mpix_s": round(world * px / (ms * 1e-3) / 1e6, 1),
                 "fwd_ms": round(fms, 4), "fwd_Mpix_s": round(world * px / (fms * 1e-3) / 1e6, 1),
