@@ -115,6 +115,7 @@ struct PreParams {
     int skip_q_normalise;
     int filter_tiles;
     long long key_capacity;
+    long long key_store_limit;  // padded capacity of the key buffers: every slot the sort may read gets a valid key
     int num_blocks;
     // outputs
     long long *counters;
@@ -145,10 +146,15 @@ __device__ __forceinline__ void bounding_box(float u, float v, float radii, int 
 #ifndef GSB_PRE_MIN_BLOCKS
 #define GSB_PRE_MIN_BLOCKS 5
 #endif
-#ifndef GSB_FILTER_MAX_TILES
-#define GSB_FILTER_MAX_TILES 16
-#endif
-constexpr int FILTER_MAX_TILES = GSB_FILTER_MAX_TILES;  // <= 64 (bit mask)
+// Per-warp staging area of the cooperative reach filter / key emission (32 splats of the warp).
+struct WarpStage {
+    float u[32], v[32], a[32], b2[32], c[32], nb_ic[32], nb_ia[32], t2[32];
+    int min_tu[32], min_tv[32], ntv[32];
+    unsigned int mask_lo[32], mask_hi[32];  // reachable tiles among the first 64 of the splat's square
+    int pref[33];                           // warp prefix of per-splat pair / key counts
+    int nk64[32], depth_key[32], off[32];
+    long long key_base[32];
+};
 
 // pixel centres of tile (tu, tv) relative to the splat centre
 __device__ __forceinline__ bool tile_reachable(const SplatReach &r, float u, float v, int tu, int tv) {
@@ -163,6 +169,7 @@ preprocess_kernel(const PreParams p) {
     __shared__ unsigned int s_ticket;
     __shared__ unsigned long long s_warp_sums[SCAN_BLOCK_THREADS / 32];
     __shared__ unsigned long long s_block_exclusive;
+    __shared__ WarpStage s_stage[SCAN_BLOCK_THREADS / 32];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -173,8 +180,8 @@ preprocess_kernel(const PreParams p) {
 
     bool in = false;
     int ntiles = 0, nkeys = 0, min_tu = 0, max_tu = 0, min_tv = 0, max_tv = 0;
-    unsigned long long keep_mask = 0;
     SplatReach reach;
+    reach.a = reach.b2 = reach.c = reach.nb_ic = reach.nb_ia = reach.t2 = 0.0f;
     reach.mode = 2;
     float4 r0 = make_float4(0, 0, 0, 0), r1 = r0, r2 = r0;
     float pc[3] = {0, 0, 0};
@@ -293,30 +300,65 @@ preprocess_kernel(const PreParams p) {
             }
             bounding_box(u, v, radius, p.W, p.H, min_tu, max_tu, min_tv, max_tv);
             ntiles = (max_tu - min_tu) * (max_tv - min_tv);
-            // Of the tiles in the reference's 3-sigma square, keep only those where alpha can reach 1/255 on
-            // some pixel centre (conservative reach test, common.cuh): a dropped (tile, splat) pair is one the
-            // blend would have skipped on all 256 pixels, so no output changes; ~1/3 of the pairs go away.
+            // reach-test parameters of this splat; the (tile, splat) tests themselves are done cooperatively by
+            // the warp below (one lane per PAIR, not per splat)
             reach = make_splat_reach(inv_det * c11, inv_det * (-c01), inv_det * c00, rescale * opacity);
-            if (p.filter_tiles && reach.mode != 2) {
-                // Only the first FILTER_MAX_TILES tiles of a splat are tested (the rest are kept): one lane with a
-                // huge splat would otherwise stall its warp in this loop; splats that small carry most pairs.
-                int idx = 0;
-                for (int tu = min_tu; tu < max_tu && idx < FILTER_MAX_TILES; ++tu)
-                    for (int tv = min_tv; tv < max_tv && idx < FILTER_MAX_TILES; ++tv, ++idx) {
-                        const bool keep = reach.mode == 1 && tile_reachable(reach, u, v, tu, tv);
-                        if (keep) {
-                            ++nkeys;
-                            keep_mask |= 1ull << idx;
-                        }
-                    }
-                if (ntiles > FILTER_MAX_TILES) nkeys += ntiles - FILTER_MAX_TILES;
-            } else {
-                nkeys = ntiles;
-                keep_mask = ~0ull;
-            }
+            if (!p.filter_tiles) reach.mode = 2;
             r0 = make_float4(u, v, inv_det * c11, inv_det * (-c01));
             r1 = make_float4(inv_det * c00, rescale, opacity, pc[2]);
             r2 = make_float4(col[0], col[1], col[2], radius);
+        }
+    }
+
+    // ---- warp-cooperative reach filter.  Of the tiles in the reference's 3-sigma square only those where alpha can
+    // reach 1/255 on some pixel centre get a sort key (conservative test, common.cuh): a dropped (tile, splat)
+    // pair is one the blend would skip on all 256 pixels, so no output changes, and ~1/3 of the pairs go away.
+    // The warp's pairs (first 64 tiles of each of its 32 splats) are dealt round-robin to the lanes, so one large
+    // splat does not stall the other 31 lanes.
+    WarpStage &st = s_stage[warp];
+    {
+        const int ntv = max_tv - min_tv;
+        const int mode = in ? reach.mode : 0;
+        st.u[lane] = r0.x; st.v[lane] = r0.y;
+        st.a[lane] = reach.a; st.b2[lane] = reach.b2; st.c[lane] = reach.c;
+        st.nb_ic[lane] = reach.nb_ic; st.nb_ia[lane] = reach.nb_ia; st.t2[lane] = reach.t2;
+        st.min_tu[lane] = min_tu; st.min_tv[lane] = min_tv; st.ntv[lane] = ntv > 0 ? ntv : 1;
+        // mode 2 (keep everything): all of the first 64 bits set; mode 0 (never visible): none
+        const int n64 = ntiles < 64 ? ntiles : 64;
+        const unsigned long long all64 = n64 >= 64 ? ~0ull : ((1ull << n64) - 1ull);
+        st.mask_lo[lane] = mode == 2 ? (unsigned int)all64 : 0u;
+        st.mask_hi[lane] = mode == 2 ? (unsigned int)(all64 >> 32) : 0u;
+        const int tcap = mode == 1 ? n64 : 0;
+        int incl_t = tcap;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl_t, d);
+            if (lane >= d) incl_t += o;
+        }
+        st.pref[lane + 1] = incl_t;
+        if (lane == 0) st.pref[0] = 0;
+        __syncwarp();
+        const int total = st.pref[32];
+        for (int q = lane; q < total; q += 32) {
+            int lo = 0;  // largest owner with pref[owner] <= q
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (st.pref[lo + step] <= q) lo += step;
+            const int idx = q - st.pref[lo];
+            const int ntv_o = st.ntv[lo];
+            const int du = idx / ntv_o;
+            const int tu = st.min_tu[lo] + du, tv = st.min_tv[lo] + (idx - du * ntv_o);
+            SplatReach r;
+            r.a = st.a[lo]; r.b2 = st.b2[lo]; r.c = st.c[lo];
+            r.nb_ic = st.nb_ic[lo]; r.nb_ia = st.nb_ia[lo]; r.t2 = st.t2[lo];
+            r.mode = 1;
+            if (tile_reachable(r, st.u[lo], st.v[lo], tu, tv))
+                atomicOr(idx < 32 ? &st.mask_lo[lo] : &st.mask_hi[lo], 1u << (idx & 31));
+        }
+        __syncwarp();
+        if (in) {
+            const int beyond = ntiles > 64 ? ntiles - 64 : 0;  // tiles past the 64-bit mask are kept untested
+            nkeys = mode == 0 ? 0 : __popc(st.mask_lo[lane]) + __popc(st.mask_hi[lane]) + beyond;
         }
     }
 
@@ -377,41 +419,69 @@ preprocess_kernel(const PreParams p) {
         }
     }
     __syncthreads();
-    if (!in) {
-        if (i < p.N) p.point_offset[i] = -1;
-        return;
-    }
     const unsigned long long excl = s_block_exclusive + warp_prefix + (incl - mine);
     const long long off = (long long)(excl >> CNT_SHIFT);
     const long long key_base = (long long)(excl & ((1ull << CNT_SHIFT) - 1));
+    if (i < p.N) p.point_offset[i] = in ? (int)off : -1;
+    if (in) {
+        p.point_id[off] = (int)i;
+        p.num_tiles[off] = ntiles;
+        p.records[3 * off] = r0;
+        p.records[3 * off + 1] = r1;
+        p.records[3 * off + 2] = r2;
+        p.point_in_camera[3 * off] = pc[0];
+        p.point_in_camera[3 * off + 1] = pc[1];
+        p.point_in_camera[3 * off + 2] = pc[2];
+    }
 
-    p.point_id[off] = (int)i;
-    p.point_offset[i] = (int)off;
-    p.num_tiles[off] = ntiles;
-    p.records[3 * off] = r0;
-    p.records[3 * off + 1] = r1;
-    p.records[3 * off + 2] = r2;
-    p.point_in_camera[3 * off] = pc[0];
-    p.point_in_camera[3 * off + 1] = pc[1];
-    p.point_in_camera[3 * off + 2] = pc[2];
-
-    // GPCR:158-170: key = tile_id << depth_bits | int32(depth * scale)   (tile_u outer, tile_v inner)
-    const int depth_key = (int)(pc[2] * p.depth_scale);
-    KeyT *keys = reinterpret_cast<KeyT *>(p.keys);
-    const int tiles_x = p.W / GSB_TILE_WIDTH;
-    long long pos = key_base;
-    int idx = 0;
-    for (int tu = min_tu; tu < max_tu; ++tu)
-        for (int tv = min_tv; tv < max_tv; ++tv, ++idx) {
-            const bool keep = idx >= FILTER_MAX_TILES || ((keep_mask >> idx) & 1ull) != 0;
-            if (!keep) continue;
-            if (pos < p.key_capacity) {
-                const KeyT tile = (KeyT)(tu + tv * tiles_x);
-                keys[pos] = (tile << p.depth_bits) | (KeyT)(unsigned int)depth_key;
-                p.vals[pos] = (int)off;
-            }
-            ++pos;
+    // ---- warp-cooperative key emission.  GPCR:158-170: key = tile_id << depth_bits | int32(depth * scale), tiles in
+    // (tile_u outer, tile_v inner) order.  The key ranges of the warp's splats are adjacent (prefix sum), so
+    // dealing the keys round-robin to the lanes makes the stores contiguous and the work balanced.
+    {
+        st.depth_key[lane] = (int)(pc[2] * p.depth_scale);
+        st.off[lane] = (int)off;
+        st.key_base[lane] = key_base;
+        int incl_k = in ? nkeys : 0;
+        const int mine_k = incl_k;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl_k, d);
+            if (lane >= d) incl_k += o;
         }
+        __syncwarp();  // every lane has finished reading pref[] of the filter phase
+        st.pref[lane + 1] = incl_k;
+        if (lane == 0) st.pref[0] = 0;
+        st.nk64[lane] = in ? mine_k - (ntiles > 64 ? ntiles - 64 : 0) : 0;  // kept tiles among the first 64
+        __syncwarp();
+        const int total = st.pref[32];
+        KeyT *keys = reinterpret_cast<KeyT *>(p.keys);
+        const int tiles_x = p.W / GSB_TILE_WIDTH;
+        for (int q = lane; q < total; q += 32) {
+            int lo = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (st.pref[lo + step] <= q) lo += step;
+            const int j = q - st.pref[lo];  // j-th kept tile of splat `lo`
+            int idx;
+            const int nk64 = st.nk64[lo];
+            if (j < nk64) {
+                const unsigned int mlo = st.mask_lo[lo];
+                const int plo = __popc(mlo);
+                idx = j < plo ? (int)__fns(mlo, 0, j + 1) : 32 + (int)__fns(st.mask_hi[lo], 0, j - plo + 1);
+            } else {
+                idx = 64 + (j - nk64);
+            }
+            const int ntv_o = st.ntv[lo];
+            const int du = idx / ntv_o;
+            const int tu = st.min_tu[lo] + du, tv = st.min_tv[lo] + (idx - du * ntv_o);
+            const long long pos = st.key_base[lo] + j;
+            if (pos < p.key_store_limit) {
+                const KeyT tile = (KeyT)(tu + tv * tiles_x);
+                keys[pos] = (tile << p.depth_bits) | (KeyT)(unsigned int)st.depth_key[lo];
+                p.vals[pos] = st.off[lo];
+            }
+        }
+    }
 }
 
 int launch_preprocess(const GsbForwardArgs &a, const Workspace &ws, cudaStream_t stream) {
@@ -440,6 +510,7 @@ int launch_preprocess(const GsbForwardArgs &a, const Workspace &ws, cudaStream_t
     p.skip_q_normalise = (a.flags & GSB_FLAG_Q_ALREADY_NORMALISED) ? 1 : 0;
     p.filter_tiles = (a.flags & GSB_FLAG_KEEP_ALL_TILE_PAIRS) ? 0 : 1;
     p.key_capacity = a.key_capacity;
+    p.key_store_limit = ws.layout.key_capacity_padded;
     p.num_blocks = L.scan_blocks;
     p.counters = ws.counters;
     p.tickets = ws.tickets;
