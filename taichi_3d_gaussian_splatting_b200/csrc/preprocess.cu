@@ -144,7 +144,7 @@ __device__ __forceinline__ void bounding_box(float u, float v, float radii, int 
 }
 
 #ifndef GSB_PRE_MIN_BLOCKS
-#define GSB_PRE_MIN_BLOCKS 5
+#define GSB_PRE_MIN_BLOCKS 4
 #endif
 // Per-warp staging area of the cooperative reach filter / key emission (32 splats of the warp).
 struct WarpStage {
@@ -155,6 +155,20 @@ struct WarpStage {
     int nk64[32], depth_key[32], off[32];
     long long key_base[32];
 };
+
+// position of the j-th (0-based) set bit of m; j < popc(m).  Five popc steps instead of the library's bit loop.
+__device__ __forceinline__ int select_bit32(unsigned int m, int j) {
+    int pos = 0;
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const int c = __popc(m & ((1u << w) - 1u));
+        const bool up = j >= c;
+        j -= up ? c : 0;
+        pos += up ? w : 0;
+        m = up ? (m >> w) : m;
+    }
+    return pos;
+}
 
 // pixel centres of tile (tu, tv) relative to the splat centre
 __device__ __forceinline__ bool tile_reachable(const SplatReach &r, float u, float v, int tu, int tv) {
@@ -185,6 +199,7 @@ preprocess_kernel(const PreParams p) {
     reach.mode = 2;
     float4 r0 = make_float4(0, 0, 0, 0), r1 = r0, r2 = r0;
     float pc[3] = {0, 0, 0};
+    float dir0 = 0.0f, dir1 = 0.0f, dir2 = 0.0f;  // unit view direction (GPCR:302), consumed by the SH stage
 
     if (i < p.N && p.invalid[i] != 1) {
         const PoseBlock *pb = p.poses + p.obj_id[i];
@@ -264,40 +279,7 @@ preprocess_kernel(const PreParams p) {
             float dn = sqrtf(dx * dx + dy * dy + dz * dz);
             float dinv = 1.0f / dn;
             dx = dinv * dx; dy = dinv * dy; dz = dinv * dz;
-            float sh[16];
-            sh[0] = 0.28209479177387814f;
-            sh[1] = -0.48860251190291987f * dy;
-            sh[2] = 0.48860251190291987f * dz;
-            sh[3] = -0.48860251190291987f * dx;
-            sh[4] = 1.0925484305920792f * dx * dy;
-            sh[5] = -1.0925484305920792f * dy * dz;
-            sh[6] = 0.94617469575755997f * dz * dz - 0.31539156525251999f;
-            sh[7] = -1.0925484305920792f * dx * dz;
-            sh[8] = 0.54627421529603959f * dx * dx - 0.54627421529603959f * dy * dy;
-            sh[9] = 0.59004358992664352f * dy * (-3.0f * dx * dx + dy * dy);
-            sh[10] = 2.8906114426405538f * dx * dy * dz;
-            sh[11] = 0.45704579946446572f * dy * (1.0f - 5.0f * dz * dz);
-            sh[12] = 0.3731763325901154f * dz * (5.0f * dz * dz - 3.0f);
-            sh[13] = 0.45704579946446572f * dx * (1.0f - 5.0f * dz * dz);
-            sh[14] = 1.4453057213202769f * dz * (dx * dx - dy * dy);
-            sh[15] = 0.59004358992664352f * dx * (-dx * dx + 3.0f * dy * dy);
-            // SH coefficients are streamed 16 B at a time right where they are consumed (keeps ~50 registers
-            // free; the dot product order k = 0..15 is the oracle's)
-            float col[3];
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                float acc = 0.0f;
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    const float4 c4 = __ldg(reinterpret_cast<const float4 *>(frow) + 2 + 4 * ch + k4);
-                    if (k4 == 0) acc = c4.x * sh[0];
-                    else acc = acc + c4.x * sh[4 * k4];
-                    acc = acc + c4.y * sh[4 * k4 + 1];
-                    acc = acc + c4.z * sh[4 * k4 + 2];
-                    acc = acc + c4.w * sh[4 * k4 + 3];
-                }
-                col[ch] = sigmoid_cr(acc);
-            }
+            dir0 = dx; dir1 = dy; dir2 = dz;
             bounding_box(u, v, radius, p.W, p.H, min_tu, max_tu, min_tv, max_tv);
             ntiles = (max_tu - min_tu) * (max_tv - min_tv);
             // reach-test parameters of this splat; the (tile, splat) tests themselves are done cooperatively by
@@ -306,7 +288,7 @@ preprocess_kernel(const PreParams p) {
             if (!p.filter_tiles) reach.mode = 2;
             r0 = make_float4(u, v, inv_det * c11, inv_det * (-c01));
             r1 = make_float4(inv_det * c00, rescale, opacity, pc[2]);
-            r2 = make_float4(col[0], col[1], col[2], radius);
+            r2.w = radius;
         }
     }
 
@@ -379,13 +361,55 @@ preprocess_kernel(const PreParams p) {
         if (w < warp) warp_prefix += s;
         block_total += s;
     }
-    // ---- decoupled look-back across blocks (warp 0)
+    // ---- decoupled look-back across blocks: publish first ...
+    if (warp == 0 && lane == 0)
+        st_state(&p.scan_state[blk], (blk == 0 ? ST_INCLUSIVE : ST_AGGREGATE) | block_total);
+    // ---- SH colour (GPCR:299-310), deliberately placed AFTER this block's aggregate is published: the 192 B of
+    // coefficients per point are the longest-latency loads of the kernel and nothing upstream of the scan needs
+    // the colour, so successor blocks' look-back no longer waits for them, and this block's own look-back
+    // overlaps with them.
+    if (in) {
+        const float4 *frow = reinterpret_cast<const float4 *>(p.features + (size_t)GSB_FEATURE_DIM * i);
+                    float sh[16];
+                    sh[0] = 0.28209479177387814f;
+                    sh[1] = -0.48860251190291987f * dir1;
+                    sh[2] = 0.48860251190291987f * dir2;
+                    sh[3] = -0.48860251190291987f * dir0;
+                    sh[4] = 1.0925484305920792f * dir0 * dir1;
+                    sh[5] = -1.0925484305920792f * dir1 * dir2;
+                    sh[6] = 0.94617469575755997f * dir2 * dir2 - 0.31539156525251999f;
+                    sh[7] = -1.0925484305920792f * dir0 * dir2;
+                    sh[8] = 0.54627421529603959f * dir0 * dir0 - 0.54627421529603959f * dir1 * dir1;
+                    sh[9] = 0.59004358992664352f * dir1 * (-3.0f * dir0 * dir0 + dir1 * dir1);
+                    sh[10] = 2.8906114426405538f * dir0 * dir1 * dir2;
+                    sh[11] = 0.45704579946446572f * dir1 * (1.0f - 5.0f * dir2 * dir2);
+                    sh[12] = 0.3731763325901154f * dir2 * (5.0f * dir2 * dir2 - 3.0f);
+                    sh[13] = 0.45704579946446572f * dir0 * (1.0f - 5.0f * dir2 * dir2);
+                    sh[14] = 1.4453057213202769f * dir2 * (dir0 * dir0 - dir1 * dir1);
+                    sh[15] = 0.59004358992664352f * dir0 * (-dir0 * dir0 + 3.0f * dir1 * dir1);
+                    // SH coefficients are streamed 16 B at a time right where they are consumed (keeps ~50 registers
+                    // free; the dot product order k = 0..15 is the oracle's)
+                    float col[3];
+        #pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        float acc = 0.0f;
+        #pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const float4 c4 = __ldg(frow + 2 + 4 * ch + k4);
+                            if (k4 == 0) acc = c4.x * sh[0];
+                            else acc = acc + c4.x * sh[4 * k4];
+                            acc = acc + c4.y * sh[4 * k4 + 1];
+                            acc = acc + c4.z * sh[4 * k4 + 2];
+                            acc = acc + c4.w * sh[4 * k4 + 3];
+                        }
+                        col[ch] = sigmoid_cr(acc);
+                    }
+        r2.x = col[0]; r2.y = col[1]; r2.z = col[2];
+    }
+    // ---- ... then walk back over the predecessors (warp 0)
     if (warp == 0) {
         unsigned long long exclusive = 0;
-        if (blk == 0) {
-            if (lane == 0) st_state(&p.scan_state[0], ST_INCLUSIVE | block_total);
-        } else {
-            if (lane == 0) st_state(&p.scan_state[blk], ST_AGGREGATE | block_total);
+        if (blk != 0) {
             int look = blk - 1;
             while (true) {
                 const int idx = look - lane;
@@ -467,7 +491,7 @@ preprocess_kernel(const PreParams p) {
             if (j < nk64) {
                 const unsigned int mlo = st.mask_lo[lo];
                 const int plo = __popc(mlo);
-                idx = j < plo ? (int)__fns(mlo, 0, j + 1) : 32 + (int)__fns(st.mask_hi[lo], 0, j - plo + 1);
+                idx = j < plo ? select_bit32(mlo, j) : 32 + select_bit32(st.mask_hi[lo], j - plo);
             } else {
                 idx = 64 + (j - nk64);
             }
