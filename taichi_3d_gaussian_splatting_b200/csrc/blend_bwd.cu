@@ -3,7 +3,7 @@
 // Kernel A (loop A, GPCR:531-705): one CTA per tile replays its splat list back-to-front.  The
 // reference issues 11 global atomics per contributing (pixel, splat); here the 11 per-splat partials
 // (d/duv x2, d/dcov x3, d/dcolour x3, d/dlogit, |d/duv|, pixel count) are reduced across the warp
-// with a transposing butterfly (16 shuffles for all of them) and flushed with ONE 11-lane RED.ADD.F32
+// with a transposing butterfly (13 shuffles for all of them) and flushed with ONE 11-lane RED.ADD.F32
 // per (warp patch, splat) -- per-warp culling (common.cuh) leaves ~2 of the 8 patches per (tile, splat).
 // Kernel B (loop B, GPCR:708-772 + GPCR:1102-1125, 1167-1182): per in-frustum point chain rule to
 // xyz / q / s / SH with the SH-band masking and the constant gradient factors fused in.
@@ -40,49 +40,58 @@ __device__ __forceinline__ float sqrt_approx(float x) {  // MUFU.RSQ based, ~1 u
     return y;
 }
 
-// Reduce 16 per-lane values across the warp with 16 shuffles.  On return lane l holds in v[0] the warp
-// total of value index (l >> 1) & 15 (both lanes of a pair hold the same total).
-__device__ __forceinline__ void warp_transpose_reduce16(float (&v)[16], int lane) {
+// Reduce 11 per-lane values across the warp with 13 shuffles (transposing butterfly: at every stage a lane hands
+// one half of its live values to its partner and keeps the other half, 11 -> 6 -> 3 -> 2 -> 1; the odd value of a
+// stage is summed on both sides).  On return v[0] of lane l holds the warp total of value index
+// reduce11_slot(l); the lanes for which reduce11_writer(l) is true cover 0..10 exactly once.
+__device__ __forceinline__ void warp_transpose_reduce11(float (&v)[11], int lane) {
     {
-        const bool hi = lane & 16;
+        const bool hi = lane & 16;  // keeps values 6..10 (and a duplicate of 5), partner keeps 0..5
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float send = hi ? v[i] : v[i + 8];
-            const float keep = hi ? v[i + 8] : v[i];
+        for (int i = 0; i < 5; ++i) {
+            const float send = hi ? v[i] : v[i + 6];
+            const float keep = hi ? v[i + 6] : v[i];
             v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
         }
+        v[5] += __shfl_xor_sync(0xffffffffu, v[5], 16);
     }
     {
-        const bool hi = lane & 8;
+        const bool hi = lane & 8;  // slots 3..5 vs 0..2
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float send = hi ? v[i] : v[i + 4];
-            const float keep = hi ? v[i + 4] : v[i];
+        for (int i = 0; i < 3; ++i) {
+            const float send = hi ? v[i] : v[i + 3];
+            const float keep = hi ? v[i + 3] : v[i];
             v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
         }
     }
     {
-        const bool hi = lane & 4;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float send = hi ? v[i] : v[i + 2];
-            const float keep = hi ? v[i + 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
+        const bool hi = lane & 4;  // slot 2 vs slot 0; slot 1 on both sides
+        const float send = hi ? v[0] : v[2];
+        const float keep = hi ? v[2] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        v[1] += __shfl_xor_sync(0xffffffffu, v[1], 4);
     }
     {
-        const bool hi = lane & 2;
+        const bool hi = lane & 2;  // slot 1 vs slot 0
         const float send = hi ? v[0] : v[1];
         const float keep = hi ? v[1] : v[0];
         v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
     }
     v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
+__device__ __forceinline__ int reduce11_slot(int lane) {
+    const int s2 = (lane & 2) ? 1 : ((lane & 4) ? 2 : 0);
+    const int s1 = s2 + ((lane & 8) ? 3 : 0);
+    return (lane & 16) ? (s1 == 5 ? 5 : s1 + 6) : s1;
+}
+__device__ __forceinline__ bool reduce11_writer(int lane) {
+    if (lane & 1) return false;
+    if ((lane & 2) && (lane & 4)) return false;         // slot 1 is duplicated over bit 2
+    if ((lane & 16) && (lane & 8) && !(lane & 2) && (lane & 4)) return false;  // duplicate of value 5 in the upper half
+    return true;
+}
 
 
-#ifndef GSB_BWD_BRANCHFREE
-#define GSB_BWD_BRANCHFREE 1
-#endif
 #ifndef GSB_BWD_MIN_BLOCKS
 #define GSB_BWD_MIN_BLOCKS 4
 #endif
@@ -112,6 +121,8 @@ blend_backward_kernel(const BlendBwdParams p) {
     const float g0 = p.grad_image[3 * pix], g1 = p.grad_image[3 * pix + 1], g2 = p.grad_image[3 * pix + 2];
     float mag0 = 0.0f, mag1 = 0.0f;
     const unsigned int sa = smem_u32(s_rec);
+    const int red_slot = reduce11_slot(lane);
+    const bool red_writer = reduce11_writer(lane);
 
     // deepest effective splat of this warp's patch and of the whole tile (GPCR:609-610: nothing at or
     // behind a pixel's last effective offset contributes to it)
@@ -138,7 +149,8 @@ blend_backward_kernel(const BlendBwdParams p) {
                 const float4 *rec = p.records + 3 * (size_t)o;
                 const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
                 s_r0[tid] = r0;
-                s_r1[tid] = r1;
+                // fast path: the loop needs rescale*opacity and 1-opacity, not the two factors
+                s_r1[tid] = EXACT_EXP ? r1 : make_float4(r1.x, r1.y * r1.z, 1.0f - r1.z, r1.w);
                 s_r2[tid] = __ldg(rec + 2);
                 s_off[buf][tid] = o;
                 mask = splat_patch_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y * r1.z, tile_x0, tile_y0);
@@ -160,9 +172,8 @@ blend_backward_kernel(const BlendBwdParams p) {
                     bits &= bits - 1;
                     const int idx = block_end - 1 - j;
                     if (idx >= warp_last) continue;  // warp-uniform
-                    float v[16];
+                    float v[11];
                     bool contributes;
-#if GSB_BWD_BRANCHFREE
                     // Branch-free: every lane evaluates the splat; lanes that do not contribute (behind their
                     // last effective splat, or alpha < 1/255) get zero weights, so all partials vanish and the
                     // pixel state is left untouched by predicated selects.
@@ -174,96 +185,72 @@ blend_backward_kernel(const BlendBwdParams p) {
                         const float d0 = px - r0.x, d1 = py - r0.y;
                         const float q0 = r0.z * d0 + r0.w * d1;
                         const float q1 = r0.w * d0 + r1.x * d1;
-                        float gp;
-                        if (EXACT_EXP) gp = expf(-0.5f * (d0 * q0 + d1 * q1)) * r1.y;
-                        else gp = ex2_approx_b(-0.72134752044448170368f * (d0 * q0 + d1 * q1)) * r1.y;
-                        const float opa = r1.z;
-                        const float prod_alpha = gp * opa;
-                        contributes = (idx < last) && (prod_alpha >= 1.0f / 255.0f);
-                        const float alpha = fminf(prod_alpha, 0.99f);
-                        const float inv = EXACT_EXP ? 1.0f / (1.0f - alpha) : rcp_approx(1.0f - alpha);
-                        const float Tn = T * inv;
-                        const float aT = contributes ? alpha * Tn : 0.0f;
-                        const float a_grad = contributes ? (r2.x * Tn - w0 * inv) * g0 + (r2.y * Tn - w1 * inv) * g1 +
-                                                               (r2.z * Tn - w2 * inv) * g2
-                                                         : 0.0f;
-                        T = contributes ? Tn : T;
-                        w0 = fmaf(r2.x, aT, w0);
-                        w1 = fmaf(r2.y, aT, w1);
-                        w2 = fmaf(r2.z, aT, w2);
-                        const float G = a_grad * opa * gp;
-                        const float vs0 = G * q0, vs1 = G * q1;
-                        mag0 += fabsf(vs0);
-                        mag1 += fabsf(vs1);
-                        const float hq0 = 0.5f * G * q0;
-                        v[0] = vs0;
-                        v[1] = vs1;
-                        v[2] = hq0 * q0;
-                        v[3] = hq0 * q1;
-                        v[4] = 0.5f * G * q1 * q1;
-                        v[5] = aT * g0;
-                        v[6] = aT * g1;
-                        v[7] = aT * g2;
-                        v[8] = a_grad * gp * (1.0f - opa) * opa;
-                        v[9] = EXACT_EXP ? sqrtf(vs0 * vs0 + vs1 * vs1) : sqrt_approx(vs0 * vs0 + vs1 * vs1);
-                        v[10] = contributes ? 1.0f : 0.0f;
-#pragma unroll
-                        for (int k = 11; k < 16; ++k) v[k] = 0.0f;
-                    }
-#else
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) v[k] = 0.0f;
-                    contributes = false;
-                    if (idx < last) {
-                        const unsigned int ja = sb + j * 16;
-                        const float4 r0 = lds128<0>(ja);      // u v a b
-                        const float4 r1 = lds128<PLANE>(ja);  // c rescale opacity depth
-                        const float d0 = px - r0.x, d1 = py - r0.y;
-                        const float q0 = r0.z * d0 + r0.w * d1;  // conic @ d   (UT:337-339)
-                        const float q1 = r0.w * d0 + r1.x * d1;
-                        float gp;
-                        if (EXACT_EXP) gp = expf(-0.5f * (d0 * q0 + d1 * q1)) * r1.y;  // UT:340-342
-                        else gp = ex2_approx_b(-0.72134752044448170368f * (d0 * q0 + d1 * q1)) * r1.y;
-                        const float opa = r1.z;
-                        const float prod_alpha = gp * opa;
-                        if (prod_alpha >= 1.0f / 255.0f) {  // GPCR:634
-                            contributes = true;
+                        if (EXACT_EXP) {
+                            const float gp = expf(-0.5f * (d0 * q0 + d1 * q1)) * r1.y;
+                            const float opa = r1.z;
+                            const float prod_alpha = gp * opa;
+                            contributes = (idx < last) && (prod_alpha >= 1.0f / 255.0f);
                             const float alpha = fminf(prod_alpha, 0.99f);
-                            const float4 r2 = lds128<2 * PLANE>(ja);
-                            const float inv = EXACT_EXP ? 1.0f / (1.0f - alpha) : rcp_approx(1.0f - alpha);
-                            T = T * inv;                               // GPCR:643
-                            const float aT = alpha * T;                // d pixel / d colour (GPCR:649)
-                            const float a_grad = (r2.x * T - w0 * inv) * g0 + (r2.y * T - w1 * inv) * g1 +
-                                                 (r2.z * T - w2 * inv) * g2;  // GPCR:653-657
-                            w0 += r2.x * aT;
-                            w1 += r2.y * aT;
-                            w2 += r2.z * aT;
-                            const float g_grad = a_grad * opa;         // d/d gaussian (GPCR:662)
-                            const float vs0 = g_grad * gp * q0, vs1 = g_grad * gp * q1;  // view-space grad
+                            const float inv = 1.0f / (1.0f - alpha);
+                            const float Tn = T * inv;
+                            const float aT = contributes ? alpha * Tn : 0.0f;
+                            const float a_grad = contributes ? (r2.x * Tn - w0 * inv) * g0 + (r2.y * Tn - w1 * inv) * g1 +
+                                                                   (r2.z * Tn - w2 * inv) * g2
+                                                             : 0.0f;
+                            T = contributes ? Tn : T;
+                            w0 = fmaf(r2.x, aT, w0);
+                            w1 = fmaf(r2.y, aT, w1);
+                            w2 = fmaf(r2.z, aT, w2);
+                            const float G = a_grad * opa * gp;
+                            const float vs0 = G * q0, vs1 = G * q1;
                             mag0 += fabsf(vs0);
                             mag1 += fabsf(vs1);
-                            const float hc = 0.5f * g_grad * gp;       // UT:345: 0.5 p (S^-1 d d^T S^-1)
                             v[0] = vs0;
                             v[1] = vs1;
-                            v[2] = hc * q0 * q0;
-                            v[3] = hc * q0 * q1;
-                            v[4] = hc * q1 * q1;
+                            v[2] = vs0 * q0;  // the 1/2 of UT:345 is applied once per point in the epilogue
+                            v[3] = vs0 * q1;
+                            v[4] = vs1 * q1;
                             v[5] = aT * g0;
                             v[6] = aT * g1;
                             v[7] = aT * g2;
-                            v[8] = a_grad * gp * (1.0f - opa) * opa;   // d/d logit (GPCR:658-661)
-                            v[9] = EXACT_EXP ? sqrtf(vs0 * vs0 + vs1 * vs1)
-                                             : sqrt_approx(vs0 * vs0 + vs1 * vs1);  // GPCR:691-694
-                            v[10] = 1.0f;                              // affected-pixel count
+                            v[8] = a_grad * gp * (1.0f - opa) * opa;
+                            v[9] = sqrtf(vs0 * vs0 + vs1 * vs1);
+                        } else {
+                            // r1 = c | rescale*opacity | 1-opacity | depth.  The colour recursion of GPCR:653-657,
+                            // sum_c (col_c T - w_c/(1-a)) g_c, is carried as ONE scalar: with cg = sum_c col_c g_c and
+                            // w0 = sum_c w_c g_c it is  cg T - w0/(1-a),  and w0 += cg a T.
+                            const float P = ex2_approx_b(-0.72134752044448170368f * (d0 * q0 + d1 * q1)) * r1.y;
+                            contributes = (idx < last) && (P >= 1.0f / 255.0f);
+                            const float alpha = fminf(P, 0.99f);
+                            const float inv = rcp_approx(1.0f - alpha);
+                            const float Tn = T * inv;
+                            const float aT = contributes ? alpha * Tn : 0.0f;
+                            const float cg = fmaf(r2.z, g2, fmaf(r2.y, g1, r2.x * g0));
+                            const float a_grad = contributes ? fmaf(cg, Tn, -(w0 * inv)) : 0.0f;
+                            T = contributes ? Tn : T;
+                            w0 = fmaf(cg, aT, w0);
+                            const float G = a_grad * P;  // d L / d gaussian exponent weight: a_grad * opacity * p
+                            const float vs0 = G * q0, vs1 = G * q1;
+                            mag0 += fabsf(vs0);
+                            mag1 += fabsf(vs1);
+                            v[0] = vs0;
+                            v[1] = vs1;
+                            v[2] = vs0 * q0;
+                            v[3] = vs0 * q1;
+                            v[4] = vs1 * q1;
+                            v[5] = aT * g0;
+                            v[6] = aT * g1;
+                            v[7] = aT * g2;
+                            v[8] = G * r1.z;  // a_grad * p * opacity * (1 - opacity)
+                            v[9] = sqrt_approx(vs0 * vs0 + vs1 * vs1);
                         }
+                        v[10] = contributes ? 1.0f : 0.0f;
                     }
-#endif
                     if (__any_sync(0xffffffffu, contributes)) {
                         // 11 partials of this (warp, splat) -> 11 lanes -> one RED.ADD.F32 row update
-                        warp_transpose_reduce16(v, lane);
-                        const int k = (lane >> 1) & 15;
-                        if ((lane & 1) == 0 && k < 11)
-                            atomicAdd(p.accum + (size_t)s_off[buf][j] * GSB_ACCUM_FLOATS + k, v[0]);
+                        warp_transpose_reduce11(v, lane);
+                        if (red_writer)
+                            atomicAdd(p.accum + (size_t)s_off[buf][j] * GSB_ACCUM_FLOATS + red_slot, v[0]);
                     }
                 }
             }
@@ -372,7 +359,7 @@ backward_points_kernel(const PointsBwdParams p) {
             U[c] = J[0] * Wm[c] + J[1] * Wm[3 + c] + J[2] * Wm[6 + c];
             U[3 + c] = J[3] * Wm[c] + J[4] * Wm[3 + c] + J[5] * Wm[6 + c];
         }
-        const float g00 = a0.z, g01 = a0.w, g11 = a1.x;
+        const float g00 = 0.5f * a0.z, g01 = 0.5f * a0.w, g11 = 0.5f * a1.x;  // UT:345's 1/2, see the blend loop
         // V = U^T G U  (dL/dSigma with the (g00,g01,g01,g11) weighting of GPCR:716-721)
         float V[9];
 #pragma unroll

@@ -86,7 +86,7 @@ constexpr int SORT_BLOCK_THREADS = 256;
 constexpr int SORT_ITEMS_PER_THREAD = GSB_SORT_ITEMS;
 constexpr int SORT_TILE = SORT_BLOCK_THREADS * SORT_ITEMS_PER_THREAD;  // 4096 keys per CTA
 #ifndef GSB_SCAN_THREADS
-#define GSB_SCAN_THREADS 256
+#define GSB_SCAN_THREADS 128
 #endif
 constexpr int SCAN_BLOCK_THREADS = GSB_SCAN_THREADS;
 

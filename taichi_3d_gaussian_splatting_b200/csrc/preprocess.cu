@@ -144,7 +144,7 @@ __device__ __forceinline__ void bounding_box(float u, float v, float radii, int 
 }
 
 #ifndef GSB_PRE_MIN_BLOCKS
-#define GSB_PRE_MIN_BLOCKS 4
+#define GSB_PRE_MIN_BLOCKS 8
 #endif
 // Per-warp staging area of the cooperative reach filter / key emission (32 splats of the warp).
 struct WarpStage {
