@@ -156,7 +156,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from taichi_3d_gaussian_splatting_b200 import GaussianPointCloudRasterisation as GPCR
-    from taichi_3d_gaussian_splatting_b200 import profiling
+    from taichi_3d_gaussian_splatting_b200 import fused_l1_loss_with_grad, profiling
     from taichi_3d_gaussian_splatting_b200.parallel import exchange_gradients
     from taichi_3d_gaussian_splatting_b200.synthetic import C4_YAWS, CONFIGS, make_scene
 
@@ -262,20 +262,34 @@ def run_b200(args):
             slot["K"].copy_(K_host, non_blocking=True)
             slot["ready"].record(copy_stream)
 
+    # The step's loss goes to pinned host memory with an async copy and is read one step later (what a
+    # training loop that logs its loss does); every step's loss is read inside the timed region.
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_done = [torch.cuda.Event() for _ in range(2)]
+    e2e_losses = []
+
     def run_e2e(k):
+        e2e_losses.clear()
         upload(slots[0])
         for i in range(k):
-            if i + 1 < k:
-                upload(slots[(i + 1) % 2])  # overlaps with this step's compute
             slot = slots[i % 2]
             torch.cuda.current_stream().wait_event(slot["ready"])
             scene.point_cloud.grad = None
             scene.point_cloud_features.grad = None
             image, _, _ = op(make_input(slot["q"], slot["t"], slot["K"]))
-            loss = (image - slot["target"]).abs().mean()
-            loss.backward()
+            # fused L1 loss + gradient (gsb200_l1_loss), then the operator's backward
+            loss, grad = fused_l1_loss_with_grad(image, slot["target"])
+            image.backward(grad)
             exchange_grads()
-            float(loss.item())  # D2H read of the step's result (also orders slot reuse)
+            loss_host[i % 2].copy_(loss, non_blocking=True)
+            loss_done[i % 2].record()
+            if i > 0:  # D2H read of the previous step's result; also frees its input slot for the next upload
+                loss_done[(i - 1) % 2].synchronize()
+                e2e_losses.append(float(loss_host[(i - 1) % 2]))
+            if i + 1 < k:
+                upload(slots[(i + 1) % 2])  # overlaps with this step's compute
+        loss_done[(k - 1) % 2].synchronize()
+        e2e_losses.append(float(loss_host[(k - 1) % 2]))
 
     run_e2e(3)
     e2e_ms = timed(lambda: run_e2e(steps), 1) / steps
@@ -436,7 +450,7 @@ def run_b200(args):
                    "l2": "inputs larger than L2 (scene 236 MB + 200 MB workspace per frame vs 126 MB L2)"},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(e2e_ms, 4),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "what": "per step: pinned host target image + pose + intrinsics -> device (copy stream, one step ahead), forward, L1 loss, backward, loss.item()"},
+                "what": "per step: pinned host target image + pose + intrinsics -> device (copy stream, one step ahead), forward, fused L1 loss + gradient kernel, backward, loss -> pinned host (read one step later, all inside the timed region)"},
         "forward_only": {"Mpix_s": round(world * H * W / (fwd_ms * 1e-3) / 1e6, 2), "ms": round(fwd_ms, 4),
                          "rgb_only_Mpix_s": round(world * H * W / (fwd_rgb_ms * 1e-3) / 1e6, 2),
                          "rgb_only_ms": round(fwd_rgb_ms, 4)},

@@ -205,6 +205,17 @@ int gsb200_render_host(const GsbForwardArgs *device_args, const float *host_q_po
                        float *staging_device_pose /* >= num_objects*7+9 floats, device */,
                        float *host_image_out /* (H,W,3) */, int64_t *host_counters_out /* int64[4] or NULL */);
 
+/* Fused clamp + L1 loss + gradient for the trainer step around the operator:
+ * loss = mean |clamp01(pred) - gt| (GaussianPointTrainer.py:168-170 clamp, LossFunction.py:29 L1) and, when
+ * grad_predicted_out is not NULL, d(upstream_grad * loss)/d pred = upstream_grad * sign(.)/n inside the clamp
+ * range, 0 outside -- what torch autograd produces with ~8 elementwise kernels.  All pointers are device
+ * memory, 16-byte aligned; temp holds gsb200_l1_loss_temp_bytes() bytes and must be ZERO before its first use
+ * (the call leaves it ready for the next one).  Deterministic (fixed grid, fixed summation order). */
+int64_t gsb200_l1_loss_temp_bytes(void);
+int gsb200_l1_loss(const float *predicted_image, const float *ground_truth_image, int64_t num_elements,
+                   int32_t clamp01, float upstream_grad, float *loss_out, float *grad_predicted_out, void *temp,
+                   int64_t temp_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

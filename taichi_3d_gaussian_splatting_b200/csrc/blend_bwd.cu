@@ -305,23 +305,31 @@ struct PointsBwdParams {
 };
 
 #ifndef GSB_POINTS_THREADS
-#define GSB_POINTS_THREADS 256
+#define GSB_POINTS_THREADS 128
 #endif
-__global__ void __launch_bounds__(GSB_POINTS_THREADS)
+constexpr int PT_ROW = 60;  // staged feature row stride in floats: 16-B aligned, float4 stores of 8 lanes hit 32 banks
+__global__ void __launch_bounds__(GSB_POINTS_THREADS, 6)  // 6 x 33 KB of staging per SM
 backward_points_kernel(const PointsBwdParams p) {
     // One thread per scene row: rows outside the frustum get their zeros here (no separate memset of the
-    // dense (N,3)/(N,56) gradients), rows inside get the chain rule.
+    // dense (N,3)/(N,56) gradients), rows inside get the chain rule.  A warp owns 32 consecutive rows, i.e. one
+    // contiguous 7 KB piece of the (N,56) gradient and 384 B of the (N,3) one: each lane stages its row in
+    // shared memory and the warp then streams the piece out with full 512-B stores (a lane writing its own
+    // 224-B row directly touches 32 different lines per store instruction and stalls on the LSU queue).
+    __shared__ __align__(16) float s_feat[GSB_POINTS_THREADS / 32][32 * PT_ROW];
+    __shared__ float s_xyz[GSB_POINTS_THREADS / 32][96];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *const my_feat = &s_feat[warp][lane * PT_ROW];
+    float *const my_xyz = &s_xyz[warp][lane * 3];
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < p.N; id += stride) {
-        const int o = p.point_offset[id];
-        if (o < 0) {
-            float *gxz = p.grad_xyz + 3 * (size_t)id;
-            gxz[0] = 0.0f; gxz[1] = 0.0f; gxz[2] = 0.0f;
-            float4 *gz = reinterpret_cast<float4 *>(p.grad_feat + (size_t)GSB_FEATURE_DIM * id);
+    for (long long base = (long long)blockIdx.x * blockDim.x + warp * 32; base < p.N; base += stride) {
+      const long long id = base + lane;
+      const int o = id < p.N ? p.point_offset[id] : -1;
+      if (o < 0) {
+          my_xyz[0] = 0.0f; my_xyz[1] = 0.0f; my_xyz[2] = 0.0f;
 #pragma unroll
-            for (int k = 0; k < GSB_FEATURE_DIM / 4; ++k) gz[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            continue;
-        }
+          for (int k = 0; k < GSB_FEATURE_DIM / 4; ++k)
+              reinterpret_cast<float4 *>(my_feat)[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      } else {
         const float4 *accp = reinterpret_cast<const float4 *>(p.accum + (size_t)o * GSB_ACCUM_FLOATS);
         const float4 a0 = accp[0], a1 = accp[1], a2 = accp[2];
         // a0 = guv.x guv.y g00 g01 | a1 = g11 gr gg gb | a2 = glogit mag n pad
@@ -427,9 +435,8 @@ backward_points_kernel(const PointsBwdParams p) {
         const float gcol[3] = {a1.y * (r2.x * (1.0f - r2.x)), a1.z * (r2.y * (1.0f - r2.y)),
                                a1.w * (r2.z * (1.0f - r2.z))};
 
-        float *gxp = p.grad_xyz + 3 * (size_t)id;
-        gxp[0] = gx[0]; gxp[1] = gx[1]; gxp[2] = gx[2];
-        float4 *gf = reinterpret_cast<float4 *>(p.grad_feat + (size_t)GSB_FEATURE_DIM * id);
+        my_xyz[0] = gx[0]; my_xyz[1] = gx[1]; my_xyz[2] = gx[2];
+        float4 *gf = reinterpret_cast<float4 *>(my_feat);
         gf[0] = make_float4(gq[0] * p.q_f, gq[1] * p.q_f, gq[2] * p.q_f, gq[3] * p.q_f);
         gf[1] = make_float4(gs[0] * p.s_f, gs[1] * p.s_f, gs[2] * p.s_f, a2.x * p.a_f);
 #pragma unroll
@@ -444,6 +451,24 @@ backward_points_kernel(const PointsBwdParams p) {
             for (int k4 = 0; k4 < 4; ++k4)
                 gf[2 + 4 * ch + k4] = make_float4(o16[4 * k4], o16[4 * k4 + 1], o16[4 * k4 + 2], o16[4 * k4 + 3]);
         }
+      }
+      __syncwarp();
+      // stream the warp's 32 rows out: 14 x 512 B of feature gradients, 3 x 128 B of position gradients
+      const long long rows = p.N - base < 32 ? p.N - base : 32;
+      float4 *const out_f = reinterpret_cast<float4 *>(p.grad_feat + (size_t)GSB_FEATURE_DIM * base);
+#pragma unroll
+      for (int it = 0; it < GSB_FEATURE_DIM / 4; ++it) {
+          const int f = it * 32 + lane;           // float4 index inside the piece
+          const int row = f / (GSB_FEATURE_DIM / 4), c4 = f - row * (GSB_FEATURE_DIM / 4);
+          if (row < rows) out_f[f] = *reinterpret_cast<const float4 *>(&s_feat[warp][row * PT_ROW + 4 * c4]);
+      }
+      float *const out_x = p.grad_xyz + 3 * (size_t)base;
+#pragma unroll
+      for (int it = 0; it < 3; ++it) {
+          const int f = it * 32 + lane;
+          if (f < 3 * rows) out_x[f] = s_xyz[warp][f];
+      }
+      __syncwarp();
     }
 }
 

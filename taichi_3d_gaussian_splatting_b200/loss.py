@@ -44,6 +44,60 @@ def ssim(x: torch.Tensor, y: torch.Tensor, data_range: float = 1.0, size_average
     return per_channel.mean() if size_average else per_channel.mean(1)
 
 
+_l1_temp = {}
+
+
+def fused_l1_loss_with_grad(predicted_image: torch.Tensor, ground_truth_image: torch.Tensor, clamp01: bool = False,
+                            weight: float = 1.0, want_grad: bool = True):
+    """``weight * mean|clamp01(pred) - gt|`` and its gradient w.r.t. ``pred`` in ONE CUDA kernel
+    (``gsb200_l1_loss``; clamp of GaussianPointTrainer.py:168-170 + L1 of LossFunction.py:29).
+    Returns ``(loss, grad)``: ``loss`` is a 0-dim device tensor holding the UNWEIGHTED mean, ``grad`` already
+    carries ``weight`` -- feed it to ``image.backward(grad)``.  CUDA float32 contiguous tensors only: there is
+    no CPU path."""
+    from . import _lib
+    if not (predicted_image.is_cuda and ground_truth_image.is_cuda):
+        raise RuntimeError("fused_l1_loss_with_grad needs CUDA tensors (there is no CPU path)")
+    if predicted_image.dtype != torch.float32 or ground_truth_image.dtype != torch.float32:
+        raise RuntimeError("fused_l1_loss_with_grad needs float32 tensors")
+    if predicted_image.shape != ground_truth_image.shape:
+        raise RuntimeError("fused_l1_loss_with_grad: shape mismatch")
+    pred = predicted_image.detach().contiguous()
+    gt = ground_truth_image.detach().contiguous()
+    lib = _lib.load()
+    stream = torch.cuda.current_stream(pred.device)
+    key = (pred.device.index, stream.cuda_stream)
+    temp = _l1_temp.get(key)
+    if temp is None:
+        temp = torch.zeros(int(lib.gsb200_l1_loss_temp_bytes()), dtype=torch.uint8, device=pred.device)
+        _l1_temp[key] = temp
+    loss = torch.empty((), dtype=torch.float32, device=pred.device)
+    grad = torch.empty_like(pred) if want_grad else None
+    _lib.check(lib.gsb200_l1_loss(pred.data_ptr(), gt.data_ptr(), pred.numel(), int(bool(clamp01)), float(weight),
+                                  loss.data_ptr(), grad.data_ptr() if want_grad else None, temp.data_ptr(),
+                                  temp.numel(), stream.cuda_stream), "gsb200_l1_loss")
+    return loss, grad
+
+
+class _FusedL1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, predicted_image, ground_truth_image, clamp01):
+        loss, grad = fused_l1_loss_with_grad(predicted_image, ground_truth_image, clamp01,
+                                             want_grad=predicted_image.requires_grad)
+        ctx.grad = grad
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        grad = ctx.grad
+        ctx.grad = None
+        return (grad * grad_output if grad is not None else None), None, None
+
+
+def fused_l1_loss(predicted_image: torch.Tensor, ground_truth_image: torch.Tensor, clamp01: bool = False):
+    """Differentiable form of :func:`fused_l1_loss_with_grad` (one extra scaling kernel in backward)."""
+    return _FusedL1.apply(predicted_image, ground_truth_image, clamp01)
+
+
 class LossFunction(nn.Module):
     @dataclass
     class LossFunctionConfig:
