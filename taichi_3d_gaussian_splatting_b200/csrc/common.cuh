@@ -77,14 +77,14 @@ int sort_pairs_device(const void *keys_in, const int *vals_in, void *keys_out, i
                       long long *sel_out, cudaStream_t stream);
 
 #ifndef GSB_SORT_ITEMS
-#define GSB_SORT_ITEMS 16
+#define GSB_SORT_ITEMS 12
 #endif
 #ifndef GSB_SORT_MIN_BLOCKS
 #define GSB_SORT_MIN_BLOCKS 3
 #endif
 constexpr int SORT_BLOCK_THREADS = 256;
 constexpr int SORT_ITEMS_PER_THREAD = GSB_SORT_ITEMS;
-constexpr int SORT_TILE = SORT_BLOCK_THREADS * SORT_ITEMS_PER_THREAD;  // 4096 keys per CTA
+constexpr int SORT_TILE = SORT_BLOCK_THREADS * SORT_ITEMS_PER_THREAD;  // 3072 keys per CTA
 #ifndef GSB_SCAN_THREADS
 #define GSB_SCAN_THREADS 128
 #endif

@@ -2,7 +2,7 @@
 // (replaces torch.sort + gather, GPCR:947-950) and the per-tile range detection (GPCR:175-193).
 //
 // One-sweep organisation: one histogram kernel builds the digit histograms of every pass; each
-// pass is a single kernel in which a CTA (a) pulls its 4096-key tile into shared memory with one
+// pass is a single kernel in which a CTA (a) pulls its 3072-key tile into shared memory with one
 // TMA bulk copy (cp.async.bulk + mbarrier -> SASS UBLKCP), (b) ranks the keys stably with
 // warp-level match_any, (c) obtains the global digit offsets by a per-digit decoupled look-back
 // over the preceding CTAs, and (d) scatters keys and payloads from a block-sorted shared-memory

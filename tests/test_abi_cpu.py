@@ -29,7 +29,7 @@ def test_workspace_layout_arithmetic():
     L = _lib.workspace_layout(1_000_000, 1, 8_000_000, 1072, 1920, 1000.0, 100.0, 0)
     assert (L.key_bytes, L.tile_bits, L.depth_bits, L.radix_bits, L.sort_passes) == (4, 13, 17, 8, 4)  # 8040 tiles, keys <= 1e5
     assert L.scan_blocks == (1_000_000 + 127) // 128  # preprocess CTAs of 128 points
-    assert L.key_capacity_padded % 4096 == 0 and L.key_capacity_padded >= 8_000_000
+    assert L.key_capacity_padded % 3072 == 0 and L.key_capacity_padded >= 8_000_000  # sort CTAs of 3072 keys
     offs = [L.counters, L.tickets, L.scan_state, L.sort_hist, L.sort_state, L.tile_start, L.tile_end,
             L.poses, L.point_id, L.num_tiles, L.records, L.point_in_camera, L.keys_a, L.keys_b, L.vals_a, L.vals_b]
     assert offs == sorted(offs) and all(o % 256 == 0 for o in offs)
