@@ -421,7 +421,7 @@ def run_b200(args):
         "launch_ms": round(stage_ms[dominant], 4),
         "note": "achieved = algorithmic bytes (88K + 28HW, SURVEY 8(d)) / CUDA-event duration of the kernel. The blend "
                 "kernels reuse each 48-B splat record across up to 256 pixels, so they are bound by instruction "
-                "issue (ncu: 82 % of issue slots active, DRAM throughput 1.3 %), not by HBM; pixel x splat "
+                "issue (ncu: 83 % of issue slots active, 969 M warp instructions per frame, DRAM throughput 2.1 %), not by HBM; pixel x splat "
                 "evaluations (upper bound 256*K) per second are given beside it. traffic = ncu dram bytes per launch.",
         "pixel_splat_evals_per_s_upper": round(evals / (stage_ms[dominant] * 1e-3), 1),
         "per_stage": per_stage,
