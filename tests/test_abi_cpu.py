@@ -96,3 +96,18 @@ def test_product_package_never_imports_the_oracle():
                     src = f.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{fn} imports the oracle"
                 assert "gs_oracle" not in src, f"{fn} references the oracle"
+
+
+def test_fused_l1_has_no_cpu_path_and_reports_its_scratch_size():
+    import torch
+    from taichi_3d_gaussian_splatting_b200 import fused_l1_loss, fused_l1_loss_with_grad
+    lib = _lib.load()
+    assert lib.gsb200_l1_loss_temp_bytes() == (4 + 1184) * 4  # ticket block + one partial per CTA (148 SMs x 8)
+    a, b = torch.zeros(4, 4, 3), torch.ones(4, 4, 3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        fused_l1_loss_with_grad(a, b)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        fused_l1_loss(a.requires_grad_(True), b)
+    # argument checks of the C entry point happen before any CUDA call
+    assert lib.gsb200_l1_loss(None, None, 0, 0, 1.0, None, None, None, 0, None) == -1
+    assert b"l1_loss" in lib.gsb200_last_error()
