@@ -164,14 +164,17 @@ blend_backward_kernel(const BlendBwdParams p) {
         __syncthreads();
         const unsigned int sb = sa + buf * (3 * PLANE);
         if (block_start < warp_last) {  // otherwise every splat of this batch is behind the whole patch
+            // element j <-> sorted index block_end-1-j: the first `skip` elements of the batch lie at or behind the
+            // patch's deepest effective splat and are dropped from the bit lists wholesale (warp-uniform)
+            const int skip = block_end - warp_last;
 #pragma unroll 1
-            for (int lw = 0; lw < 8; ++lw) {
+            for (int lw = skip > 0 ? (skip >> 5) : 0; lw < 8; ++lw) {
                 unsigned int bits = s_bits[buf][warp][lw];
+                if (skip > lw * 32) bits &= ~((1u << (skip - lw * 32)) - 1u);  // 0 < skip - 32 lw < 32 here
                 while (bits) {
                     const int j = lw * 32 + __ffs(bits) - 1;
                     bits &= bits - 1;
                     const int idx = block_end - 1 - j;
-                    if (idx >= warp_last) continue;  // warp-uniform
                     float v[11];
                     bool contributes;
                     // Branch-free: every lane evaluates the splat; lanes that do not contribute (behind their
