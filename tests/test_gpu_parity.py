@@ -162,6 +162,32 @@ def test_small_scene_sh3_vs_oracle(seed, band, scale):
         assert grad_close(gf[:, sl], bwd.grad_pointcloud_features[:, sl])[0], grad_close(gf[:, sl], bwd.grad_pointcloud_features[:, sl])
 
 
+@pytest.mark.parametrize("keep_all", [False, True])
+@pytest.mark.parametrize("sigma", [0.3, 0.6])
+def test_large_splats_vs_oracle(sigma, keep_all):
+    """Splats whose 3-sigma square spans 17..96 tiles of a 12 x 8 tile image (several hundred of them cover more
+    than 64 tiles): the cooperative reach filter tests only the first 64 tiles of a splat and keeps the rest, and
+    the per-tile lists run to ~1000 entries before the pixels saturate."""
+    scene = make_scene(1500, 128, 192, sigma, 31, sh_degree=3, yaw_degrees=4.0)
+    scene.point_cloud_features[:, 7] -= 2.0  # low opacity: long lists before saturation
+    o, fwd, feats_n = oracle_forward(scene)
+    assert int((fwd.num_overlap_tiles > 64).sum()) >= 20 and int(fwd.num_overlap_tiles.max()) == 96
+    sc = cuda_scene(scene, requires_grad=True)
+    op = make_op(exact_exp=True, keep_all_tile_pairs=keep_all)
+    image, depth, count = run_forward(op, sc, band=3)
+    _check_stages(op.last_frame, fwd)
+    assert np.abs(n(image) - fwd.image).max() <= 1e-4
+    assert (n(count) == fwd.pixel_valid_point_count).all()
+    g = torch.Generator().manual_seed(9)
+    grad_image = torch.randn(image.shape, generator=g, dtype=torch.float32)
+    image.backward(grad_image.cuda())
+    bwd = oracle_backward(o, fwd, scene, feats_n, grad_image.numpy(), 3)
+    assert grad_close(n(sc.point_cloud.grad), bwd.grad_pointcloud)[0], grad_close(n(sc.point_cloud.grad), bwd.grad_pointcloud)
+    gf = n(sc.point_cloud_features.grad)
+    for sl in (slice(0, 4), slice(4, 7), slice(7, 8), slice(8, 56)):
+        assert grad_close(gf[:, sl], bwd.grad_pointcloud_features[:, sl])[0], grad_close(gf[:, sl], bwd.grad_pointcloud_features[:, sl])
+
+
 def test_two_points_scene_golden():
     """Scene of reference tests/GaussianPointCloudRasterisation_test.py:152-205, hand-derived values
      through the CUDA path."""
