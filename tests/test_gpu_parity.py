@@ -176,8 +176,11 @@ def test_large_splats_vs_oracle(sigma, keep_all):
     op = make_op(exact_exp=True, keep_all_tile_pairs=keep_all)
     image, depth, count = run_forward(op, sc, band=3)
     _check_stages(op.last_frame, fwd)
-    assert np.abs(n(image) - fwd.image).max() <= 1e-4
-    assert (n(count) == fwd.pixel_valid_point_count).all()
+    # up to 1.7e7 (pixel, splat) evaluations: allow the odd pair that sits within an ulp of the alpha = 1/255 cut-off
+    # to fall on the other side of it (CUDA expf vs libm expf), as in the full-size test
+    d = np.abs(n(image) - fwd.image)
+    assert (d > 1e-4).sum() <= 3 and d.max() <= 5e-3
+    assert count_above(n(count), fwd.pixel_valid_point_count, 0) <= 3
     g = torch.Generator().manual_seed(9)
     grad_image = torch.randn(image.shape, generator=g, dtype=torch.float32)
     image.backward(grad_image.cuda())
