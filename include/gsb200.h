@@ -60,7 +60,7 @@ typedef struct GsbWorkspaceLayout {
     int64_t counters;          /* int64[8]: [0]=M in-frustum points, [1]=K (tile,splat) pairs emitted/needed,
                                   [2]=overflow (K > key_capacity), [3]=sorted-buffer selector (0=a,1=b) */
     int64_t tickets;           /* uint32[16] dynamic block tickets */
-    int64_t scan_state;        /* uint64[ceil(N/256)+1] decoupled look-back state of the compaction scan */
+    int64_t scan_state;        /* uint64[scan_blocks+1] decoupled look-back state of the compaction scan (one word per 128-point CTA) */
     int64_t sort_hist;         /* uint32[8][1024] global digit histograms */
     int64_t sort_state;        /* uint32[passes][sort_blocks][2^radix_bits] onesweep look-back state */
     int64_t tile_start;        /* int32[T]  GPCR:952-957 tile_points_start */
