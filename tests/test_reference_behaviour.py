@@ -135,3 +135,41 @@ def test_backward_coverage(backend):
         losses.append(float(loss.detach()))
     assert losses[-1] < losses[0]  # :351
     assert min(losses[-5:]) < 0.9 * losses[0]
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_adaptive_controller_basic(backend):
+    """tests/GaussianPointAdaptiveController_test.py:15-98 ("ensure the code can run"): 10 000 slots of which 1000 hold
+    Gaussians, the controller's ``update`` as backward hook, ``refinement()`` after every optimiser step.  The warm-up /
+    densify intervals are shortened so that densification happens within the reduced iteration count."""
+    from taichi_3d_gaussian_splatting_b200 import GaussianPointAdaptiveController
+    num_points, iterations = (10000, 330) if backend == "cuda" else (4000, 130)
+    device = torch.device("cuda:0" if backend == "cuda" else "cpu")
+    point_cloud, features, mask, obj, camera_info, _, _ = _coverage_scene(num_points, device, seed=3)
+    mask[1000:] = 1  # :34
+    q = torch.tensor([[0.0, 0.0, 0.0, 1.0]], device=device)  # :53-54
+    t = torch.tensor([[0.0, 0.0, -2.0]], device=device)
+    controller = GaussianPointAdaptiveController(
+        config=GaussianPointAdaptiveController.GaussianPointAdaptiveControllerConfig(
+            num_iterations_warm_up=100, num_iterations_densify=20),
+        maintained_parameters=GaussianPointAdaptiveController.GaussianPointAdaptiveControllerMaintainedParameters(
+            pointcloud=point_cloud, pointcloud_features=features, point_invalid_mask=mask, point_object_id=obj),
+        generator=torch.Generator().manual_seed(0) if backend == "oracle" else None)
+    rasterisation, _ = _rasteriser(backend, hook=controller.update, near_plane=1.0, far_plane=10.0)
+    fake_image = _fake_image(device)
+    optimizer = torch.optim.Adam([point_cloud, features], lr=0.001)
+    losses = []
+    for idx in range(iterations):
+        optimizer.zero_grad()
+        pred_image, _, _ = rasterisation(GPCR.GaussianPointCloudRasterisationInput(
+            point_cloud=point_cloud, point_cloud_features=features, point_object_id=obj, point_invalid_mask=mask,
+            camera_info=camera_info, q_pointcloud_camera=q, t_pointcloud_camera=t, color_max_sh_band=idx // 100))
+        loss = ((pred_image - fake_image) ** 2).sum()
+        loss.backward()
+        optimizer.step()
+        controller.refinement()
+        losses.append(float(loss.detach()))
+    assert losses[-1] < losses[0]  # :98
+    num_valid = int((mask == 0).sum())
+    assert 1000 < num_valid <= num_points  # densification filled free slots
+    assert bool(torch.isfinite(point_cloud).all()) and bool(torch.isfinite(features).all())
