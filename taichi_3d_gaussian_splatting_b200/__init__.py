@@ -7,6 +7,7 @@ from .Camera import CameraInfo, CameraView  # noqa: F401
 from .densification import GaussianPointAdaptiveController  # noqa: F401
 from .loss import LossFunction, fused_l1_loss, fused_l1_loss_with_grad  # noqa: F401
 from .scene_io import GaussianPointCloudScene  # noqa: F401
+from .image_pose_dataset import ImagePoseDataset  # noqa: F401
 from .GaussianPointCloudRasterisation import (  # noqa: F401
     BOUNDARY_TILES,
     TILE_HEIGHT,
@@ -16,5 +17,5 @@ from .GaussianPointCloudRasterisation import (  # noqa: F401
 )
 
 __all__ = ["CameraInfo", "CameraView", "GaussianPointCloudRasterisation", "GaussianPointAdaptiveController",
-           "LossFunction", "fused_l1_loss", "fused_l1_loss_with_grad", "GaussianPointCloudScene", "find_tile_start_and_end",
+           "LossFunction", "fused_l1_loss", "fused_l1_loss_with_grad", "GaussianPointCloudScene", "ImagePoseDataset", "find_tile_start_and_end",
            "TILE_WIDTH", "TILE_HEIGHT", "BOUNDARY_TILES"]
