@@ -97,8 +97,9 @@ class GaussianPointCloudScene(nn.Module):
     def __init__(self, point_cloud: Union[np.ndarray, torch.Tensor], config: "GaussianPointCloudScene.PointCloudSceneConfig",
                  point_cloud_features: Optional[torch.Tensor] = None, point_object_id: Optional[torch.Tensor] = None):
         super().__init__()
-        point_cloud = torch.as_tensor(np.asarray(point_cloud) if isinstance(point_cloud, np.ndarray) else point_cloud,
-                                      dtype=torch.float32)
+        if isinstance(point_cloud, np.ndarray):
+            point_cloud = torch.tensor(point_cloud, dtype=torch.float32)  # copies (pandas hands out read-only views)
+        point_cloud = torch.as_tensor(point_cloud, dtype=torch.float32)
         if point_cloud.dim() != 2 or point_cloud.shape[1] != 3:
             raise ValueError("point_cloud must be (N, 3)")
         num_points = point_cloud.shape[0]

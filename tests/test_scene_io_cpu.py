@@ -82,3 +82,53 @@ def test_ply_layout_and_round_trip(tmp_path):
     assert torch.allclose(back.point_cloud_features.detach(), feat, atol=1e-6)
     v = read_ply_vertices(path)
     assert set(v) == set(PLY_PROPERTIES) and v["x"].shape == (37,)
+
+
+# ---------------------------------------------------------------- against the REFERENCE's own scene class
+# tests/golden/make_scene_golden.py ran /root/reference's GaussianPointCloudScene on sparse_points.parquet and stored
+# what it built (scene_vectors.json) and wrote (reference_scene.parquet); it also verified that the reference loads a
+# parquet written by our class with identical tensors.
+def _scene_golden():
+    import json
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with open(os.path.join(here, "scene_vectors.json")) as f:
+        return here, json.load(f)
+
+
+def test_reads_the_parquet_the_reference_wrote():
+    import os
+    here, ref = _scene_golden()
+    assert ref["reference_reads_our_parquet"] is True
+    scene = Scene.from_parquet(os.path.join(here, "reference_scene.parquet"))
+    valid = np.array(ref["point_invalid_mask"]) == 0
+    assert scene.point_cloud.shape == (int(valid.sum()), 3)
+    assert np.array_equal(scene.point_cloud.detach().numpy(), np.array(ref["point_cloud"], dtype=np.float32)[valid])
+    assert np.array_equal(scene.point_cloud_features.detach().numpy(),
+                          np.array(ref["point_cloud_features"], dtype=np.float32)[valid])
+
+
+def test_initialisation_from_a_sparse_cloud_matches_the_reference():
+    import os
+    here, ref = _scene_golden()
+    cfg = Scene.PointCloudSceneConfig(**ref["config"])
+    scene = Scene.from_parquet(os.path.join(here, "sparse_points.parquet"), config=cfg)
+    exp_xyz = np.array(ref["point_cloud"], dtype=np.float32)
+    exp_f = np.array(ref["point_cloud_features"], dtype=np.float32)
+    assert scene.point_cloud.shape == exp_xyz.shape == (100, 3)  # 40 points x max_num_points_ratio 2.5
+    assert scene.point_invalid_mask.tolist() == ref["point_invalid_mask"]
+    assert scene.point_object_id.tolist() == ref["point_object_id"]
+    assert np.array_equal(scene.point_cloud.detach().numpy(), exp_xyz)
+    f = scene.point_cloud_features.detach().numpy()
+    valid = np.array(ref["point_invalid_mask"]) == 0
+    # everything except the random unit quaternion is deterministic: kNN log-scales (ratio 0.7, clipped at 0.4),
+    # opacity logit, SH DC from the 0..255 colours (clamped to 0.99; a zero channel gives -inf like the reference)
+    assert np.allclose(f[:, 4:7], exp_f[:, 4:7], rtol=0, atol=1e-6)
+    assert np.array_equal(f[:, 7], exp_f[:, 7]) and float(f[0, 7]) == -1.5
+    with np.errstate(invalid="ignore"):
+        same = (f[:, 8:] == exp_f[:, 8:]) | (np.abs(f[:, 8:] - exp_f[:, 8:]) <= 1e-5 * np.abs(exp_f[:, 8:]))
+    assert same.all()
+    assert np.isneginf(f[0, 24]) and np.isneginf(exp_f[0, 24])  # g = 0 on point 0
+    assert np.allclose(np.linalg.norm(f[:, 0:4], axis=1), 1.0, atol=1e-6)
+    assert np.allclose(np.linalg.norm(exp_f[:, 0:4], axis=1), 1.0, atol=1e-6)
+    assert (f[~valid, 4:7] == 0).all() and (exp_f[~valid, 4:7] == 0).all()
