@@ -109,3 +109,59 @@ def test_trainer_loop_with_oracle_reduces_loss_and_densifies():
     assert psnr1 > psnr0 + 2.0, (psnr0, psnr1)
     assert np.mean([h["loss"] for h in hist[-8:]]) < 0.8 * np.mean([h["loss"] for h in hist[:8]])
     assert hist[-1]["num_valid_points"] > hist[0]["num_valid_points"]  # densification added points
+
+
+def test_controller_trajectory_matches_the_reference_class():
+    """tests/golden/make_controller_golden.py ran the REFERENCE's GaussianPointAdaptiveController (imported from
+    /root/reference, Taichi / matplotlib stubbed) on the scenario of tests/golden/controller_fixture.py and stored, per
+    iteration, the points it decided to remove / densify and every maintained tensor and accumulator.  Ours must follow
+    the same trajectory: identical ids and masks, float tensors to 1e-6."""
+    import json
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    from controller_fixture import CONFIG, ITERATIONS, hook_fields, initial_state
+    from taichi_3d_gaussian_splatting_b200 import GaussianPointAdaptiveController as C
+    from taichi_3d_gaussian_splatting_b200 import GaussianPointCloudRasterisation as R
+    with open(os.path.join(here, "controller_vectors.json")) as f:
+        golden = json.load(f)
+    assert len(golden) == ITERATIONS
+    xyz, feat, mask, obj = initial_state()
+    ctl = C(config=C.GaussianPointAdaptiveControllerConfig(**CONFIG),
+            maintained_parameters=C.GaussianPointAdaptiveControllerMaintainedParameters(
+                pointcloud=xyz, pointcloud_features=feat, point_invalid_mask=mask, point_object_id=obj))
+
+    def close(a, b):
+        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        return a.shape == b.shape and np.allclose(a, b, rtol=1e-6, atol=1e-6, equal_nan=True)
+
+    branches = set()
+    for it, ref in enumerate(golden):
+        ctl.update(R.BackwardValidPointHookInput(**hook_fields(it, mask)))
+        info = ctl.densify_point_info
+        if ref["found"] is None:
+            assert info is None, it
+        else:
+            assert info is not None, it
+            for key in ("floater_point_id", "transparent_point_id", "densify_point_id"):
+                assert getattr(info, key).tolist() == ref["found"][key], (it, key)
+                if ref["found"][key]:
+                    branches.add(key)
+            assert close(info.densify_size_reduction_factor.flatten().tolist(), ref["found"]["densify_size_reduction_factor"])
+            assert close(info.densify_point_grad_position.tolist(), ref["found"]["densify_point_grad_position"])
+            factors = set(np.round(ref["found"]["densify_size_reduction_factor"], 4))
+            branches |= {"clone" if f == 0 else "split" for f in factors}
+        ctl.refinement()
+        assert mask.tolist() == ref["mask"], it
+        assert obj.tolist() == ref["obj"], it
+        assert close(xyz.tolist(), ref["xyz"]), it
+        assert close(feat[:, 4:8].tolist(), ref["scale_alpha"]), it
+        assert abs(float(torch.nan_to_num(feat).double().sum()) - ref["feat_checksum"]) <= 1e-4, it
+        assert ctl.accumulated_num_pixels.tolist() == ref["acc_pixels"], it
+        assert ctl.accumulated_num_in_camera.tolist() == ref["acc_in_camera"], it
+        assert close(ctl.accumulated_view_space_position_gradients.tolist(), ref["acc_view"]), it
+        assert close(ctl.accumulated_view_space_position_gradients_avg.tolist(), ref["acc_view_avg"]), it
+        assert close(ctl.accumulated_position_gradients.tolist(), ref["acc_pos"]), it
+        assert close(ctl.accumulated_position_gradients_norm.tolist(), ref["acc_pos_norm"]), it
+    assert branches == {"floater_point_id", "transparent_point_id", "densify_point_id", "clone", "split"}
