@@ -165,3 +165,32 @@ def test_controller_trajectory_matches_the_reference_class():
         assert close(ctl.accumulated_position_gradients.tolist(), ref["acc_pos"]), it
         assert close(ctl.accumulated_position_gradients_norm.tolist(), ref["acc_pos_norm"]), it
     assert branches == {"floater_point_id", "transparent_point_id", "densify_point_id", "clone", "split"}
+
+
+def test_downsample_and_psnr_match_the_reference_helpers():
+    """tests/golden/make_trainer_golden.py executed the REFERENCE's ``_downsample_image_and_camera_info``
+    (GaussianPointTrainer.py:97-116) and the PSNR of ``_compute_pnsr_and_ssim`` (:278-285) on generated frames."""
+    import json
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    from make_trainer_golden import fixture_image
+    from taichi_3d_gaussian_splatting_b200 import CameraInfo
+    from taichi_3d_gaussian_splatting_b200.trainer import psnr
+    with open(os.path.join(here, "trainer_vectors.json")) as f:
+        golden = json.load(f)
+    for k, ref in enumerate(golden["downsample"]):
+        h, w, factor = ref["h"], ref["w"], ref["factor"]
+        info = CameraInfo(camera_intrinsics=torch.tensor([[0.9 * w, 0.0, w / 2 + 3.0], [0.0, 0.8 * h, h / 2 - 1.0], [0.0, 0.0, 1.0]]),
+                          camera_height=h, camera_width=w, camera_id=k)
+        small, small_info = downsample_image_and_camera_info(fixture_image(h, w, k), info, factor)
+        assert list(small.shape) == ref["shape"] and small.is_contiguous()
+        assert (small_info.camera_height, small_info.camera_width, small_info.camera_id) == \
+            (ref["camera_height"], ref["camera_width"], ref["camera_id"])
+        assert np.allclose(small_info.camera_intrinsics.numpy(), np.array(ref["K"]), rtol=1e-6, atol=1e-5)
+        assert abs(float(small.double().mean()) - ref["mean"]) <= 1e-5  # antialiased bilinear resize
+        for y, x, r, g, b in ref["probes"]:
+            assert np.allclose(small[:, y, x].numpy(), [r, g, b], atol=1e-4)
+    for k, ref in enumerate(golden["psnr"]):
+        assert abs(psnr(fixture_image(48, 64, 10 + k), fixture_image(48, 64, 20 + k)) - ref) <= 1e-4
