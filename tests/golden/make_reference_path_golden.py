@@ -1,0 +1,73 @@
+"""Golden vectors for the WHOLE hot path, produced by the reference's own kernels.
+
+The reference's rasteriser (GaussianPointCloudRasterisation.py:31-1204 with GaussianPoint3D.py, SphericalHarmonics.py and
+the ``ti.func`` helpers of utils.py) is imported from /root/reference and executed, unmodified, under ``taichi_shim``
+(a minimal Taichi stand-in, see its docstring: float32 numpy arithmetic, by-value ``ti.func`` arguments, lock-step SIMT
+emulation of the two shared-memory kernels).  For every scene of ``reference_path_scenes.py`` it runs
+forward + backward through the reference's ``torch.autograd.Function`` on CPU tensors and stores: image, depth, valid
+point count, the in-place-normalised feature tensor, both gradients and every tensor handed to the backward hook.
+
+One deviation from a literal run: ``Tensor.sort`` is made stable.  The reference calls ``sort()`` on a CUDA tensor, where
+it is CUB's (stable) radix sort; the CPU fallback is not, and tie order is part of the contract.
+
+    python tests/golden/make_reference_path_golden.py     # build container only (~2 min); writes reference_path_vectors.npz
+"""
+import os
+import sys
+import time
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import taichi_shim  # noqa: E402
+from reference_path_scenes import scenes  # noqa: E402
+
+
+def main():
+    taichi_shim.install()
+    sys.modules.setdefault("dataclass_wizard", types.SimpleNamespace(YAMLWizard=object))
+    sys.path.insert(0, "/root/reference")
+    plain_sort = torch.Tensor.sort
+    torch.Tensor.sort = lambda self, *a, **k: plain_sort(self, *a, **{"stable": True, **k})
+    from taichi_3d_gaussian_splatting.Camera import CameraInfo
+    from taichi_3d_gaussian_splatting.GaussianPointCloudRasterisation import GaussianPointCloudRasterisation as G
+
+    out = {}
+    for name, sc in scenes().items():
+        t0 = time.time()
+        pc = sc["point_cloud"].clone().requires_grad_(True)
+        feat = sc["point_cloud_features"].clone().requires_grad_(True)
+        hook = {}
+        module = G(config=G.GaussianPointCloudRasterisationConfig(
+            near_plane=sc["near_plane"], far_plane=sc["far_plane"], depth_to_sort_key_scale=sc["depth_to_sort_key_scale"]),
+            backward_valid_point_hook=lambda h: hook.update(h=h))
+        info = CameraInfo(camera_intrinsics=sc["camera_intrinsics"].clone(), camera_height=sc["camera_height"],
+                          camera_width=sc["camera_width"], camera_id=0)
+        image, depth, count = module(G.GaussianPointCloudRasterisationInput(
+            point_cloud=pc, point_cloud_features=feat, point_object_id=sc["point_object_id"],
+            point_invalid_mask=sc["point_invalid_mask"], camera_info=info, q_pointcloud_camera=sc["q_pointcloud_camera"],
+            t_pointcloud_camera=sc["t_pointcloud_camera"], color_max_sh_band=sc["color_max_sh_band"]))
+        grad_image = torch.randn(image.shape, generator=torch.Generator().manual_seed(sc["grad_seed"]))
+        image.backward(grad_image)
+        h = hook["h"]
+        rec = dict(image=image.detach(), depth=depth.detach(), count=count.detach(), features_after_forward=feat.detach(),
+                   grad_pointcloud=pc.grad, grad_pointcloud_features=feat.grad,
+                   hook_point_id_in_camera_list=h.point_id_in_camera_list, hook_grad_point_in_camera=h.grad_point_in_camera,
+                   hook_grad_pointfeatures_in_camera=h.grad_pointfeatures_in_camera, hook_grad_viewspace=h.grad_viewspace,
+                   hook_magnitude_grad_viewspace=h.magnitude_grad_viewspace,
+                   hook_magnitude_grad_viewspace_on_image=h.magnitude_grad_viewspace_on_image,
+                   hook_num_overlap_tiles=h.num_overlap_tiles, hook_num_affected_pixels=h.num_affected_pixels,
+                   hook_point_depth=h.point_depth, hook_point_uv_in_camera=h.point_uv_in_camera)
+        for key, value in rec.items():
+            out[f"{name}/{key}"] = value.detach().cpu().numpy()
+        print(f"{name}: {time.time() - t0:.1f} s, M={h.point_id_in_camera_list.shape[0]}, "
+              f"max blended per pixel={int(count.max())}, image max={float(image.max()):.3f}")
+    np.savez_compressed(os.path.join(HERE, "reference_path_vectors.npz"), **out)
+    print("wrote", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

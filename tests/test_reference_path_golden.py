@@ -1,0 +1,133 @@
+"""The whole hot path against vectors produced by the REFERENCE's own kernels.
+
+``tests/golden/make_reference_path_golden.py`` imports the reference rasteriser from /root/reference and executes its
+unmodified ``@ti.kernel`` / ``@ti.func`` source under ``tests/golden/taichi_shim.py`` (float32 numpy arithmetic, by-value
+``ti.func`` arguments, lock-step SIMT emulation of the two shared-memory kernels), forward + backward through the
+reference's ``torch.autograd.Function``, for the scenes of ``tests/golden/reference_path_scenes.py``; the outputs are
+committed in ``reference_path_vectors.npz``.  This pins, against the reference source itself, what its unit tests do
+not: multi-splat ordering and ties, the alpha cut-off / clamp / saturation rule, depth and count outputs, the
+w-recursion of the backward, SH colour and its gradient with band masking, the in-place quaternion normalisation, the
+off-screen bounding-box quirk, multi-object poses and every tensor handed to the backward hook.
+
+* CPU: the oracle must reproduce the vectors to float32 rounding (it is a strict-IEEE restatement of the same arithmetic).
+* GPU (``-m gpu``): the CUDA operator must reproduce them within the path's tolerances (RGB 1e-4, gradients 1e-3).
+"""
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from reference_path_scenes import scenes  # noqa: E402
+
+from helpers import grad_close, oracle_backward, oracle_forward  # noqa: E402
+from taichi_3d_gaussian_splatting_b200 import CameraInfo  # noqa: E402
+
+SCENES = scenes()
+GOLDEN = np.load(os.path.join(HERE, "golden", "reference_path_vectors.npz"))
+
+
+def _golden(name):
+    prefix = name + "/"
+    return SimpleNamespace(**{k[len(prefix):]: GOLDEN[k] for k in GOLDEN.files if k.startswith(prefix)})
+
+
+def _as_scene(sc, device="cpu"):
+    return SimpleNamespace(
+        point_cloud=sc["point_cloud"].clone().to(device), point_cloud_features=sc["point_cloud_features"].clone().to(device),
+        point_invalid_mask=sc["point_invalid_mask"].to(device), point_object_id=sc["point_object_id"].to(device),
+        camera_info=CameraInfo(camera_intrinsics=sc["camera_intrinsics"].clone().to(device), camera_height=sc["camera_height"],
+                               camera_width=sc["camera_width"], camera_id=0),
+        q_pointcloud_camera=sc["q_pointcloud_camera"].to(device), t_pointcloud_camera=sc["t_pointcloud_camera"].to(device))
+
+
+def _grad_image(sc):
+    shape = (sc["camera_height"], sc["camera_width"], 3)
+    return torch.randn(shape, generator=torch.Generator().manual_seed(sc["grad_seed"]))
+
+
+def _close(a, b, rtol, floor):
+    ok, worst, nviol = grad_close(a, b, rtol=rtol, floor_frac=floor)
+    return ok, (worst, nviol)
+
+
+def test_scenes_exercise_what_they_claim():
+    b = _golden("B_dense_saturating")
+    sc = SCENES["B_dense_saturating"]
+    _, fwd, _ = oracle_forward(_as_scene(sc), near_plane=sc["near_plane"], far_plane=sc["far_plane"],
+                               depth_to_sort_key_scale=sc["depth_to_sort_key_scale"])
+    lengths = fwd.tile_points_end - fwd.tile_points_start
+    assert lengths.min() > 256                                     # more than one shared-memory group per tile
+    assert (fwd.pixel_offset_of_last_effective_point < fwd.tile_points_end[0]).any()  # early termination happens
+    assert b.count.max() >= 50 and float(fwd.pixel_accumulated_alpha.max()) > 0.999
+    d = _golden("D_borders_band0")
+    assert d.hook_point_id_in_camera_list.shape[0] < 80             # frustum rejections
+    assert (d.hook_num_overlap_tiles == 0).any()                    # right / bottom off-screen: no tile
+    c = _golden("C_two_objects_band1_ties")
+    assert float(np.abs(c.grad_pointcloud_features[:, 12:24]).max()) == 0.0  # band 1: coefficients 4..15 masked
+    assert float(np.abs(c.grad_pointcloud_features[:, 9:12]).max()) > 0.0
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+def test_oracle_reproduces_the_reference_kernels(name):
+    sc, ref = SCENES[name], _golden(name)
+    scene = _as_scene(sc)
+    o, fwd, feats = oracle_forward(scene, near_plane=sc["near_plane"], far_plane=sc["far_plane"],
+                                   depth_to_sort_key_scale=sc["depth_to_sort_key_scale"])
+    assert np.array_equal(fwd.point_id_in_camera_list, ref.hook_point_id_in_camera_list)
+    assert np.array_equal(fwd.num_overlap_tiles, ref.hook_num_overlap_tiles)
+    assert np.array_equal(fwd.pixel_valid_point_count, ref.count)
+    assert np.abs(fwd.image - ref.image).max() <= 2e-6
+    assert np.abs(fwd.depth - ref.depth).max() <= 1e-4 * max(1.0, float(np.abs(ref.depth).max()))
+    assert np.abs(feats - ref.features_after_forward).max() <= 1e-6   # q normalised in place, nothing else touched
+    assert np.abs(fwd.point_uv - ref.hook_point_uv_in_camera).max() <= 1e-3  # pixels
+    assert np.allclose(fwd.point_in_camera[:, 2], ref.hook_point_depth, rtol=1e-6, atol=1e-6)
+    bwd = oracle_backward(o, fwd, scene, feats, _grad_image(sc).numpy(), sc["color_max_sh_band"])
+    for got, exp in ((bwd.grad_pointcloud, ref.grad_pointcloud), (bwd.grad_pointcloud_features, ref.grad_pointcloud_features),
+                     (bwd.grad_point_in_camera, ref.hook_grad_point_in_camera),
+                     (bwd.grad_pointfeatures_in_camera, ref.hook_grad_pointfeatures_in_camera),
+                     (bwd.grad_viewspace, ref.hook_grad_viewspace), (bwd.magnitude_grad_viewspace, ref.hook_magnitude_grad_viewspace),
+                     (bwd.magnitude_grad_viewspace_on_image, ref.hook_magnitude_grad_viewspace_on_image)):
+        # the reference sums its per-pixel contributions in float32 (thread order under the shim), the oracle in
+        # double: with ~80 blended splats per pixel and ~500 pixels per splat that is worth a few 1e-5 on scene B
+        rtol, floor = (3e-4, 3e-5) if name == "B_dense_saturating" else (2e-5, 2e-6)
+        ok, info = _close(got, exp, rtol=rtol, floor=floor)
+        assert ok, (name, info)
+    assert np.array_equal(bwd.num_affected_pixels, ref.hook_num_affected_pixels)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(SCENES))
+def test_cuda_operator_reproduces_the_reference_kernels(name):
+    from gpu_helpers import make_op, n, run_forward
+    sc, ref = SCENES[name], _golden(name)
+    scene = _as_scene(sc, "cuda")
+    scene.point_cloud.requires_grad_(True)
+    scene.point_cloud_features.requires_grad_(True)
+    hook = {}
+    op = make_op(hook=lambda h: hook.update(h=h), exact_exp=True, near_plane=sc["near_plane"], far_plane=sc["far_plane"],
+                 depth_to_sort_key_scale=sc["depth_to_sort_key_scale"])
+    image, depth, count = run_forward(op, scene, band=sc["color_max_sh_band"])
+    assert np.abs(n(image) - ref.image).max() <= 1e-4
+    assert np.abs(n(depth) - ref.depth).max() <= 1e-3 * max(1.0, float(np.abs(ref.depth).max()))
+    assert (n(count) != ref.count).sum() <= 2  # a (pixel, splat) pair within an ulp of the alpha cut-off may flip
+    assert np.abs(n(scene.point_cloud_features) - ref.features_after_forward).max() <= 1e-6
+    image.backward(_grad_image(sc).cuda())
+    h = hook["h"]
+    assert np.array_equal(n(h.point_id_in_camera_list), ref.hook_point_id_in_camera_list)
+    assert np.array_equal(n(h.num_overlap_tiles), ref.hook_num_overlap_tiles)
+    assert (n(h.num_affected_pixels) != ref.hook_num_affected_pixels).sum() <= 2
+    for got, exp in ((scene.point_cloud.grad, ref.grad_pointcloud), (scene.point_cloud_features.grad, ref.grad_pointcloud_features),
+                     (h.grad_point_in_camera, ref.hook_grad_point_in_camera),
+                     (h.grad_pointfeatures_in_camera, ref.hook_grad_pointfeatures_in_camera),
+                     (h.grad_viewspace, ref.hook_grad_viewspace), (h.magnitude_grad_viewspace, ref.hook_magnitude_grad_viewspace),
+                     (h.magnitude_grad_viewspace_on_image, ref.hook_magnitude_grad_viewspace_on_image)):
+        got = n(got)
+        ok, (worst, nviol) = _close(got, exp, rtol=1e-3, floor=1e-5)
+        # float32 atomics over ~500 pixels x ~80 blended splats (scene B): as in the full-size parity test, a few
+        # entries in a thousand may leave the per-entry tolerance, none by more than 1e-3 of the largest entry
+        assert ok or (nviol <= 2e-3 * exp.size and np.abs(got - exp).max() <= 1e-3 * np.abs(exp).max()), (name, worst, nviol)
