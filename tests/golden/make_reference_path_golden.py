@@ -5,7 +5,9 @@ the ``ti.func`` helpers of utils.py) is imported from /root/reference and execut
 (a minimal Taichi stand-in, see its docstring: float32 numpy arithmetic, by-value ``ti.func`` arguments, lock-step SIMT
 emulation of the two shared-memory kernels).  For every scene of ``reference_path_scenes.py`` it runs
 forward + backward through the reference's ``torch.autograd.Function`` on CPU tensors and stores: image, depth, valid
-point count, the in-place-normalised feature tensor, both gradients and every tensor handed to the backward hook.
+point count, the in-place-normalised feature tensor, both gradients, every tensor handed to the backward hook, and the
+per-stage tensors the kernels write (projected attributes, sorted keys and offsets, tile ranges, accumulated alpha, last
+effective offsets).
 
 One deviation from a literal run: ``Tensor.sort`` is made stable.  The reference calls ``sort()`` on a CUDA tensor, where
 it is CUB's (stable) radix sort; the CPU fallback is not, and tie order is part of the contract.
@@ -33,7 +35,26 @@ def main():
     plain_sort = torch.Tensor.sort
     torch.Tensor.sort = lambda self, *a, **k: plain_sort(self, *a, **{"stable": True, **k})
     from taichi_3d_gaussian_splatting.Camera import CameraInfo
+    import taichi_3d_gaussian_splatting.GaussianPointCloudRasterisation as refmod
     from taichi_3d_gaussian_splatting.GaussianPointCloudRasterisation import GaussianPointCloudRasterisation as G
+
+    # record the tensors the kernels write in place (the orchestration calls them by module-level name)
+    stage = {}
+
+    def recording(kernel_name, keys):
+        kernel = getattr(refmod, kernel_name)
+
+        def wrapped(**kwargs):
+            kernel(**kwargs)
+            for key in keys:
+                stage[key] = kwargs[key].detach().clone()
+        setattr(refmod, kernel_name, wrapped)
+
+    recording("generate_point_attributes_in_camera_plane", ["point_uv", "point_in_camera", "point_uv_conic_and_rescale",
+                                                            "point_alpha_after_activation", "point_color", "point_radii"])
+    recording("find_tile_start_and_end", ["point_in_camera_sort_key", "tile_points_start", "tile_points_end"])
+    recording("gaussian_point_rasterisation", ["point_offset_with_sort_key", "pixel_accumulated_alpha",
+                                               "pixel_offset_of_last_effective_point"])
 
     out = {}
     for name, sc in scenes().items():
@@ -61,6 +82,8 @@ def main():
                    hook_magnitude_grad_viewspace_on_image=h.magnitude_grad_viewspace_on_image,
                    hook_num_overlap_tiles=h.num_overlap_tiles, hook_num_affected_pixels=h.num_affected_pixels,
                    hook_point_depth=h.point_depth, hook_point_uv_in_camera=h.point_uv_in_camera)
+        rec.update({f"stage_{k}": v for k, v in stage.items()})
+        stage.clear()
         for key, value in rec.items():
             out[f"{name}/{key}"] = value.detach().cpu().numpy()
         print(f"{name}: {time.time() - t0:.1f} s, M={h.point_id_in_camera_list.shape[0]}, "

@@ -86,6 +86,19 @@ def test_oracle_reproduces_the_reference_kernels(name):
     assert np.abs(feats - ref.features_after_forward).max() <= 1e-6   # q normalised in place, nothing else touched
     assert np.abs(fwd.point_uv - ref.hook_point_uv_in_camera).max() <= 1e-3  # pixels
     assert np.allclose(fwd.point_in_camera[:, 2], ref.hook_point_depth, rtol=1e-6, atol=1e-6)
+    # per-stage tensors written by the reference kernels: integer stages exactly, per-point floats to float32 rounding
+    assert np.array_equal(fwd.point_in_camera_sort_key, ref.stage_point_in_camera_sort_key)     # sorted 64-bit keys
+    assert np.array_equal(fwd.point_offset_with_sort_key, ref.stage_point_offset_with_sort_key)  # incl. the tie order
+    assert np.array_equal(fwd.tile_points_start, ref.stage_tile_points_start)
+    assert np.array_equal(fwd.tile_points_end, ref.stage_tile_points_end)
+    assert np.array_equal(fwd.pixel_offset_of_last_effective_point, ref.stage_pixel_offset_of_last_effective_point)
+    for got, exp, tol in ((fwd.point_uv, ref.stage_point_uv, 1e-4), (fwd.point_in_camera, ref.stage_point_in_camera, 1e-5),
+                          (fwd.point_alpha_after_activation, ref.stage_point_alpha_after_activation, 1e-6),
+                          (fwd.point_color, ref.stage_point_color, 1e-6),
+                          (fwd.pixel_accumulated_alpha, ref.stage_pixel_accumulated_alpha, 2e-6)):
+        assert np.abs(got - exp).max() <= tol, (name, float(np.abs(got - exp).max()))
+    assert np.allclose(fwd.point_uv_conic_and_rescale, ref.stage_point_uv_conic_and_rescale, rtol=2e-4, atol=1e-7)
+    assert np.allclose(fwd.point_radii, ref.stage_point_radii, rtol=1e-4, atol=1e-4)
     bwd = oracle_backward(o, fwd, scene, feats, _grad_image(sc).numpy(), sc["color_max_sh_band"])
     for got, exp in ((bwd.grad_pointcloud, ref.grad_pointcloud), (bwd.grad_pointcloud_features, ref.grad_pointcloud_features),
                      (bwd.grad_point_in_camera, ref.hook_grad_point_in_camera),
