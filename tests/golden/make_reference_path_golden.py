@@ -28,10 +28,30 @@ import taichi_shim  # noqa: E402
 from reference_path_scenes import scenes  # noqa: E402
 
 
+def validate_shim():
+    """The shim is only trusted as far as the reference's OWN unit tests of the Taichi functions on this path pass
+    under it: Sigma' projection and quaternion -> R (tests/GaussianPoint3D_test.py, whole file) and the 2-D Gaussian
+    density with its mean / covariance gradients (tests/utils_test.py: Test2DGaussianPDF).  They build Taichi fields,
+    define kernels inside the test and compare with numpy / scipy -- run here unmodified."""
+    import contextlib
+    import importlib
+    import io
+    import unittest
+    sys.path.insert(0, "/root/reference/tests")
+    loader, suite = unittest.defaultTestLoader, unittest.TestSuite()
+    suite.addTests(loader.loadTestsFromModule(importlib.import_module("GaussianPoint3D_test")))
+    suite.addTests(loader.loadTestsFromTestCase(importlib.import_module("utils_test").Test2DGaussianPDF))
+    with contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()):
+        result = unittest.TextTestRunner(stream=io.StringIO(), verbosity=0).run(suite)
+    assert result.testsRun == 3 and result.wasSuccessful(), (result.failures, result.errors)
+    print("shim check: the reference's 3 unit tests of the path's Taichi functions pass under the shim")
+
+
 def main():
     taichi_shim.install()
     sys.modules.setdefault("dataclass_wizard", types.SimpleNamespace(YAMLWizard=object))
     sys.path.insert(0, "/root/reference")
+    validate_shim()
     plain_sort = torch.Tensor.sort
     torch.Tensor.sort = lambda self, *a, **k: plain_sort(self, *a, **{"stable": True, **k})
     from taichi_3d_gaussian_splatting.Camera import CameraInfo

@@ -108,6 +108,9 @@ class Tensor(np.ndarray):
     def transpose(self):
         return np.ndarray.transpose(self).copy()
 
+    def to_numpy(self):
+        return np.asarray(self).copy()
+
     def norm(self):
         return np.sqrt(np.float32((np.asarray(self) ** 2).sum(dtype=np.float32)))
 
@@ -177,22 +180,44 @@ def _flatten(args):
     return out
 
 
-def _vector_type(n):
-    def make(*args):
-        flat = _flatten(args)
-        if len(flat) == 1:
-            flat = flat * n
-        assert len(flat) == n, (n, flat)
-        return Tensor(flat)
-    make.n = n
-    return make
+class _Field:
+    """A 0-d Taichi field of vectors / matrices, as the reference's unit tests use it: from_numpy, f[None], to_numpy."""
+
+    def __init__(self, tensor_type, shape=()):
+        assert shape == () or shape == (), "only 0-d fields are modelled"
+        self.value = tensor_type(0.0)
+
+    def from_numpy(self, arr):
+        self.value = Tensor(np.asarray(arr, dtype=np.float32).reshape(self.value.shape))
+
+    def to_numpy(self):
+        return np.asarray(self.value).copy()
+
+    def __getitem__(self, index):
+        return self.value
+
+    def __setitem__(self, index, v):
+        self.value = Tensor(np.asarray(v, dtype=np.float32).reshape(self.value.shape))
 
 
-def _matrix_type(n, m):
-    def make(*args):
-        if len(args) == 1 and isinstance(args[0], (list, tuple, np.ndarray)):
-            arr = np.asarray([[np.float32(v) for v in _flatten([row])] for row in args[0]], dtype=np.float32) \
-                if isinstance(args[0][0], (list, tuple, np.ndarray)) else np.asarray(_flatten(args), dtype=np.float32).reshape(n, m)
+class _TensorType:
+    def __init__(self, n, m=None):
+        self.n, self.m = n, m
+
+    def field(self, shape=()):
+        return _Field(self, shape)
+
+    def __call__(self, *args):
+        n, m = self.n, self.m
+        if m is None:
+            flat = _flatten(args)
+            if len(flat) == 1:
+                flat = flat * n
+            assert len(flat) == n, (n, flat)
+            return Tensor(flat)
+        if len(args) == 1 and isinstance(args[0], (list, tuple, np.ndarray)) and len(args[0]) and \
+                isinstance(args[0][0], (list, tuple, np.ndarray)):
+            arr = np.asarray([[np.float32(v) for v in _flatten([row])] for row in args[0]], dtype=np.float32)
         else:
             flat = _flatten(args)
             if len(flat) == 1:
@@ -200,8 +225,14 @@ def _matrix_type(n, m):
             arr = np.asarray(flat, dtype=np.float32).reshape(n, m)
         assert arr.shape == (n, m), (arr.shape, n, m)
         return Tensor(arr)
-    make.n, make.m = n, m
-    return make
+
+
+def _vector_type(n):
+    return _TensorType(n)
+
+
+def _matrix_type(n, m):
+    return _TensorType(n, m)
 
 
 def Vector(values, dt=None):  # noqa: N802
@@ -391,6 +422,9 @@ def _recompile(fn, simt_kernel=False):
     namespace = fn.__globals__
     namespace.setdefault("__ti_run_blocks", _run_blocks)
     namespace.setdefault("__ti_take_block_dim", _take_block_dim)
+    if fn.__closure__:  # a kernel defined inside a test method: give it the enclosing variables it refers to
+        namespace = dict(namespace)
+        namespace.update({name: cell.cell_contents for name, cell in zip(fn.__code__.co_freevars, fn.__closure__)})
     local = {}
     exec(compile(tree, inspect.getsourcefile(fn) or "<taichi_shim>", "exec"), namespace, local)
     new_fn = local[fdef.name]
