@@ -29,10 +29,17 @@ from reference_path_scenes import scenes  # noqa: E402
 
 
 def validate_shim():
-    """The shim is only trusted as far as the reference's OWN unit tests of the Taichi functions on this path pass
-    under it: Sigma' projection and quaternion -> R (tests/GaussianPoint3D_test.py, whole file) and the 2-D Gaussian
-    density with its mean / covariance gradients (tests/utils_test.py: Test2DGaussianPDF).  They build Taichi fields,
-    define kernels inside the test and compare with numpy / scipy -- run here unmodified."""
+    """The shim is only trusted as far as the reference's OWN unit tests of the Taichi code on this path pass under it,
+    run unmodified (they build Taichi fields, define kernels inside the test, compare with numpy / scipy / torch autograd):
+
+    * tests/GaussianPoint3D_test.py (whole file): Sigma' projection, quaternion -> R;
+    * tests/utils_test.py::Test2DGaussianPDF: 2-D Gaussian density and its mean / covariance gradients;
+    * tests/GaussianPointCloudRasterisation_test.py: find_tile_start_and_end, the feature-row loader, the two-point
+      scene rendered through the operator, and test_single_point (operator forward AND backward -- alpha, d/d uv,
+      d/d cov, d/d xyz, d/d q, d/d s, d/d logit -- against torch autograd).  That file asks for cuda:0 tensors; its
+      ``torch.device`` is redirected to the CPU, nothing else is touched.
+    The operator's stress / optimisation tests of that file (1e5 points at 1080p, 1e4 Adam iterations) are too large for
+    an interpreter and are restated in tests/test_reference_behaviour.py instead."""
     import contextlib
     import importlib
     import io
@@ -41,19 +48,28 @@ def validate_shim():
     loader, suite = unittest.defaultTestLoader, unittest.TestSuite()
     suite.addTests(loader.loadTestsFromModule(importlib.import_module("GaussianPoint3D_test")))
     suite.addTests(loader.loadTestsFromTestCase(importlib.import_module("utils_test").Test2DGaussianPDF))
+    rast = importlib.import_module("GaussianPointCloudRasterisation_test")
+    cpu = torch.device("cpu")
+    rast.torch = types.SimpleNamespace(**{k: getattr(torch, k) for k in dir(torch) if not k.startswith("__")})
+    rast.torch.device = lambda *a, **k: cpu
+    wanted = ("test_find_tile_start_and_end", "test_load_point_cloud_row_into_gaussian_point_3d",
+              "test_rasterisation_two_points", "test_single_point")
+    for attr in vars(rast).values():
+        if isinstance(attr, type) and issubclass(attr, unittest.TestCase):
+            suite.addTests(attr(name) for name in wanted if hasattr(attr, name))
     with contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()):
         result = unittest.TextTestRunner(stream=io.StringIO(), verbosity=0).run(suite)
-    assert result.testsRun == 3 and result.wasSuccessful(), (result.failures, result.errors)
-    print("shim check: the reference's 3 unit tests of the path's Taichi functions pass under the shim")
+    assert result.testsRun == 7 and result.wasSuccessful(), (result.testsRun, result.failures, result.errors)
+    print("shim check: 7 of the reference's own unit tests of this path pass with its kernels running under the shim")
 
 
 def main():
     taichi_shim.install()
     sys.modules.setdefault("dataclass_wizard", types.SimpleNamespace(YAMLWizard=object))
     sys.path.insert(0, "/root/reference")
-    validate_shim()
     plain_sort = torch.Tensor.sort
     torch.Tensor.sort = lambda self, *a, **k: plain_sort(self, *a, **{"stable": True, **k})
+    validate_shim()
     from taichi_3d_gaussian_splatting.Camera import CameraInfo
     import taichi_3d_gaussian_splatting.GaussianPointCloudRasterisation as refmod
     from taichi_3d_gaussian_splatting.GaussianPointCloudRasterisation import GaussianPointCloudRasterisation as G
