@@ -60,4 +60,13 @@ def scenes():
     d["point_cloud"][50:55, 2] = 20.0                             # beyond the far plane below
     d.update(color_max_sh_band=0, far_plane=15.0)
     out["D_borders_band0"] = d
+    # E: 3 x 4 tiles, splats from sub-pixel (the +0.3 low-pass / rescale path dominates) to screen-filling, opacities from
+    # nearly 0 (never reaches 1/255) to nearly 1, SH band 2
+    e = _base(150, 48, 64, 0.05, 7, yaw=12.0)
+    e["point_cloud_features"][:30, 4:7] -= 3.0     # tiny: projected sigma well below a pixel
+    e["point_cloud_features"][30:45, 4:7] += 2.5   # huge: cover every tile
+    e["point_cloud_features"][45:60, 7] = -7.0     # almost transparent
+    e["point_cloud_features"][60:75, 7] = 7.0      # almost opaque
+    e.update(color_max_sh_band=2, depth_to_sort_key_scale=10.0)
+    out["E_extreme_scales_band2"] = e
     return out
