@@ -1,6 +1,7 @@
 """CPU tests of the §8(f) rows around the operator: SSIM restatement, densification controller logic, and
 the trainer loop driven by the ORACLE rasteriser (the CUDA operator cannot run here)."""
 import numpy as np
+import pytest
 import torch
 
 from taichi_3d_gaussian_splatting_b200 import GaussianPointAdaptiveController as Controller
@@ -111,11 +112,14 @@ def test_trainer_loop_with_oracle_reduces_loss_and_densifies():
     assert hist[-1]["num_valid_points"] > hist[0]["num_valid_points"]  # densification added points
 
 
-def test_controller_trajectory_matches_the_reference_class():
+@pytest.mark.parametrize("scenario", ["default", "ellipsoid_offset"])
+def test_controller_trajectory_matches_the_reference_class(scenario):
     """tests/golden/make_controller_golden.py ran the REFERENCE's GaussianPointAdaptiveController (imported from
     /root/reference, Taichi / matplotlib stubbed) on the scenario of tests/golden/controller_fixture.py and stored, per
     iteration, the points it decided to remove / densify and every maintained tensor and accumulator.  Ours must follow
-    the same trajectory: identical ids and masks, float tensors to 1e-6."""
+    the same trajectory: identical ids and masks, float tensors to 1e-6.  In the second scenario split points are moved to
+    the foci of their ellipsoid -- the reference does that in a Taichi kernel (compute_ellipsoid_offset), executed under
+    tests/golden/taichi_shim.py when the vectors were made."""
     import json
     import os
     import sys
@@ -126,9 +130,11 @@ def test_controller_trajectory_matches_the_reference_class():
     from taichi_3d_gaussian_splatting_b200 import GaussianPointCloudRasterisation as R
     with open(os.path.join(here, "controller_vectors.json")) as f:
         golden = json.load(f)
+    golden = golden[scenario]
     assert len(golden) == ITERATIONS
     xyz, feat, mask, obj = initial_state()
-    ctl = C(config=C.GaussianPointAdaptiveControllerConfig(**CONFIG),
+    config = dict(CONFIG, enable_ellipsoid_offset=(scenario == "ellipsoid_offset"))
+    ctl = C(config=C.GaussianPointAdaptiveControllerConfig(**config),
             maintained_parameters=C.GaussianPointAdaptiveControllerMaintainedParameters(
                 pointcloud=xyz, pointcloud_features=feat, point_invalid_mask=mask, point_object_id=obj))
 
