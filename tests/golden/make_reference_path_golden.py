@@ -12,7 +12,8 @@ effective offsets).
 One deviation from a literal run: ``Tensor.sort`` is made stable.  The reference calls ``sort()`` on a CUDA tensor, where
 it is CUB's (stable) radix sort; the CPU fallback is not, and tie order is part of the contract.
 
-    python tests/golden/make_reference_path_golden.py     # build container only (~2 min); writes reference_path_vectors.npz
+    python tests/golden/make_reference_path_golden.py [--with-c1]   # build container only; writes reference_path_vectors.npz
+                                                                    # (--with-c1: also BASELINE config 1 -> reference_path_c1.npz)
 """
 import os
 import sys
@@ -25,7 +26,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import taichi_shim  # noqa: E402
-from reference_path_scenes import scenes  # noqa: E402
+from reference_path_scenes import baseline_config_1, scenes  # noqa: E402
 
 
 def validate_shim():
@@ -92,8 +93,12 @@ def main():
     recording("gaussian_point_rasterisation", ["point_offset_with_sort_key", "pixel_accumulated_alpha",
                                                "pixel_offset_of_last_effective_point"])
 
+    with_c1 = "--with-c1" in sys.argv  # BASELINE config 1 takes a few minutes in the interpreter; its file is separate
+    todo = dict(scenes())
+    if with_c1:
+        todo["C1_baseline_config_1"] = baseline_config_1()
     out = {}
-    for name, sc in scenes().items():
+    for name, sc in todo.items():
         t0 = time.time()
         pc = sc["point_cloud"].clone().requires_grad_(True)
         feat = sc["point_cloud_features"].clone().requires_grad_(True)
@@ -124,8 +129,23 @@ def main():
             out[f"{name}/{key}"] = value.detach().cpu().numpy()
         print(f"{name}: {time.time() - t0:.1f} s, M={h.point_id_in_camera_list.shape[0]}, "
               f"max blended per pixel={int(count.max())}, image max={float(image.max()):.3f}")
-    np.savez_compressed(os.path.join(HERE, "reference_path_vectors.npz"), **out)
-    print("wrote", len(out), "arrays")
+    small = {k: v for k, v in out.items() if not k.startswith("C1_")}
+    np.savez_compressed(os.path.join(HERE, "reference_path_vectors.npz"), **small)
+    print("wrote", len(small), "arrays")
+    if with_c1:
+        # keep the file small: the dense gradients are stored for the in-frustum rows only (the hook tensors), the rest is
+        # checked to be zero here
+        c1 = {k: v for k, v in out.items() if k.startswith("C1_")}
+        ids = c1["C1_baseline_config_1/hook_point_id_in_camera_list"].astype(np.int64)
+        for key in ("grad_pointcloud", "grad_pointcloud_features"):
+            dense = c1.pop(f"C1_baseline_config_1/{key}")
+            rest = np.ones(dense.shape[0], dtype=bool)
+            rest[ids] = False
+            assert not dense[rest].any()
+        c1.pop("C1_baseline_config_1/features_after_forward")
+        c1.pop("C1_baseline_config_1/hook_magnitude_grad_viewspace_on_image")
+        np.savez_compressed(os.path.join(HERE, "reference_path_c1.npz"), **c1)
+        print("wrote", len(c1), "arrays for BASELINE config 1")
 
 
 if __name__ == "__main__":

@@ -29,6 +29,14 @@ def _base(num_points, height, width, sigma, seed, sh_degree=3, yaw=0.0):
         color_max_sh_band=3, near_plane=0.8, far_plane=1000.0, depth_to_sort_key_scale=100.0, grad_seed=seed + 1000)
 
 
+def baseline_config_1():
+    """BASELINE config 1 (the correctness gate): 1e4 Gaussians, 256 x 256, sigma_med 0.03, seed 0, SH deg 0.
+    Same generator as taichi_3d_gaussian_splatting_b200.synthetic.make_scene(**CONFIGS["C1"])."""
+    c1 = _base(10_000, 256, 256, 0.03, 0, sh_degree=0)
+    c1.update(color_max_sh_band=0)
+    return c1
+
+
 def scenes():
     out = {}
     # A: rotated camera, un-normalised quaternions (normalised in place by the forward), unused slots, SH deg 3

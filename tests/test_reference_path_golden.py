@@ -144,3 +144,70 @@ def test_cuda_operator_reproduces_the_reference_kernels(name):
         # float32 atomics over ~500 pixels x ~80 blended splats (scene B): as in the full-size parity test, a few
         # entries in a thousand may leave the per-entry tolerance, none by more than 1e-3 of the largest entry
         assert ok or (nviol <= 2e-3 * exp.size and np.abs(got - exp).max() <= 1e-3 * np.abs(exp).max()), (name, worst, nviol)
+
+
+# ---------------------------------------------------------------- BASELINE config 1 through the reference's kernels
+# reference_path_c1.npz: the same generator, run with --with-c1 (5 minutes in the interpreter), on SURVEY 8(d) C1 =
+# BASELINE config 1 (1e4 Gaussians, 256 x 256, SH deg 0).  The dense gradients are stored for the in-frustum rows only
+# (= the hook tensors; the other rows were checked to be zero when the file was made).
+def _c1():
+    from reference_path_scenes import baseline_config_1
+    g = np.load(os.path.join(HERE, "golden", "reference_path_c1.npz"))
+    prefix = "C1_baseline_config_1/"
+    return baseline_config_1(), SimpleNamespace(**{k[len(prefix):]: g[k] for k in g.files})
+
+
+def test_oracle_reproduces_the_reference_kernels_at_baseline_config_1():
+    sc, ref = _c1()
+    scene = _as_scene(sc)
+    o, fwd, feats = oracle_forward(scene)
+    assert np.array_equal(fwd.point_id_in_camera_list, ref.hook_point_id_in_camera_list) and fwd.point_id_in_camera_list.shape[0] == 9566
+    assert np.array_equal(fwd.num_overlap_tiles, ref.hook_num_overlap_tiles)
+    assert np.array_equal(fwd.point_in_camera_sort_key, ref.stage_point_in_camera_sort_key)
+    assert np.array_equal(fwd.point_offset_with_sort_key, ref.stage_point_offset_with_sort_key)
+    assert np.array_equal(fwd.tile_points_start, ref.stage_tile_points_start)
+    assert np.array_equal(fwd.tile_points_end, ref.stage_tile_points_end)
+    assert np.array_equal(fwd.pixel_valid_point_count, ref.count)
+    assert np.array_equal(fwd.pixel_offset_of_last_effective_point, ref.stage_pixel_offset_of_last_effective_point)
+    assert np.abs(fwd.image - ref.image).max() <= 2e-6
+    assert np.abs(fwd.depth - ref.depth).max() <= 1e-4
+    assert np.abs(fwd.pixel_accumulated_alpha - ref.stage_pixel_accumulated_alpha).max() <= 2e-6
+    assert np.abs(fwd.point_color - ref.stage_point_color).max() <= 1e-6
+    bwd = oracle_backward(o, fwd, scene, feats, _grad_image(sc).numpy(), 0)
+    ids = ref.hook_point_id_in_camera_list.astype(np.int64)
+    for got, exp in ((bwd.grad_pointcloud[ids], ref.hook_grad_point_in_camera),
+                     (bwd.grad_pointcloud_features[ids], ref.hook_grad_pointfeatures_in_camera),
+                     (bwd.grad_viewspace, ref.hook_grad_viewspace), (bwd.magnitude_grad_viewspace, ref.hook_magnitude_grad_viewspace)):
+        ok, info = _close(got, exp, rtol=1e-4, floor=1e-5)
+        assert ok, info
+    assert np.array_equal(bwd.num_affected_pixels, ref.hook_num_affected_pixels)
+
+
+@pytest.mark.gpu
+def test_cuda_operator_reproduces_the_reference_kernels_at_baseline_config_1():
+    from gpu_helpers import make_op, n, run_forward
+    sc, ref = _c1()
+    scene = _as_scene(sc, "cuda")
+    scene.point_cloud.requires_grad_(True)
+    scene.point_cloud_features.requires_grad_(True)
+    hook = {}
+    op = make_op(hook=lambda h: hook.update(h=h), exact_exp=True)
+    image, depth, count = run_forward(op, scene, band=0)
+    assert np.abs(n(image) - ref.image).max() <= 1e-4
+    assert np.abs(n(depth) - ref.depth).max() <= 1e-3
+    assert (n(count) != ref.count).sum() <= 3
+    image.backward(_grad_image(sc).cuda())
+    h = hook["h"]
+    assert np.array_equal(n(h.point_id_in_camera_list), ref.hook_point_id_in_camera_list)
+    assert np.array_equal(n(h.num_overlap_tiles), ref.hook_num_overlap_tiles)
+    assert (n(h.num_affected_pixels) != ref.hook_num_affected_pixels).sum() <= 3
+    ids = torch.from_numpy(ref.hook_point_id_in_camera_list.astype(np.int64)).cuda()
+    for got, exp in ((scene.point_cloud.grad[ids], ref.hook_grad_point_in_camera),
+                     (scene.point_cloud_features.grad[ids], ref.hook_grad_pointfeatures_in_camera),
+                     (h.grad_viewspace, ref.hook_grad_viewspace), (h.magnitude_grad_viewspace, ref.hook_magnitude_grad_viewspace)):
+        got = n(got)
+        ok, (worst, nviol) = _close(got, exp, rtol=1e-3, floor=1e-5)
+        assert ok or (nviol <= 2e-3 * exp.size and np.abs(got - exp).max() <= 1e-3 * np.abs(exp).max()), (worst, nviol)
+    rest = torch.ones(scene.point_cloud.shape[0], dtype=torch.bool, device="cuda")
+    rest[ids] = False
+    assert float(scene.point_cloud.grad[rest].abs().max()) == 0.0 and float(scene.point_cloud_features.grad[rest].abs().max()) == 0.0
