@@ -415,6 +415,11 @@ def run_b200(args):
     if args.workload == "C3" and os.path.exists(tpath):  # DRAM bytes per launch from the committed ncu capture
         with open(tpath) as f:
             traffic = json.load(f).get(dominant)
+    ncu_static = None
+    ipath = os.path.join(ROOT, "profiles", "r01_issue.json")
+    if args.workload == "C3" and os.path.exists(ipath):  # issue-slot utilisation etc. of the committed ncu capture (not live)
+        with open(ipath) as f:
+            ncu_static = json.load(f).get(dominant)
     roofline = {
         "kernel": dominant, "bound": "hbm", "achieved": round(dom_gbs, 2), "peak": peak, "unit": "GB/s",
         "frac": round(dom_gbs / peak, 5), "traffic": traffic, "peak_source": peak_src,
@@ -424,6 +429,7 @@ def run_b200(args):
                 "issue (ncu: 83 % of issue slots active, 969 M warp instructions per frame, DRAM throughput 2.1 %), not by HBM; pixel x splat "
                 "evaluations (upper bound 256*K) per second are given beside it. traffic = ncu dram bytes per launch.",
         "pixel_splat_evals_per_s_upper": round(evals / (stage_ms[dominant] * 1e-3), 1),
+        "ncu_committed_capture": ncu_static,
         "per_stage": per_stage,
     }
 
