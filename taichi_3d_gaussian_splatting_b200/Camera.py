@@ -15,7 +15,7 @@ class CameraInfo:
     camera_intrinsics: torch.Tensor  # 3x3 f32 pinhole matrix (device tensor in the reference)
     camera_height: int
     camera_width: int
-    camera_id: int = 0
+    camera_id: int
 
 
 @dataclass

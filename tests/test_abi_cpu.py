@@ -3,6 +3,7 @@ that include/gsb200.h declares, its structs match the ctypes mirrors, the worksp
 is right, and the Python surface keeps the reference's names.  No compute calls."""
 import dataclasses
 import os
+import sys
 import re
 
 import pytest
@@ -111,3 +112,54 @@ def test_fused_l1_has_no_cpu_path_and_reports_its_scratch_size():
     # argument checks of the C entry point happen before any CUDA call
     assert lib.gsb200_l1_loss(None, None, 0, 0, 1.0, None, None, None, 0, None) == -1
     assert b"l1_loss" in lib.gsb200_last_error()
+
+
+def test_python_surface_matches_the_reference_modules():
+    """tests/golden/surface.json was read off the reference's own modules (dataclass fields with defaults, constructor /
+    forward parameters, constants, public methods).  Ours must offer every one of them, with the same defaults; extra
+    keyword-only options of ours are allowed."""
+    import dataclasses
+    import inspect
+    import json
+    import taichi_3d_gaussian_splatting_b200 as pkg
+    mod = sys.modules["taichi_3d_gaussian_splatting_b200.GaussianPointCloudRasterisation"]  # the package re-exports the class under this name
+    with open(os.path.join(ROOT, "tests", "golden", "surface.json")) as f:
+        ref = json.load(f)
+    G, C, S, D = (pkg.GaussianPointCloudRasterisation, pkg.GaussianPointAdaptiveController, pkg.GaussianPointCloudScene,
+                  pkg.ImagePoseDataset)
+
+    def check_fields(cls, expected):
+        ours = {f.name: f for f in dataclasses.fields(cls)}
+        assert [n for n, _, _ in expected] == [n for n in ours if n in {e[0] for e in expected}], cls  # same order
+        for name, default, has_default in expected:
+            assert name in ours, (cls, name)
+            if has_default and not isinstance(default, str):
+                assert ours[name].default == default, (cls, name, ours[name].default, default)
+            elif not has_default:
+                assert ours[name].default is dataclasses.MISSING and ours[name].default_factory is dataclasses.MISSING, (cls, name)
+
+    def check_params(fn, expected):
+        ours = [p for p in inspect.signature(fn).parameters if p != "self"]
+        assert ours[:len(expected)] == expected, (fn, ours, expected)
+
+    for name, value in ref["constants"].items():
+        assert getattr(mod, name) == value
+    r = ref["rasterisation"]
+    check_fields(G.GaussianPointCloudRasterisationConfig, r["config"])
+    check_fields(G.GaussianPointCloudRasterisationInput, r["input"])
+    check_fields(G.BackwardValidPointHookInput, r["hook_input"])
+    check_params(G.__init__, r["init"])
+    check_params(G.forward, r["forward"])
+    check_fields(pkg.CameraInfo, ref["camera_info"])
+    c = ref["controller"]
+    check_fields(C.GaussianPointAdaptiveControllerConfig, c["config"])
+    check_fields(C.GaussianPointAdaptiveControllerMaintainedParameters, c["maintained"])
+    check_fields(C.GaussianPointAdaptiveControllerDensifyPointInfo, c["densify_info"])
+    check_params(C.__init__, c["init"])
+    s = ref["scene"]
+    check_fields(S.PointCloudSceneConfig, s["config"])
+    check_params(S.__init__, s["init"])
+    check_params(D.__init__, ref["dataset"]["init"])
+    for cls, methods in ((C, c["methods"]), (S, s["methods"]), (D, ref["dataset"]["methods"])):
+        for m in methods:
+            assert callable(getattr(cls, m)), (cls, m)
