@@ -97,9 +97,6 @@ class Tensor(np.ndarray):
     def __new__(cls, data):
         return np.asarray(data, dtype=np.float32).view(cls)
 
-    def _get(self, i):
-        return self[i]
-
     x = property(lambda s: s[0], lambda s, v: s.__setitem__(0, v))
     y = property(lambda s: s[1], lambda s, v: s.__setitem__(1, v))
     z = property(lambda s: s[2], lambda s, v: s.__setitem__(2, v))
@@ -184,7 +181,7 @@ class _Field:
     """A 0-d Taichi field of vectors / matrices, as the reference's unit tests use it: from_numpy, f[None], to_numpy."""
 
     def __init__(self, tensor_type, shape=()):
-        assert shape == () or shape == (), "only 0-d fields are modelled"
+        assert tuple(shape) == (), "only 0-d fields are modelled"
         self.value = tensor_type(0.0)
 
     def from_numpy(self, arr):
