@@ -200,3 +200,27 @@ def test_downsample_and_psnr_match_the_reference_helpers():
             assert np.allclose(small[:, y, x].numpy(), [r, g, b], atol=1e-4)
     for k, ref in enumerate(golden["psnr"]):
         assert abs(psnr(fixture_image(48, 64, 10 + k), fixture_image(48, 64, 20 + k)) - ref) <= 1e-4
+
+
+def test_loss_function_matches_the_reference_class(monkeypatch):
+    """tests/golden/make_loss_golden.py evaluated the REFERENCE's LossFunction with its third-party SSIM call replaced by a
+    fixed stand-in; with the same stand-in ours must give the same L, L1 and 1 - SSIM terms (mix, regulariser, weights)."""
+    import json
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    from make_loss_golden import CASES, inputs, placeholder_ssim
+    from taichi_3d_gaussian_splatting_b200 import loss as loss_module
+    monkeypatch.setattr(loss_module, "ssim", placeholder_ssim)
+    with open(os.path.join(here, "loss_vectors.json")) as f:
+        golden = json.load(f)
+    for case, ref in zip(CASES, golden):
+        pred, gt, mask, feats = inputs(case["seed"])
+        if case.get("batched"):
+            pred, gt = pred.unsqueeze(0), gt.unsqueeze(0)
+        fn = LossFunction(LossFunction.LossFunctionConfig(**case["config"]))
+        total, l1, ld = fn(pred, gt, point_invalid_mask=mask, pointcloud_features=feats)
+        bare, _, _ = fn(pred, gt)
+        for got, key in ((total, "loss"), (l1, "l1"), (ld, "ld_ssim"), (bare, "loss_without_features")):
+            assert abs(float(got) - ref[key]) <= 1e-6 * max(1.0, abs(ref[key])), (case, key)
