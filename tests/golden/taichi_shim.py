@@ -108,17 +108,29 @@ class Tensor(np.ndarray):
     def to_numpy(self):
         return np.asarray(self).copy()
 
-    def norm(self):
-        return np.sqrt(np.float32((np.asarray(self) ** 2).sum(dtype=np.float32)))
+    def _seq_sum(self, values):
+        # Taichi unrolls Matrix.sum() as ((e0 + e1) + e2) + ... in float32
+        acc = np.float32(values[0])
+        for v in values[1:]:
+            acc = np.float32(acc + v)
+        return acc
 
     def norm_sqr(self):
-        return np.float32((np.asarray(self) ** 2).sum(dtype=np.float32))
+        flat = np.asarray(self, dtype=np.float32).reshape(-1)
+        return self._seq_sum(flat * flat)
+
+    def norm(self):
+        return np.sqrt(self.norm_sqr())
 
     def normalized(self):
-        return self / self.norm()
+        # taichi/lang/matrix.py: invlen = 1 / (self.norm() + eps); return invlen * self
+        invlen = np.float32(1.0) / self.norm()
+        return invlen * self
 
     def dot(self, other):
-        return np.float32((np.asarray(self) * np.asarray(other)).sum(dtype=np.float32))
+        a = np.asarray(self, dtype=np.float32).reshape(-1)
+        b = np.asarray(other, dtype=np.float32).reshape(-1)
+        return self._seq_sum(a * b)
 
     def determinant(self):
         a = np.asarray(self)
@@ -139,8 +151,8 @@ class Tensor(np.ndarray):
     def outer_product(self, other):
         return Tensor(np.outer(np.asarray(self), np.asarray(other)))
 
-    def sum(self, *args, **kwargs):  # a Taichi vector sum is a scalar
-        return np.float32(np.asarray(self).sum(dtype=np.float32))
+    def sum(self, *args, **kwargs):  # a Taichi vector sum is a scalar, accumulated in element order
+        return self._seq_sum(np.asarray(self, dtype=np.float32).reshape(-1))
 
     def __matmul__(self, other):
         # explicit float32 accumulation in index order (no BLAS), like the unrolled Taichi code
@@ -248,10 +260,13 @@ Vector.zero = lambda dt, n: Tensor(np.zeros(n, dtype=np.float32))
 
 
 def _unary(np_fn):
+    """float32 -> float32 elementary function, evaluated in double and rounded once: the correctly rounded float32
+    result, independent of the libm / SIMD routine numpy happens to use (the oracle makes the same choice)."""
     def fn(x):
         if isinstance(x, np.ndarray):
-            return np_fn(x.astype(np.float32)).view(type(x)) if isinstance(x, Tensor) else np_fn(x)
-        return np_fn(np.float32(x))
+            out = np_fn(x.astype(np.float64)).astype(np.float32)
+            return out.view(type(x)) if isinstance(x, Tensor) else out
+        return np.float32(np_fn(np.float64(np.float32(x))))
     return fn
 
 
@@ -293,7 +308,7 @@ for _n in (2, 3, 4):
 math_ns.exp, math_ns.sqrt, math_ns.log, math_ns.sin, math_ns.cos = exp, sqrt, log, sin, cos
 math_ns.pi = math.pi
 math_ns.dot = lambda a, b: Tensor(a).dot(b)
-math_ns.normalize = lambda v: v / Tensor(v).norm()
+math_ns.normalize = lambda v: Tensor(v).normalized()
 math_ns.length = lambda v: Tensor(v).norm()
 math_ns.cross = lambda a, b: Tensor(np.cross(np.asarray(a), np.asarray(b)))
 math_ns.clamp = lambda x, lo, hi: min(max(x, lo), hi)

@@ -81,24 +81,28 @@ def test_oracle_reproduces_the_reference_kernels(name):
     assert np.array_equal(fwd.point_id_in_camera_list, ref.hook_point_id_in_camera_list)
     assert np.array_equal(fwd.num_overlap_tiles, ref.hook_num_overlap_tiles)
     assert np.array_equal(fwd.pixel_valid_point_count, ref.count)
-    assert np.abs(fwd.image - ref.image).max() <= 2e-6
-    assert np.abs(fwd.depth - ref.depth).max() <= 1e-4 * max(1.0, float(np.abs(ref.depth).max()))
-    assert np.abs(feats - ref.features_after_forward).max() <= 1e-6   # q normalised in place, nothing else touched
-    assert np.abs(fwd.point_uv - ref.hook_point_uv_in_camera).max() <= 1e-3  # pixels
-    assert np.allclose(fwd.point_in_camera[:, 2], ref.hook_point_depth, rtol=1e-6, atol=1e-6)
+    assert np.abs(fwd.image - ref.image).max() <= 5e-7
+    assert np.abs(fwd.depth - ref.depth).max() <= 1e-5 * max(1.0, float(np.abs(ref.depth).max()))
+    assert np.array_equal(fwd.point_uv, ref.hook_point_uv_in_camera) and np.array_equal(fwd.point_in_camera[:, 2], ref.hook_point_depth)
     # per-stage tensors written by the reference kernels: integer stages exactly, per-point floats to float32 rounding
     assert np.array_equal(fwd.point_in_camera_sort_key, ref.stage_point_in_camera_sort_key)     # sorted 64-bit keys
     assert np.array_equal(fwd.point_offset_with_sort_key, ref.stage_point_offset_with_sort_key)  # incl. the tie order
     assert np.array_equal(fwd.tile_points_start, ref.stage_tile_points_start)
     assert np.array_equal(fwd.tile_points_end, ref.stage_tile_points_end)
     assert np.array_equal(fwd.pixel_offset_of_last_effective_point, ref.stage_pixel_offset_of_last_effective_point)
-    for got, exp, tol in ((fwd.point_uv, ref.stage_point_uv, 1e-4), (fwd.point_in_camera, ref.stage_point_in_camera, 1e-5),
-                          (fwd.point_alpha_after_activation, ref.stage_point_alpha_after_activation, 1e-6),
-                          (fwd.point_color, ref.stage_point_color, 1e-6),
-                          (fwd.pixel_accumulated_alpha, ref.stage_pixel_accumulated_alpha, 2e-6)):
-        assert np.abs(got - exp).max() <= tol, (name, float(np.abs(got - exp).max()))
-    assert np.allclose(fwd.point_uv_conic_and_rescale, ref.stage_point_uv_conic_and_rescale, rtol=2e-4, atol=1e-7)
-    assert np.allclose(fwd.point_radii, ref.stage_point_radii, rtol=1e-4, atol=1e-4)
+    # The per-point stage is BIT-IDENTICAL: the shim follows Taichi's own definitions (Matrix.sum in element order,
+    # normalized() = (1 / norm) * v, elementary functions correctly rounded) and the oracle restates the same operation
+    # order, so projection, covariance, conic, rescale, opacity, SH colour, radius and the in-place normalised quaternion
+    # agree to the last bit.
+    for got, exp in ((fwd.point_uv, ref.stage_point_uv), (fwd.point_in_camera, ref.stage_point_in_camera),
+                     (fwd.point_uv_conic_and_rescale, ref.stage_point_uv_conic_and_rescale),
+                     (fwd.point_alpha_after_activation, ref.stage_point_alpha_after_activation),
+                     (fwd.point_color, ref.stage_point_color), (fwd.point_radii, ref.stage_point_radii),
+                     (feats, ref.features_after_forward)):
+        assert np.array_equal(got, exp), (name, float(np.abs(got - exp).max()))
+    # the blend evaluates exp() per (pixel, splat): libm expf here, correctly rounded in the shim -- last-bit differences
+    assert np.abs(fwd.pixel_accumulated_alpha - ref.stage_pixel_accumulated_alpha).max() <= 2e-6
+    assert (fwd.image == ref.image).mean() >= 0.99
     bwd = oracle_backward(o, fwd, scene, feats, _grad_image(sc).numpy(), sc["color_max_sh_band"])
     for got, exp in ((bwd.grad_pointcloud, ref.grad_pointcloud), (bwd.grad_pointcloud_features, ref.grad_pointcloud_features),
                      (bwd.grad_point_in_camera, ref.hook_grad_point_in_camera),
@@ -169,10 +173,13 @@ def test_oracle_reproduces_the_reference_kernels_at_baseline_config_1():
     assert np.array_equal(fwd.tile_points_end, ref.stage_tile_points_end)
     assert np.array_equal(fwd.pixel_valid_point_count, ref.count)
     assert np.array_equal(fwd.pixel_offset_of_last_effective_point, ref.stage_pixel_offset_of_last_effective_point)
-    assert np.abs(fwd.image - ref.image).max() <= 2e-6
+    assert np.abs(fwd.image - ref.image).max() <= 5e-7 and (fwd.image == ref.image).mean() >= 0.99
     assert np.abs(fwd.depth - ref.depth).max() <= 1e-4
     assert np.abs(fwd.pixel_accumulated_alpha - ref.stage_pixel_accumulated_alpha).max() <= 2e-6
-    assert np.abs(fwd.point_color - ref.stage_point_color).max() <= 1e-6
+    for got, exp in ((fwd.point_uv, ref.stage_point_uv), (fwd.point_uv_conic_and_rescale, ref.stage_point_uv_conic_and_rescale),
+                     (fwd.point_alpha_after_activation, ref.stage_point_alpha_after_activation),
+                     (fwd.point_color, ref.stage_point_color), (fwd.point_radii, ref.stage_point_radii)):
+        assert np.array_equal(got, exp)  # the per-point stage is bit-identical (see above)
     bwd = oracle_backward(o, fwd, scene, feats, _grad_image(sc).numpy(), 0)
     ids = ref.hook_point_id_in_camera_list.astype(np.int64)
     for got, exp in ((bwd.grad_pointcloud[ids], ref.hook_grad_point_in_camera),
