@@ -26,7 +26,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import taichi_shim  # noqa: E402
-from reference_path_scenes import baseline_config_1, scenes  # noqa: E402
+from reference_path_scenes import baseline_config_1, reduced_config_2, scenes  # noqa: E402
 
 
 def validate_shim():
@@ -97,6 +97,9 @@ def main():
     todo = dict(scenes())
     if with_c1:
         todo["C1_baseline_config_1"] = baseline_config_1()
+    with_c2r = "--with-c2r" in sys.argv  # reduced BASELINE config 2: about an hour in the interpreter, sampled output
+    if with_c2r:
+        todo = {"C2R_reduced_config_2": reduced_config_2()} if "--only-c2r" in sys.argv else {**todo, "C2R_reduced_config_2": reduced_config_2()}
     out = {}
     for name, sc in todo.items():
         t0 = time.time()
@@ -129,9 +132,41 @@ def main():
             out[f"{name}/{key}"] = value.detach().cpu().numpy()
         print(f"{name}: {time.time() - t0:.1f} s, M={h.point_id_in_camera_list.shape[0]}, "
               f"max blended per pixel={int(count.max())}, image max={float(image.max()):.3f}")
-    small = {k: v for k, v in out.items() if not k.startswith("C1_")}
-    np.savez_compressed(os.path.join(HERE, "reference_path_vectors.npz"), **small)
-    print("wrote", len(small), "arrays")
+    small = {k: v for k, v in out.items() if not k.startswith(("C1_", "C2R_"))}
+    if small:
+        np.savez_compressed(os.path.join(HERE, "reference_path_vectors.npz"), **small)
+        print("wrote", len(small), "arrays")
+    if with_c2r:
+        # 976 x 544 pixels, 3.7e4 points, 4.9e5 pairs: keep hashes of everything that must be bit-equal and samples of the rest
+        import hashlib
+        pre = "C2R_reduced_config_2/"
+        full = {k[len(pre):]: v for k, v in out.items() if k.startswith(pre)}
+        digest = lambda a: np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)  # noqa: E731
+        keep = {}
+        for key in ("hook_point_id_in_camera_list", "hook_num_overlap_tiles", "hook_num_affected_pixels", "count",
+                    "stage_point_in_camera_sort_key", "stage_point_offset_with_sort_key", "stage_tile_points_start",
+                    "stage_tile_points_end", "stage_pixel_offset_of_last_effective_point", "stage_point_uv",
+                    "stage_point_in_camera", "stage_point_uv_conic_and_rescale", "stage_point_alpha_after_activation",
+                    "stage_point_color", "stage_point_radii", "features_after_forward"):
+            keep["sha256_" + key] = digest(full[key])
+        rng = np.random.default_rng(0)
+        h, w = full["count"].shape
+        pix = rng.choice(h * w, 6000, replace=False)
+        keep["pixel_index"] = pix
+        for key in ("image", "depth", "count", "stage_pixel_accumulated_alpha"):
+            keep["pixel_" + key] = full[key].reshape(h * w, -1)[pix]
+        tiles = full["image"].reshape(h // 16, 16, w // 16, 16, 3).astype(np.float64).sum(axis=(1, 3))
+        keep["tile_image_sum"] = tiles.astype(np.float32)
+        m = full["hook_point_id_in_camera_list"].shape[0]
+        rows = np.sort(rng.choice(m, 1500, replace=False))
+        keep["point_rows"] = rows
+        for key in ("hook_grad_point_in_camera", "hook_grad_pointfeatures_in_camera", "hook_grad_viewspace",
+                    "hook_magnitude_grad_viewspace"):
+            keep["rows_" + key] = full[key][rows]
+            keep["l1_" + key] = np.array([np.abs(full[key].astype(np.float64)).sum()])
+        keep["sizes"] = np.array([m, full["stage_point_offset_with_sort_key"].shape[0], int(full["count"].max())])
+        np.savez_compressed(os.path.join(HERE, "reference_path_c2_reduced.npz"), **keep)
+        print("wrote", len(keep), "arrays for the reduced BASELINE config 2")
     if with_c1:
         # keep the file small: the dense gradients are stored for the in-frustum rows only (the hook tensors), the rest is
         # checked to be zero here

@@ -37,6 +37,13 @@ def baseline_config_1():
     return c1
 
 
+def reduced_config_2():
+    """BASELINE config 2 at a tenth of its Gaussians (SURVEY 8(d) names "a reduced C2 (N = 4.3e4)" as the CPU-feasible
+    stand-in): 976 x 544 = 61 x 34 tiles, seed 1, SH deg 3; sigma_med 0.02 * 10^(1/3) keeps the number of splats per tile
+    in C2's range (mean ~240, max ~400: several 256-splat groups per tile)."""
+    return _base(43_000, 544, 976, 0.02 * 10 ** (1.0 / 3.0), 1, sh_degree=3)
+
+
 def scenes():
     out = {}
     # A: rotated camera, un-normalised quaternions (normalised in place by the forward), unused slots, SH deg 3

@@ -226,3 +226,101 @@ def test_cuda_operator_reproduces_the_reference_kernels_at_baseline_config_1():
     rest = torch.ones(scene.point_cloud.shape[0], dtype=torch.bool, device="cuda")
     rest[ids] = False
     assert float(scene.point_cloud.grad[rest].abs().max()) == 0.0 and float(scene.point_cloud_features.grad[rest].abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------- reduced BASELINE config 2 through the reference's kernels
+# reference_path_c2_reduced.npz (generator option --with-c2r, about an hour in the interpreter): 4.3e4 Gaussians at
+# 976 x 544 = 2074 tiles with C2's splat density per tile.  Everything that must be bit-equal is stored as a SHA-256,
+# images and gradients as samples (6000 pixels, per-tile sums, 1500 in-frustum rows, global L1 norms).
+def _c2r():
+    import hashlib
+    from reference_path_scenes import reduced_config_2
+    path = os.path.join(HERE, "golden", "reference_path_c2_reduced.npz")
+    if not os.path.exists(path):
+        pytest.skip("reference_path_c2_reduced.npz has not been generated")
+    g = np.load(path)
+    digest = lambda a: np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)  # noqa: E731
+    return reduced_config_2(), SimpleNamespace(**{k: g[k] for k in g.files}), digest
+
+
+def test_oracle_reproduces_the_reference_kernels_at_reduced_config_2():
+    sc, ref, digest = _c2r()
+    scene = _as_scene(sc)
+    o, fwd, feats = oracle_forward(scene)
+    assert (fwd.point_uv.shape[0], fwd.point_offset_with_sort_key.shape[0], int(fwd.pixel_valid_point_count.max())) == tuple(ref.sizes)
+    lengths = fwd.tile_points_end - fwd.tile_points_start
+    assert lengths.shape[0] == 61 * 34 and lengths.max() > 256
+    for key, got in (("hook_point_id_in_camera_list", fwd.point_id_in_camera_list), ("hook_num_overlap_tiles", fwd.num_overlap_tiles),
+                     ("count", fwd.pixel_valid_point_count), ("stage_point_in_camera_sort_key", fwd.point_in_camera_sort_key),
+                     ("stage_point_offset_with_sort_key", fwd.point_offset_with_sort_key),
+                     ("stage_tile_points_start", fwd.tile_points_start), ("stage_tile_points_end", fwd.tile_points_end),
+                     ("stage_pixel_offset_of_last_effective_point", fwd.pixel_offset_of_last_effective_point),
+                     ("stage_point_uv", fwd.point_uv), ("stage_point_in_camera", fwd.point_in_camera),
+                     ("stage_point_uv_conic_and_rescale", fwd.point_uv_conic_and_rescale),
+                     ("stage_point_alpha_after_activation", fwd.point_alpha_after_activation),
+                     ("stage_point_color", fwd.point_color), ("stage_point_radii", fwd.point_radii),
+                     ("features_after_forward", feats)):
+        assert np.array_equal(digest(got), getattr(ref, "sha256_" + key)), key  # bit-identical arrays
+    h, w = fwd.pixel_valid_point_count.shape
+    pix = ref.pixel_index
+    assert np.abs(fwd.image.reshape(h * w, 3)[pix] - ref.pixel_image).max() <= 5e-7
+    assert np.abs(fwd.depth.reshape(h * w, 1)[pix] - ref.pixel_depth).max() <= 1e-4
+    assert np.abs(fwd.pixel_accumulated_alpha.reshape(h * w, 1)[pix] - ref.pixel_stage_pixel_accumulated_alpha).max() <= 2e-6
+    tiles = fwd.image.reshape(h // 16, 16, w // 16, 16, 3).astype(np.float64).sum(axis=(1, 3))
+    assert np.abs(tiles - ref.tile_image_sum).max() <= 1e-4
+    bwd = oracle_backward(o, fwd, scene, feats, _grad_image(sc).numpy(), 3)
+    assert np.array_equal(digest(bwd.num_affected_pixels), ref.sha256_hook_num_affected_pixels)
+    rows = ref.point_rows
+    for got, key in ((bwd.grad_point_in_camera, "hook_grad_point_in_camera"),
+                     (bwd.grad_pointfeatures_in_camera, "hook_grad_pointfeatures_in_camera"),
+                     (bwd.grad_viewspace, "hook_grad_viewspace"), (bwd.magnitude_grad_viewspace, "hook_magnitude_grad_viewspace")):
+        ok, info = _close(got[rows], getattr(ref, "rows_" + key), rtol=3e-4, floor=3e-5)
+        assert ok, (key, info)
+        l1 = float(np.abs(got.astype(np.float64)).sum())
+        assert abs(l1 - float(getattr(ref, "l1_" + key)[0])) <= 1e-4 * l1, key
+
+
+@pytest.mark.gpu
+def test_cuda_operator_reproduces_the_reference_kernels_at_reduced_config_2():
+    from gpu_helpers import make_op, n, run_forward
+    sc, ref, digest = _c2r()
+    scene = _as_scene(sc, "cuda")
+    scene.point_cloud.requires_grad_(True)
+    scene.point_cloud_features.requires_grad_(True)
+    hook = {}
+    op = make_op(hook=lambda h: hook.update(h=h), exact_exp=True, keep_all_tile_pairs=True)
+    image, depth, count = run_forward(op, scene, band=3)
+    frame = op.last_frame
+    assert (frame.num_points_in_camera, frame.num_keys) == tuple(ref.sizes[:2])
+    # integer stages: bit-identical to the reference kernels (SHA-256 of the arrays the reference produced)
+    packed = n(frame.sorted_keys).astype(np.int64)
+    bits = frame.layout.depth_bits
+    keys64 = ((packed >> bits) << 32) | (packed & ((1 << bits) - 1))  # back to the reference's (tile << 32) + depth
+    for key, got in (("hook_point_id_in_camera_list", frame.point_id_in_camera_list), ("hook_num_overlap_tiles", frame.num_overlap_tiles),
+                     ("stage_point_offset_with_sort_key", frame.point_offset_with_sort_key),
+                     ("stage_tile_points_start", frame.tile_points_start), ("stage_tile_points_end", frame.tile_points_end)):
+        assert np.array_equal(digest(np.ascontiguousarray(n(got))), getattr(ref, "sha256_" + key)), key
+    # per-point floats: equal to the oracle's (value equality, so that a signed zero cannot matter), and the oracle's are
+    # equal to the reference kernels' bit for bit (the CPU test above compares their SHA-256)
+    from test_gpu_parity import _check_stages
+    _, fwd, _ = oracle_forward(_as_scene(sc))
+    _check_stages(frame, fwd)
+    assert np.array_equal(digest(keys64), ref.sha256_stage_point_in_camera_sort_key)
+    h, w = count.shape
+    pix = ref.pixel_index
+    assert np.abs(n(image).reshape(h * w, 3)[pix] - ref.pixel_image).max() <= 1e-4
+    assert (n(count).reshape(h * w, 1)[pix] != ref.pixel_count).sum() <= 3
+    tiles = n(image).reshape(h // 16, 16, w // 16, 16, 3).astype(np.float64).sum(axis=(1, 3))
+    assert np.abs(tiles - ref.tile_image_sum).max() <= 2e-3
+    image.backward(_grad_image(sc).cuda())
+    h_in = hook["h"]
+    rows = ref.point_rows
+    for got, key in ((h_in.grad_point_in_camera, "hook_grad_point_in_camera"),
+                     (h_in.grad_pointfeatures_in_camera, "hook_grad_pointfeatures_in_camera"),
+                     (h_in.grad_viewspace, "hook_grad_viewspace"), (h_in.magnitude_grad_viewspace, "hook_magnitude_grad_viewspace")):
+        got = n(got)
+        exp = getattr(ref, "rows_" + key)
+        ok, (worst, nviol) = _close(got[rows], exp, rtol=1e-3, floor=1e-5)
+        assert ok or (nviol <= 2e-3 * exp.size and np.abs(got[rows] - exp).max() <= 1e-3 * np.abs(exp).max()), (key, worst, nviol)
+        l1 = float(np.abs(got.astype(np.float64)).sum())
+        assert abs(l1 - float(getattr(ref, "l1_" + key)[0])) <= 1e-3 * l1, key
