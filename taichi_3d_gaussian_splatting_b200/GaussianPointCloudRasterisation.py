@@ -20,6 +20,7 @@ Defined where the reference leaves memory uninitialised: an empty frame (no spla
 renders zeros, and with ``rgb_only=True`` the auxiliary outputs are zeros.
 """
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Callable, Optional
 
@@ -222,18 +223,27 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
         force_key64: bool = False,
         initial_key_capacity: Optional[int] = None,
         keep_all_tile_pairs: bool = False,
+        backward_impl: Optional[str] = None,
     ):
         """``exact_exp``: blend kernels use ``expf`` instead of ``ex2.approx`` (parity debugging).
         ``force_key64``: sort the reference's 64-bit ``tile << 32 | depth`` keys even when the live
         bits fit 32.  ``initial_key_capacity``: first guess for the number of (tile, splat) pairs;
         the buffers grow automatically when a frame needs more.  ``keep_all_tile_pairs``: emit a sort key for
         every tile of the reference's 3-sigma square instead of only the tiles the splat can actually reach with
-        alpha >= 1/255 (same outputs, ~1.5x more keys; used by tests that compare the sorted list itself)."""
+        alpha >= 1/255 (same outputs, ~1.5x more keys; used by tests that compare the sorted list itself).
+        ``backward_impl``: ``"butterfly"`` (default; ``csrc/blend_bwd.cu``) or ``"transposed"`` -- the EXPERIMENTAL
+        second implementation of the blend backward (``csrc/blend_bwd_transposed.cu``; logic verified on the CPU under
+        ``tests/simt``, not yet timed on a B200), which also skips the hook-only statistics when no hook is installed.
+        ``None`` reads the environment variable ``GSB200_BACKWARD_IMPL``."""
         super().__init__()
         self.config = config
         self.backward_valid_point_hook = backward_valid_point_hook
         self._flags = (_lib.GSB_FLAG_EXACT_EXP if exact_exp else 0) | (_lib.GSB_FLAG_FORCE_KEY64 if force_key64 else 0) | \
             (_lib.GSB_FLAG_KEEP_ALL_TILE_PAIRS if keep_all_tile_pairs else 0)
+        backward_impl = backward_impl or os.environ.get("GSB200_BACKWARD_IMPL", "butterfly")
+        if backward_impl not in ("butterfly", "transposed"):
+            raise ValueError(f"backward_impl must be 'butterfly' or 'transposed', got {backward_impl!r}")
+        self.backward_impl = backward_impl
         self._key_capacity = int(initial_key_capacity) if initial_key_capacity else 0
         self.last_frame: Optional[Frame] = None
         self.last_gradient_buffer: Optional[torch.Tensor] = None  # flat storage behind the latest backward's grads
@@ -396,6 +406,11 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
             accum = torch.empty((max(M, 1), _ACCUM_FLOATS), dtype=torch.float32, device=device)
             magnitude_on_image = torch.empty((H, W, 2), dtype=torch.float32, device=device)
             t_pc = t_pointcloud_camera.contiguous()
+            backward_flags = frame.flags
+            if self.backward_impl == "transposed":
+                backward_flags |= _lib.GSB_FLAG_BACKWARD_TRANSPOSED
+                if self.backward_valid_point_hook is None:  # the reference's need_extra_info = False, GPCR:521
+                    backward_flags |= _lib.GSB_FLAG_NO_HOOK_STATS
             args = _lib.GsbBackwardArgs(
                 num_points=N, pointcloud=_ptr(pointcloud), pointcloud_features=_ptr(pointcloud_features),
                 point_object_id=_ptr(point_object_id), num_objects=ctx.num_objects,
@@ -403,7 +418,7 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
                 far_plane=cfg.far_plane, depth_to_sort_key_scale=cfg.depth_to_sort_key_scale,
                 color_max_sh_band=band_i, grad_q_factor=cfg.grad_q_factor, grad_s_factor=cfg.grad_s_factor,
                 grad_alpha_factor=cfg.grad_alpha_factor, grad_color_factor=cfg.grad_color_factor,
-                grad_high_order_color_factor=cfg.grad_high_order_color_factor, flags=frame.flags,
+                grad_high_order_color_factor=cfg.grad_high_order_color_factor, flags=backward_flags,
                 workspace=_ptr(ws), workspace_bytes=frame.layout.total_bytes, key_capacity=frame.key_capacity,
                 grad_rasterized_image=_ptr(grad_image), pixel_accumulated_alpha=_ptr(acc_alpha),
                 pixel_offset_of_last_effective_point=_ptr(last_effective), accum=_ptr(accum),

@@ -13,6 +13,8 @@ GSB_FLAG_EXACT_EXP = 1
 GSB_FLAG_FORCE_KEY64 = 2
 GSB_FLAG_Q_ALREADY_NORMALISED = 4
 GSB_FLAG_KEEP_ALL_TILE_PAIRS = 8
+GSB_FLAG_BACKWARD_TRANSPOSED = 16  # experimental, csrc/blend_bwd_transposed.cu
+GSB_FLAG_NO_HOOK_STATS = 32
 
 c_i64, c_i32, c_u32, c_f32, c_vp = (ctypes.c_int64, ctypes.c_int32, ctypes.c_uint32, ctypes.c_float,
                                     ctypes.c_void_p)

@@ -27,6 +27,7 @@ SOURCES = {
     "sort.cu": [],
     "blend_fwd.cu": [],
     "blend_bwd.cu": [],
+    "blend_bwd_transposed.cu": [],
     "loss.cu": [],
 }
 

@@ -7,38 +7,9 @@
 // per (warp patch, splat) -- per-warp culling (common.cuh) leaves ~2 of the 8 patches per (tile, splat).
 // Kernel B (loop B, GPCR:708-772 + GPCR:1102-1125, 1167-1182): per in-frustum point chain rule to
 // xyz / q / s / SH with the SH-band masking and the constant gradient factors fused in.
-#include "common.cuh"
+#include "blend_bwd.cuh"
 
 namespace gsb {
-
-struct BlendBwdParams {
-    int H, W, tiles_x;
-    const int *tile_start;
-    const int *tile_end;
-    const int *sorted_vals;
-    const float4 *records;
-    const float *grad_image;
-    const float *acc_alpha;
-    const int *last_effective;
-    float *accum;      // rows of 12 floats
-    float *mag_image;  // (H,W,2)
-};
-
-__device__ __forceinline__ float ex2_approx_b(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, <= 1 ulp
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float sqrt_approx(float x) {  // MUFU.RSQ based, ~1 ulp
-    float y;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 
 // Reduce 11 per-lane values across the warp with 13 shuffles (transposing butterfly: at every stage a lane hands
 // one half of its live values to its partner and keeps the other half, 11 -> 6 -> 3 -> 2 -> 1; the odd value of a
@@ -263,6 +234,7 @@ blend_backward_kernel(const BlendBwdParams p) {
     p.mag_image[2 * pix + 1] = mag1;
 }
 
+#ifndef GSB_HOST_EMU
 int launch_blend_backward(const GsbBackwardArgs &a, const Workspace &ws, cudaStream_t stream) {
     const GsbWorkspaceLayout &L = ws.layout;
     BlendBwdParams p;
@@ -280,6 +252,9 @@ int launch_blend_backward(const GsbBackwardArgs &a, const Workspace &ws, cudaStr
     p.mag_image = a.magnitude_grad_viewspace_on_image;
     const int tiles = p.tiles_x * (a.camera_height / GSB_TILE_HEIGHT);
     if (tiles <= 0) return GSB_OK;
+    if (a.flags & GSB_FLAG_BACKWARD_TRANSPOSED)  // experimental, see blend_bwd_transposed.cu
+        return launch_blend_backward_transposed(p, tiles, (a.flags & GSB_FLAG_EXACT_EXP) != 0,
+                                                (a.flags & GSB_FLAG_NO_HOOK_STATS) == 0, stream);
     if (a.flags & GSB_FLAG_EXACT_EXP)
         blend_backward_kernel<true><<<tiles, GSB_TILE_PIXELS, 0, stream>>>(p);
     else
@@ -287,6 +262,7 @@ int launch_blend_backward(const GsbBackwardArgs &a, const Workspace &ws, cudaStr
     GSB_CUDA_CHECK(cudaGetLastError());
     return GSB_OK;
 }
+#endif  // GSB_HOST_EMU
 
 // ------------------------------------------------------------------ loop B + P4
 struct PointsBwdParams {
@@ -475,6 +451,7 @@ backward_points_kernel(const PointsBwdParams p) {
     }
 }
 
+#ifndef GSB_HOST_EMU
 int launch_backward_points(const GsbBackwardArgs &a, const Workspace &ws, cudaStream_t stream) {
     if (a.num_points <= 0) return GSB_OK;
     PointsBwdParams p;
@@ -506,5 +483,6 @@ int launch_backward_points(const GsbBackwardArgs &a, const Workspace &ws, cudaSt
     GSB_CUDA_CHECK(cudaGetLastError());
     return GSB_OK;
 }
+#endif  // GSB_HOST_EMU
 
 }  // namespace gsb

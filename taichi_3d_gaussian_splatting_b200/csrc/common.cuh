@@ -99,7 +99,19 @@ constexpr int SCAN_BLOCK_THREADS = GSB_SCAN_THREADS;
 // inside; otherwise attained on one of the four edges, a clamped 1-D minimisation each).  The test is
 // conservative (t2 padded by 0.2 % + 1e-3; degenerate or NaN conics keep every patch), so it never
 // changes a result -- it only lets a warp skip splats none of its 32 pixels can see.
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(GSB_HOST_EMU)
+#ifdef GSB_HOST_EMU
+// tests/simt compiles the blend-backward kernels as host C++ under a lock-step SIMT emulator (simt_emu.h): "shared
+// space addresses" are 32-bit offsets from an anchor inside the emulator's image, the approximations are libm calls.
+template <int BYTE_OFFSET>
+inline float4 lds128(unsigned int saddr) {
+    return *reinterpret_cast<const float4 *>(simt_emu::smem_anchor() + (long long)(int)saddr + BYTE_OFFSET);
+}
+inline unsigned int smem_u32(const void *p) {
+    return (unsigned int)(int)(reinterpret_cast<const char *>(p) - simt_emu::smem_anchor());
+}
+inline float rcp_fast(float x) { return 1.0f / x; }
+#else
 // 128-bit shared-memory load from an explicit shared-space address (keeps the address arithmetic of the
 // blend inner loops to one IMAD instead of a generic->shared window computation per access).
 template <int BYTE_OFFSET>
@@ -117,6 +129,7 @@ __device__ __forceinline__ unsigned int smem_u32(const void *p) {
     asm volatile("" : "+r"(a));
     return a;
 }
+#endif
 
 // Reach test of one splat: can alpha = exp(-q/2) * ro reach 1/255 anywhere in a rectangle of pixel centres?
 // q(d) = d^T conic d <= t2 = 2 ln(255 ro) (padded by 0.2 % + 1e-3).  `mode`: 0 = never (ro too small),
@@ -128,11 +141,13 @@ struct SplatReach {
     float t2;
     int mode;
 };
+#ifndef GSB_HOST_EMU
 __device__ __forceinline__ float rcp_fast(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+#endif
 __device__ __forceinline__ float quad_form(const SplatReach &r, float dx, float dy) {
     return fmaf(dx, fmaf(r.b2, dy, r.a * dx), r.c * dy * dy);
 }
