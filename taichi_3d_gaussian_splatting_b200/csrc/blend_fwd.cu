@@ -25,12 +25,16 @@ struct BlendFwdParams {
     int *valid_count;
 };
 
+#ifdef GSB_HOST_EMU  // tests/simt: host build under the SIMT emulator
+__device__ __forceinline__ float ex2_approx(float x) { return exp2f(x); }
+#else
 __device__ __forceinline__ float ex2_approx(float x) {
     // one MUFU.EX2; rel. error ~2^-22
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+#endif
 
 #ifndef GSB_FWD_MIN_BLOCKS
 #define GSB_FWD_MIN_BLOCKS 5
@@ -152,6 +156,7 @@ blend_forward_kernel(const BlendFwdParams p) {
     }
 }
 
+#ifndef GSB_HOST_EMU
 int launch_blend_forward(const GsbForwardArgs &a, const Workspace &ws, cudaStream_t stream) {
     const GsbWorkspaceLayout &L = ws.layout;
     BlendFwdParams p;
@@ -180,5 +185,6 @@ int launch_blend_forward(const GsbForwardArgs &a, const Workspace &ws, cudaStrea
     GSB_CUDA_CHECK(cudaGetLastError());
     return GSB_OK;
 }
+#endif  // GSB_HOST_EMU
 
 }  // namespace gsb

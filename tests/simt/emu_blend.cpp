@@ -1,7 +1,8 @@
-// emu_blend_bwd.cpp -- loop A of the backward (both implementations) compiled as host C++ under simt_emu.h.
-// TEST INFRASTRUCTURE, see simt_emu.h; built by tests/test_simt_blend_backward_cpu.py with g++.
+// emu_blend.cpp -- the forward blend and loop A of the backward (both implementations) compiled as host C++ under simt_emu.h.
+// TEST INFRASTRUCTURE, see simt_emu.h; built by tests/test_simt_blend_cpu.py with g++.
 #include "simt_emu.h"
 // the kernel sources, unmodified (their launchers are compiled out under GSB_HOST_EMU)
+#include "../../taichi_3d_gaussian_splatting_b200/csrc/blend_fwd.cu"
 #include "../../taichi_3d_gaussian_splatting_b200/csrc/blend_bwd.cu"
 #include "../../taichi_3d_gaussian_splatting_b200/csrc/blend_bwd_transposed.cu"
 
@@ -38,6 +39,35 @@ extern "C" long long emu_blend_backward(int transposed, int exact_exp, int stats
     } else {
         if (stats) simt_emu::launch(blend_backward_transposed_kernel<false, true>, tiles, GSB_TILE_PIXELS, p);
         else simt_emu::launch(blend_backward_transposed_kernel<false, false>, tiles, GSB_TILE_PIXELS, p);
+    }
+    return simt_emu::M().switches;
+}
+
+extern "C" long long emu_blend_forward(int rgb_only, int exact_exp, int H, int W, const int *tile_start, const int *tile_end,
+                                       const int *sorted_vals, const float *records, float *image, float *depth,
+                                       float *acc_alpha, int *last_effective, int *valid_count) {
+    using namespace gsb;
+    BlendFwdParams p;
+    p.H = H;
+    p.W = W;
+    p.tiles_x = W / GSB_TILE_WIDTH;
+    p.tile_start = tile_start;
+    p.tile_end = tile_end;
+    p.sorted_vals = sorted_vals;
+    p.records = reinterpret_cast<const float4 *>(records);
+    p.image = image;
+    p.depth = depth;
+    p.acc_alpha = acc_alpha;
+    p.last_effective = last_effective;
+    p.valid_count = valid_count;
+    const int tiles = p.tiles_x * (H / GSB_TILE_HEIGHT);
+    simt_emu::M().switches = 0;
+    if (rgb_only) {
+        if (exact_exp) simt_emu::launch(blend_forward_kernel<true, true>, tiles, GSB_TILE_PIXELS, p);
+        else simt_emu::launch(blend_forward_kernel<true, false>, tiles, GSB_TILE_PIXELS, p);
+    } else {
+        if (exact_exp) simt_emu::launch(blend_forward_kernel<false, true>, tiles, GSB_TILE_PIXELS, p);
+        else simt_emu::launch(blend_forward_kernel<false, false>, tiles, GSB_TILE_PIXELS, p);
     }
     return simt_emu::M().switches;
 }

@@ -1,6 +1,6 @@
 """EXPERIMENTAL blend backward (``backward_impl="transposed"``, csrc/blend_bwd_transposed.cu) on the GPU.
 
-The kernel's logic is verified on the CPU (tests/test_simt_blend_backward_cpu.py: the unmodified kernel source under a
+The kernel's logic is verified on the CPU (tests/test_simt_blend_cpu.py: the unmodified kernel source under a
 lock-step SIMT emulator, against the oracle and against the default kernel).  It was written after this round's GPU
 minutes were spent, it is NOT the default path and no measured number depends on it; these tests are therefore marked
 ``xfail(strict=False)`` until their first B200 run has been seen (they are expected to XPASS), and the module sorts

@@ -1,6 +1,7 @@
-"""Loop A of the backward -- both CUDA implementations -- executed on the CPU under a lock-step SIMT emulator.
+"""The blend kernels -- forward, and both CUDA implementations of loop A of the backward -- executed on the CPU under a
+lock-step SIMT emulator.
 
-``tests/simt/emu_blend_bwd.cpp`` compiles ``csrc/blend_bwd.cu`` (butterfly reduction per (warp, splat): the default,
+``tests/simt/emu_blend.cpp`` compiles ``csrc/blend_bwd.cu`` (butterfly reduction per (warp, splat): the default,
 verified on the GPU) and ``csrc/blend_bwd_transposed.cu`` (experimental: splat-per-lane accumulation after a
 shared-memory transposition, GSB_FLAG_BACKWARD_TRANSPOSED) UNMODIFIED as host C++; ``tests/simt/simt_emu.h`` runs the
 256 threads of a CTA as fibres that meet in the warp / block collectives.  The emulated kernels are fed the oracle's
@@ -27,13 +28,15 @@ CSRC = os.path.join(os.path.dirname(HERE), "taichi_3d_gaussian_splatting_b200", 
 @pytest.fixture(scope="module")
 def emu():
     out = os.path.join(SIMT, "libsimt_emu.so")
-    srcs = [os.path.join(SIMT, "emu_blend_bwd.cpp"), os.path.join(SIMT, "simt_emu.h"),
-            *(os.path.join(CSRC, f) for f in ("blend_bwd.cu", "blend_bwd_transposed.cu", "blend_bwd.cuh", "common.cuh"))]
+    srcs = [os.path.join(SIMT, "emu_blend.cpp"), os.path.join(SIMT, "simt_emu.h"),
+            *(os.path.join(CSRC, f) for f in ("blend_fwd.cu", "blend_bwd.cu", "blend_bwd_transposed.cu", "blend_bwd.cuh",
+                                               "common.cuh"))]
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(s) for s in srcs):
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", cuda_inc, "-o", out, srcs[0]], check=True)
     L = ctypes.CDLL(out)
     L.emu_blend_backward.restype = ctypes.c_longlong
+    L.emu_blend_forward.restype = ctypes.c_longlong
     return L
 
 
@@ -137,3 +140,29 @@ def test_transposed_kernel_matches_the_butterfly_kernel(emu, scene, exact):
     ok, nbad, worst = _close(lean[:, :9], got[:, :9], 1e-6, 1e-7)
     assert ok, (nbad, worst)
     assert (lean[:, 9:] == 0).all() and (lean_img == -1.0).all()
+
+
+@pytest.mark.parametrize("scene", SCENES)
+@pytest.mark.parametrize("exact", [True, False])
+def test_emulated_forward_blend_reproduces_the_oracle(emu, scene, exact):
+    """csrc/blend_fwd.cu (K6, GPCR:318-485) under the emulator: staging, per-patch culling lists, saturation exits."""
+    fwd, rec, g = _state(*scene)
+    H, W = g.shape[:2]
+    image, depth = np.full((H, W, 3), -1.0, np.float32), np.full((H, W), -1.0, np.float32)
+    acc, last, cnt = np.full((H, W), -1.0, np.float32), np.full((H, W), -7, np.int32), np.full((H, W), -7, np.int32)
+    c = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    args = (H, W, c(np.ascontiguousarray(fwd.tile_points_start, dtype=np.int32)),
+            c(np.ascontiguousarray(fwd.tile_points_end, dtype=np.int32)),
+            c(np.ascontiguousarray(fwd.point_offset_with_sort_key, dtype=np.int32)), c(rec))
+    assert emu.emu_blend_forward(0, int(exact), *args, c(image), c(depth), c(acc), c(last), c(cnt)) > 0
+    tol = 2e-6 if exact else 1e-4  # exact: the oracle's operation order with libm expf; fast: exp2 of a folded exponent
+    assert np.abs(image - fwd.image).max() <= tol
+    assert np.abs(acc - fwd.pixel_accumulated_alpha).max() <= tol
+    assert np.abs(depth - fwd.depth).max() <= 1e-3 * max(1.0, float(np.abs(fwd.depth).max()))
+    flips = int((cnt != fwd.pixel_valid_point_count).sum())  # a pair within an ulp of the alpha = 1/255 cut-off may flip
+    assert flips <= (0 if exact else 2)
+    if flips == 0:
+        assert np.array_equal(last, fwd.pixel_offset_of_last_effective_point)
+    rgb = np.full((H, W, 3), -1.0, np.float32)
+    assert emu.emu_blend_forward(1, int(exact), *args, c(rgb), c(depth), c(acc), c(last), c(cnt)) > 0
+    assert np.array_equal(rgb, image)
