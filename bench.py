@@ -453,7 +453,8 @@ def run_b200(args):
                                f"1 view per GPU per step, M={M} in frustum, K={Kk} (tile,splat) pairs sorted and blended "
                                f"(of {K_ref} in the reference's 3-sigma squares; the rest cannot reach alpha>=1/255)",
                    "parallelism": f"view-parallel x{world}" + (" + NCCL all-reduce of dense grads" if world > 1 else ""),
-                   "l2": "inputs larger than L2 (scene 236 MB + 200 MB workspace per frame vs 126 MB L2)"},
+                   "l2": "inputs larger than L2 (scene 236 MB + 200 MB workspace per frame vs 126 MB L2)",
+                   "backward_impl": op.backward_impl},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(e2e_ms, 4),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "what": "per step: pinned host target image + pose + intrinsics -> device (copy stream, one step ahead), forward, fused L1 loss + gradient kernel, backward, loss -> pinned host (read one step later, all inside the timed region)"},

@@ -406,11 +406,7 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
             accum = torch.empty((max(M, 1), _ACCUM_FLOATS), dtype=torch.float32, device=device)
             magnitude_on_image = torch.empty((H, W, 2), dtype=torch.float32, device=device)
             t_pc = t_pointcloud_camera.contiguous()
-            backward_flags = frame.flags
-            if self.backward_impl == "transposed":
-                backward_flags |= _lib.GSB_FLAG_BACKWARD_TRANSPOSED
-                if self.backward_valid_point_hook is None:  # the reference's need_extra_info = False, GPCR:521
-                    backward_flags |= _lib.GSB_FLAG_NO_HOOK_STATS
+            backward_flags = self.backward_flags(frame.flags)
             args = _lib.GsbBackwardArgs(
                 num_points=N, pointcloud=_ptr(pointcloud), pointcloud_features=_ptr(pointcloud_features),
                 point_object_id=_ptr(point_object_id), num_objects=ctx.num_objects,
@@ -445,6 +441,14 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
                     point_depth=frame.point_in_camera[:, 2],
                 ))
         return grad_pointcloud, grad_pointcloud_features
+
+    def backward_flags(self, frame_flags: int) -> int:
+        """Flags of the backward call for a frame rendered with ``frame_flags`` (adds the experimental kernel selection)."""
+        if self.backward_impl == "transposed":
+            frame_flags |= _lib.GSB_FLAG_BACKWARD_TRANSPOSED
+            if self.backward_valid_point_hook is None:  # the reference's need_extra_info = False, GPCR:521
+                frame_flags |= _lib.GSB_FLAG_NO_HOOK_STATS
+        return frame_flags
 
     # ------------------------------------------------------------------ public forward (GPCR:1184-1204)
     def forward(self, input_data: "GaussianPointCloudRasterisation.GaussianPointCloudRasterisationInput"):

@@ -73,7 +73,7 @@ def stage_times(op: GaussianPointCloudRasterisation, input_data, grad_image: tor
             depth_to_sort_key_scale=cfg.depth_to_sort_key_scale, color_max_sh_band=3,
             grad_q_factor=cfg.grad_q_factor, grad_s_factor=cfg.grad_s_factor,
             grad_alpha_factor=cfg.grad_alpha_factor, grad_color_factor=cfg.grad_color_factor,
-            grad_high_order_color_factor=cfg.grad_high_order_color_factor, flags=frame.flags,
+            grad_high_order_color_factor=cfg.grad_high_order_color_factor, flags=op.backward_flags(frame.flags),
             workspace=_ptr(ws), workspace_bytes=layout.total_bytes, key_capacity=frame.key_capacity,
             grad_rasterized_image=_ptr(grad_image.contiguous()), pixel_accumulated_alpha=_ptr(acc),
             pixel_offset_of_last_effective_point=_ptr(last), accum=_ptr(accum), accum_rows=M,
