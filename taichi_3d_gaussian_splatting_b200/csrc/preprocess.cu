@@ -508,6 +508,7 @@ preprocess_kernel(const PreParams p) {
     }
 }
 
+#ifndef GSB_HOST_EMU  // tests/simt compiles the kernels above as host C++ under the SIMT emulator
 int launch_preprocess(const GsbForwardArgs &a, const Workspace &ws, cudaStream_t stream) {
     const GsbWorkspaceLayout &L = ws.layout;
     if (a.num_objects > 0) {
@@ -553,5 +554,6 @@ int launch_preprocess(const GsbForwardArgs &a, const Workspace &ws, cudaStream_t
     GSB_CUDA_CHECK(cudaGetLastError());
     return GSB_OK;
 }
+#endif  // GSB_HOST_EMU
 
 }  // namespace gsb

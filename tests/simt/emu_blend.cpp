@@ -71,3 +71,37 @@ extern "C" long long emu_blend_forward(int rgb_only, int exact_exp, int H, int W
     }
     return simt_emu::M().switches;
 }
+
+// loop B + P4 (per-point chain rule, SH-band masking, gradient factors): backward_points_kernel of blend_bwd.cu
+extern "C" long long emu_backward_points(long long N, const int *point_offset, const float *records,
+                                         const float *point_in_camera, const float *accum, const float *poses,
+                                         const float *xyz, const float *features, const int *obj_id,
+                                         const float *t_pc_cam, const float *K, int color_max_sh_band, float q_f, float s_f,
+                                         float a_f, float c_f, float h_f, float *grad_xyz, float *grad_feat) {
+    using namespace gsb;
+    PointsBwdParams p;
+    p.N = N;
+    p.point_offset = point_offset;
+    p.records = reinterpret_cast<const float4 *>(records);
+    p.point_in_camera = point_in_camera;
+    p.accum = accum;
+    p.poses = reinterpret_cast<const PoseBlock *>(poses);
+    p.xyz = xyz;
+    p.features = features;
+    p.obj_id = obj_id;
+    p.t_pc_cam = t_pc_cam;
+    p.K = K;
+    const int band = color_max_sh_band;
+    p.first_cleared = band <= 0 ? 1 : band == 1 ? 4 : band == 2 ? 9 : 16;  // as launch_backward_points
+    p.q_f = q_f;
+    p.s_f = s_f;
+    p.a_f = a_f;
+    p.c_f = c_f;
+    p.h_f = h_f;
+    p.grad_xyz = grad_xyz;
+    p.grad_feat = grad_feat;
+    simt_emu::M().switches = 0;
+    const int blocks = (int)std::min<long long>((N + GSB_POINTS_THREADS - 1) / GSB_POINTS_THREADS, 16 * 148);
+    if (N > 0) simt_emu::launch(backward_points_kernel, blocks, GSB_POINTS_THREADS, p);
+    return simt_emu::M().switches;
+}

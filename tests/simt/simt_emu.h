@@ -174,29 +174,41 @@ inline void __syncwarp(unsigned int mask = 0xffffffffu) {
     assert(mask == 0xffffffffu);
     simt_emu::warp_exchange(0u);
 }
+namespace simt_emu {
+// value of lane `src(lane)` (the caller's own value when src is out of range), 4- or 8-byte operands
+template <class T, class Src>
+inline T shuffle(unsigned int mask, T v, Src src) {
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "32- and 64-bit shuffles only");
+    assert(mask == 0xffffffffu);
+    (void)mask;
+    unsigned int w[2] = {0u, 0u}, got[2] = {0u, 0u};
+    std::memcpy(w, &v, sizeof(T));
+    const int lane = (int)(threadIdx.x & 31);
+    const int from = src(lane);
+    for (unsigned int k = 0; k < sizeof(T) / 4; ++k) {
+        const unsigned int *r = warp_exchange(w[k]);
+        got[k] = (from >= 0 && from < 32) ? r[from] : w[k];
+    }
+    T out;
+    std::memcpy(&out, got, sizeof(T));
+    return out;
+}
+}  // namespace simt_emu
 template <class T>
 inline T __shfl_xor_sync(unsigned int mask, T v, int lane_mask) {
-    static_assert(sizeof(T) == 4, "32-bit shuffles only");
-    assert(mask == 0xffffffffu);
-    unsigned int u;
-    std::memcpy(&u, &v, 4);
-    const unsigned int *r = simt_emu::warp_exchange(u);
-    const unsigned int got = r[(threadIdx.x & 31) ^ lane_mask];
-    T out;
-    std::memcpy(&out, &got, 4);
-    return out;
+    return simt_emu::shuffle(mask, v, [=](int lane) { return lane ^ lane_mask; });
 }
 template <class T>
 inline T __shfl_sync(unsigned int mask, T v, int src_lane) {
-    static_assert(sizeof(T) == 4, "32-bit shuffles only");
-    assert(mask == 0xffffffffu);
-    unsigned int u;
-    std::memcpy(&u, &v, 4);
-    const unsigned int *r = simt_emu::warp_exchange(u);
-    const unsigned int got = r[src_lane & 31];
-    T out;
-    std::memcpy(&out, &got, 4);
-    return out;
+    return simt_emu::shuffle(mask, v, [=](int) { return src_lane & 31; });
+}
+template <class T>
+inline T __shfl_up_sync(unsigned int mask, T v, unsigned int delta) {
+    return simt_emu::shuffle(mask, v, [=](int lane) { return lane - (int)delta; });
+}
+template <class T>
+inline T __shfl_down_sync(unsigned int mask, T v, unsigned int delta) {
+    return simt_emu::shuffle(mask, v, [=](int lane) { return lane + (int)delta; });
 }
 inline unsigned int __ballot_sync(unsigned int mask, int pred) {
     assert(mask == 0xffffffffu);
@@ -213,6 +225,17 @@ inline float atomicAdd(float *a, float v) {
     *a = old + v;
     return old;
 }
+inline unsigned int atomicAdd(unsigned int *a, unsigned int v) {
+    const unsigned int old = *a;
+    *a = old + v;
+    return old;
+}
+inline unsigned int atomicOr(unsigned int *a, unsigned int v) {
+    const unsigned int old = *a;
+    *a = old | v;
+    return old;
+}
+inline void __threadfence() {}
 inline int atomicMax(int *a, int v) {
     const int old = *a;
     *a = std::max(old, v);

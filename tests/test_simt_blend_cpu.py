@@ -11,7 +11,6 @@ recursions, the 16-splat chunk transposition, reduction slots, row addressing); 
 test infrastructure, not a CPU path of the product."""
 import ctypes
 import os
-import subprocess
 
 import numpy as np
 import pytest
@@ -19,6 +18,7 @@ import pytest
 from helpers import oracle_forward
 from oracle.gs_oracle import lib as oracle_lib, _p
 from taichi_3d_gaussian_splatting_b200.synthetic import make_scene
+from test_simt_preprocess_cpu import build_emulator
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SIMT = os.path.join(HERE, "simt")
@@ -27,17 +27,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "taichi_3d_gaussian_splatting_b200", 
 
 @pytest.fixture(scope="module")
 def emu():
-    out = os.path.join(SIMT, "libsimt_emu.so")
-    srcs = [os.path.join(SIMT, "emu_blend.cpp"), os.path.join(SIMT, "simt_emu.h"),
-            *(os.path.join(CSRC, f) for f in ("blend_fwd.cu", "blend_bwd.cu", "blend_bwd_transposed.cu", "blend_bwd.cuh",
-                                               "common.cuh"))]
-    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(s) for s in srcs):
-        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", cuda_inc, "-o", out, srcs[0]], check=True)
-    L = ctypes.CDLL(out)
-    L.emu_blend_backward.restype = ctypes.c_longlong
-    L.emu_blend_forward.restype = ctypes.c_longlong
-    return L
+    return build_emulator()
 
 
 def _state(num_points, H, W, sigma, seed, **cfg):
