@@ -37,6 +37,15 @@ __device__ __forceinline__ void st_u32_volatile(unsigned int *p, unsigned int v)
     *reinterpret_cast<volatile unsigned int *>(p) = v;
 }
 
+#ifdef GSB_HOST_EMU  // tests/simt: host build under the SIMT emulator -- the bulk copy is a memcpy that has landed at once
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned int) { *bar = 0; }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *, unsigned int) {}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, unsigned int bytes,
+                                              unsigned long long *) {
+    memcpy(dst_smem, src_gmem, bytes);
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *, unsigned int) {}
+#else
 // ---- mbarrier / bulk-copy helpers (TMA 1-D bulk copy, global -> shared)
 __device__ __forceinline__ unsigned int smem_addr(const void *p) {
     return (unsigned int)__cvta_generic_to_shared(p);
@@ -71,6 +80,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int 
         "r"(parity)
         : "memory");
 }
+#endif
 
 // ------------------------------------------------------------------ histograms of all passes
 template <typename KeyT, int RBITS>
@@ -139,7 +149,11 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, const int *__restrict__ v
                      unsigned int *__restrict__ ticket_ctr) {
     constexpr int RADIX = 1 << RBITS;
     constexpr int DPT = RADIX / SORT_BLOCK_THREADS;  // digits owned by a thread: [tid*DPT, tid*DPT+DPT)
+#ifdef GSB_HOST_EMU
+    unsigned char *const smem_raw = simt_emu::dynamic_smem();
+#else
     extern __shared__ unsigned char smem_raw[];
+#endif
     PassSmem<KeyT, RBITS> &s = *reinterpret_cast<PassSmem<KeyT, RBITS> *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -311,6 +325,7 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, const int *__restrict__ v
     }
 }
 
+#ifndef GSB_HOST_EMU
 template <typename KeyT, int RBITS>
 static int sort_pairs_typed(const KeyT *keys_in, const int *vals_in, KeyT *keys_out, int *vals_out,
                             const long long *n_dev, int64_t capacity, int end_bit, unsigned int *hist,
@@ -375,6 +390,8 @@ int sort_pairs_device(const void *keys_in, const int *vals_in, void *keys_out, i
     return GSB_EINVAL;
 }
 
+#endif  // GSB_HOST_EMU
+
 // ------------------------------------------------------------------ tile ranges (GPCR:175-193)
 template <typename KeyT>
 __global__ void __launch_bounds__(256)
@@ -397,6 +414,7 @@ tile_ranges_kernel(const KeyT *__restrict__ keys, const long long *__restrict__ 
     }
 }
 
+#ifndef GSB_HOST_EMU
 int launch_sort(const Workspace &ws, int64_t key_capacity, cudaStream_t stream) {
     const GsbWorkspaceLayout &L = ws.layout;
     // in = keys_a (emitted), out = keys_b, tmp = keys_a: pass p alternates b/a so that the last pass
@@ -448,5 +466,7 @@ int launch_tile_ranges(const Workspace &ws, int64_t key_capacity, int num_tiles,
     GSB_CUDA_CHECK(cudaGetLastError());
     return GSB_OK;
 }
+
+#endif  // GSB_HOST_EMU
 
 }  // namespace gsb

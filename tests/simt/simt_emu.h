@@ -217,6 +217,22 @@ inline unsigned int __ballot_sync(unsigned int mask, int pred) {
     for (int l = 0; l < 32; ++l) bits |= (r[l] & 1u) << l;
     return bits;
 }
+template <class T>
+inline unsigned int __match_any_sync(unsigned int mask, T v) {
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "32- and 64-bit operands only");
+    assert(mask == 0xffffffffu);
+    (void)mask;
+    unsigned int w[2] = {0u, 0u};
+    std::memcpy(w, &v, sizeof(T));
+    unsigned int peers = 0xffffffffu;
+    for (unsigned int k = 0; k < sizeof(T) / 4; ++k) {
+        const unsigned int *r = simt_emu::warp_exchange(w[k]);
+        unsigned int same = 0;
+        for (int l = 0; l < 32; ++l) same |= (r[l] == w[k] ? 1u : 0u) << l;
+        peers &= same;
+    }
+    return peers;
+}
 inline int __any_sync(unsigned int mask, int pred) { return __ballot_sync(mask, pred) != 0u; }
 inline int __all_sync(unsigned int mask, int pred) { return __ballot_sync(mask, pred) == 0xffffffffu; }
 

@@ -2,8 +2,9 @@
 backward (default and experimental kernel) -> per-point chain rule, every kernel the UNMODIFIED CUDA source running under
 the lock-step SIMT emulator of ``tests/simt``, chained through the same buffers the library uses (packed records,
 in-camera offsets, accumulator rows) and compared with the oracle's image and final dense gradients under the path's
-criteria (forward <= 1e-4, gradients 1e-3 relative).  Only the radix sort (TMA bulk copies, ``match.any``) is replaced by
-``numpy.argsort(kind="stable")``; it has its own bit-exact GPU tests.  Test infrastructure, not a product path."""
+criteria (forward <= 1e-4, gradients 1e-3 relative).  No stage is replaced: the one-sweep radix sort and the tile-range
+kernel run from ``csrc/sort.cu`` as well (its TMA bulk copy becomes a memcpy under the emulator) and are also checked
+against ``numpy.argsort(kind="stable")`` on their own.  Test infrastructure, not a product path."""
 import ctypes
 
 import numpy as np
@@ -16,20 +17,54 @@ from test_simt_preprocess_cpu import _large_splats, _run as run_preprocess, buil
 
 @pytest.fixture(scope="module")
 def emu():
-    L = build_emulator()
-    L.emu_backward_points.restype = ctypes.c_longlong
-    return L
+    return build_emulator()
+
+
+def emu_sort(emu, keys, vals, end_bit):
+    keys, vals = np.ascontiguousarray(keys), np.ascontiguousarray(vals, dtype=np.int32)
+    ko, vo = np.empty_like(keys), np.empty_like(vals)
+    c = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    if keys.shape[0]:
+        assert emu.emu_sort_pairs(c(keys), c(vals), c(ko), c(vo), ctypes.c_longlong(keys.shape[0]), keys.dtype.itemsize, end_bit) > 0
+    return ko, vo
+
+
+@pytest.mark.parametrize("dtype,end_bit", [(np.uint32, 30), (np.uint32, 13), (np.uint64, 45), (np.uint64, 64)])
+@pytest.mark.parametrize("n", [1, 37, 3071, 3072, 3073, 10000])
+def test_emulated_radix_sort_is_the_stable_sort(emu, dtype, end_bit, n):
+    """csrc/sort.cu: tiles of 3072 keys (exact multiple, one short, one over), many ties, partial last TMA granule."""
+    rng = np.random.default_rng(n + end_bit)
+    live = min(end_bit, 12 if n > 100 else 3)  # few distinct keys -> long runs of equal keys: stability matters
+    keys = (rng.integers(0, 1 << live, n, dtype=np.uint64) << np.uint64(end_bit - live)).astype(dtype)
+    if end_bit < 8 * keys.dtype.itemsize:  # bits above end_bit are not sorted: leave them zero like the frame keys
+        assert int(keys.max()) < (1 << end_bit)
+    vals = rng.permutation(n).astype(np.int32)
+    ko, vo = emu_sort(emu, keys, vals, end_bit)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(ko, keys[order]) and np.array_equal(vo, vals[order])
+
+
+def test_emulated_tile_ranges_known_answer(emu):
+    """The reference's own known answer (tests/GaussianPointCloudRasterisation_test.py:18-51 shape): keys tile << 32 | depth."""
+    tiles = np.array([0, 0, 0, 2, 2, 5, 5, 5, 5, 7], np.uint64)
+    keys = (tiles << np.uint64(32)) | np.arange(10, dtype=np.uint64)
+    start, end = np.zeros(9, np.int32), np.zeros(9, np.int32)
+    c = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    emu.emu_tile_ranges(c(keys), ctypes.c_longlong(10), 8, 32, 9, c(start), c(end))
+    assert start.tolist() == [0, 0, 3, 0, 0, 5, 0, 9, 0] and end.tolist() == [3, 0, 5, 0, 0, 9, 0, 10, 0]
 
 
 def _pipeline(emu, scene, transposed, exact, band):
     c = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
     pre = run_preprocess(emu, scene, {}, key64=False, filter_tiles=True)
     M, Kk = int(pre.counters[0]), int(pre.counters[1])
+    sk, sv = emu_sort(emu, pre.keys[:Kk], pre.vals[:Kk], pre.tile_bits + pre.depth_bits)
     order = np.argsort(pre.keys[:Kk], kind="stable")
-    sk, sv = pre.keys[:Kk][order].astype(np.int64), np.ascontiguousarray(pre.vals[:Kk][order])
-    tile = sk >> pre.depth_bits
-    start = np.searchsorted(tile, np.arange(pre.T), side="left").astype(np.int32)
-    end = np.searchsorted(tile, np.arange(pre.T), side="right").astype(np.int32)
+    assert np.array_equal(sk, pre.keys[:Kk][order]) and np.array_equal(sv, pre.vals[:Kk][order])
+    start, end = np.zeros(pre.T, np.int32), np.zeros(pre.T, np.int32)
+    emu.emu_tile_ranges(c(sk), ctypes.c_longlong(Kk), sk.dtype.itemsize, pre.depth_bits, pre.T, c(start), c(end))
+    tile = sk.astype(np.int64) >> pre.depth_bits
+    assert np.array_equal(end - start, np.bincount(tile, minlength=pre.T)) and (start[end > start] == np.searchsorted(tile, np.flatnonzero(end > start))).all()
     H, W = pre.H, pre.W
     image, depth, acc = np.zeros((H, W, 3), np.float32), np.zeros((H, W), np.float32), np.zeros((H, W), np.float32)
     last, cnt = np.zeros((H, W), np.int32), np.zeros((H, W), np.int32)

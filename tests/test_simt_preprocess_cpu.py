@@ -27,7 +27,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "taichi_3d_gaussian_splatting_b200", 
 
 def build_emulator():
     out = os.path.join(SIMT, "libsimt_emu.so")
-    tus = [os.path.join(SIMT, f) for f in ("emu_blend.cpp", "emu_preprocess.cpp")]
+    tus = [os.path.join(SIMT, f) for f in ("emu_blend.cpp", "emu_preprocess.cpp", "emu_sort.cpp")]
     deps = tus + [os.path.join(SIMT, "simt_emu.h")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(s) for s in deps):
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
@@ -37,6 +37,8 @@ def build_emulator():
     L.emu_blend_backward.restype = ctypes.c_longlong
     L.emu_blend_forward.restype = ctypes.c_longlong
     L.emu_preprocess.restype = ctypes.c_longlong
+    L.emu_backward_points.restype = ctypes.c_longlong
+    L.emu_sort_pairs.restype = ctypes.c_longlong
     return L
 
 
@@ -82,7 +84,7 @@ def _run(emu, scene, fwd_cfg, key64, filter_tiles):
         c(counters), c(point_id), c(point_offset), c(num_tiles), c(records), c(pic), c(keys), c(vals))
     assert sw > 0
     return SimpleNamespace(feats=feats, counters=counters, point_id=point_id, point_offset=point_offset, num_tiles=num_tiles,
-                           records=records, pic=pic, keys=keys, vals=vals, depth_bits=depth_bits, H=H, W=W, T=T)
+                           records=records, pic=pic, keys=keys, vals=vals, depth_bits=depth_bits, tile_bits=tile_bits, H=H, W=W, T=T)
 
 
 def _check(out, fwd, feats_n, filter_tiles):
