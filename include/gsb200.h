@@ -223,6 +223,21 @@ int gsb200_l1_loss(const float *predicted_image, const float *ground_truth_image
                    int32_t clamp01, float upstream_grad, float *loss_out, float *grad_predicted_out, void *temp,
                    int64_t temp_bytes, void *stream);
 
+/* The trainer's whole image loss and its gradient in two kernels:
+ *   pred = clamp(rasterized_image, 0, 1)                                  GaussianPointTrainer.py:168-170
+ *   L    = (1 - lambda) * mean|pred - gt| + lambda * (1 - SSIM(pred, gt))  LossFunction.py:20-38
+ * SSIM = the published pytorch_msssim algorithm the reference calls (LossFunction.py:4,31): 11-tap Gaussian window,
+ * sigma 1.5, VALID padding, K = (0.01, 0.03), data_range 1, mean over the map.  rasterized_image is (H,W,3) as the
+ * rasteriser returns it, ground_truth_image (3,H,W) as the dataset yields it; H, W > 10.  loss_out3 = {L, L1, 1 - SSIM};
+ * grad_rasterized_image (H,W,3), if not NULL, receives upstream_grad * dL/d rasterized_image (zero where the clamp is
+ * active).  temp holds gsb200_image_loss_temp_bytes(H, W) bytes, 16-byte aligned; its first 16 bytes must be ZERO before
+ * the first use (the call leaves them ready for the next one).  Deterministic (fixed grid, fixed summation order).
+ * Replaces ~60 autograd kernels per step (5 grouped convolutions, their transposes, ~25 elementwise). */
+int64_t gsb200_image_loss_temp_bytes(int32_t camera_height, int32_t camera_width);
+int gsb200_image_loss(const float *rasterized_image, const float *ground_truth_image, int32_t camera_height,
+                      int32_t camera_width, float lambda_value, float upstream_grad, float *loss_out3,
+                      float *grad_rasterized_image, void *temp, int64_t temp_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

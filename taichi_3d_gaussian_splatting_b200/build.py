@@ -29,6 +29,7 @@ SOURCES = {
     "blend_bwd.cu": [],
     "blend_bwd_transposed.cu": [],
     "loss.cu": [],
+    "image_loss.cu": [],
 }
 
 

@@ -98,6 +98,69 @@ def fused_l1_loss(predicted_image: torch.Tensor, ground_truth_image: torch.Tenso
     return _FusedL1.apply(predicted_image, ground_truth_image, clamp01)
 
 
+_image_loss_temp = {}
+
+
+def fused_image_loss_with_grad(rasterized_image: torch.Tensor, ground_truth_image: torch.Tensor, lambda_value: float = 0.2,
+                               weight: float = 1.0, want_grad: bool = True):
+    """The trainer's whole image loss in two CUDA kernels (``gsb200_image_loss``, csrc/image_loss.cu):
+    ``pred = clamp(rasterized_image, 0, 1)`` (GaussianPointTrainer.py:168-170), ``L = (1 - lambda) * L1 + lambda *
+    (1 - SSIM)`` (LossFunction.py:29-33) and ``weight * dL/d rasterized_image``.  ``rasterized_image`` is the (H, W, 3)
+    tensor the rasteriser returns (no permute), ``ground_truth_image`` the (3, H, W) tensor of the dataset.  Returns
+    ``(losses, grad)``: ``losses`` a device tensor ``[L, L1, 1 - SSIM]`` (unweighted), ``grad`` (H, W, 3) or None --
+    feed it to ``rasterized_image.backward(grad)``.  CUDA float32 tensors only: there is no CPU path."""
+    from . import _lib
+    if not (rasterized_image.is_cuda and ground_truth_image.is_cuda):
+        raise RuntimeError("fused_image_loss_with_grad needs CUDA tensors (there is no CPU path)")
+    if rasterized_image.dtype != torch.float32 or ground_truth_image.dtype != torch.float32:
+        raise RuntimeError("fused_image_loss_with_grad needs float32 tensors")
+    if rasterized_image.dim() != 3 or rasterized_image.shape[2] != 3:
+        raise RuntimeError("rasterized_image must be (H, W, 3)")
+    H, W = int(rasterized_image.shape[0]), int(rasterized_image.shape[1])
+    if tuple(ground_truth_image.shape) != (3, H, W):
+        raise RuntimeError(f"ground_truth_image must be (3, {H}, {W}), got {tuple(ground_truth_image.shape)}")
+    if H <= 10 or W <= 10:
+        raise RuntimeError("images must be larger than the 11-tap SSIM window")
+    pred = rasterized_image.detach().contiguous()
+    gt = ground_truth_image.detach().contiguous()
+    lib = _lib.load()
+    stream = torch.cuda.current_stream(pred.device)
+    key = (pred.device.index, stream.cuda_stream, H, W)
+    temp = _image_loss_temp.get(key)
+    if temp is None:
+        temp = torch.zeros(int(lib.gsb200_image_loss_temp_bytes(H, W)), dtype=torch.uint8, device=pred.device)
+        _image_loss_temp[key] = temp
+    losses = torch.empty((3,), dtype=torch.float32, device=pred.device)
+    grad = torch.empty_like(pred) if want_grad else None
+    _lib.check(lib.gsb200_image_loss(pred.data_ptr(), gt.data_ptr(), H, W, float(lambda_value), float(weight),
+                                     losses.data_ptr(), grad.data_ptr() if want_grad else None, temp.data_ptr(),
+                                     temp.numel(), stream.cuda_stream), "gsb200_image_loss")
+    return losses, grad
+
+
+class _FusedImageLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rasterized_image, ground_truth_image, lambda_value):
+        losses, grad = fused_image_loss_with_grad(rasterized_image, ground_truth_image, lambda_value,
+                                                  want_grad=rasterized_image.requires_grad)
+        ctx.grad = grad
+        loss, l1, ld_ssim = losses[0], losses[1], losses[2]
+        ctx.mark_non_differentiable(l1, ld_ssim)
+        return loss, l1, ld_ssim
+
+    @staticmethod
+    def backward(ctx, grad_loss, grad_l1, grad_dssim):
+        grad = ctx.grad
+        ctx.grad = None
+        return (grad * grad_loss if grad is not None else None), None, None
+
+
+def fused_image_loss(rasterized_image: torch.Tensor, ground_truth_image: torch.Tensor, lambda_value: float = 0.2):
+    """Differentiable form of :func:`fused_image_loss_with_grad`: ``(L, L1, 1 - SSIM)`` as 0-dim tensors, ``L`` carrying
+    the gradient to ``rasterized_image`` (one extra scaling kernel in backward)."""
+    return _FusedImageLoss.apply(rasterized_image, ground_truth_image, lambda_value)
+
+
 class LossFunction(nn.Module):
     @dataclass
     class LossFunctionConfig:
@@ -108,6 +171,16 @@ class LossFunction(nn.Module):
     def __init__(self, config: "LossFunction.LossFunctionConfig"):
         super().__init__()
         self.config = config
+
+    def forward_rasterized(self, rasterized_image, ground_truth_image, point_invalid_mask=None, pointcloud_features=None):
+        """The trainer-step form of ``forward`` on the rasteriser's own (H, W, 3) output, UNclamped, against the dataset's
+        (3, H, W) image: clamp (GaussianPointTrainer.py:168-170) + loss in two fused CUDA kernels instead of ~60 autograd
+        kernels.  Same return value as ``forward(clamp(rasterized_image).permute(2, 0, 1), ground_truth_image, ...)``."""
+        loss, l1, ld_ssim = fused_image_loss(rasterized_image, ground_truth_image, self.config.lambda_value)
+        if pointcloud_features is not None and self.config.enable_regularization:
+            s = pointcloud_features[point_invalid_mask == 0, 4:7]
+            loss = loss + self.config.regularization_weight * torch.norm(torch.exp(s), dim=1).mean()
+        return loss, l1, ld_ssim
 
     def forward(self, predicted_image, ground_truth_image, point_invalid_mask=None, pointcloud_features=None):
         """predicted / ground truth: (B, C, H, W) or (C, H, W).  Returns (L, L1, 1 - SSIM)."""

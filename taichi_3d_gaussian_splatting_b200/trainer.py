@@ -75,8 +75,12 @@ class GaussianPointCloudTrainer:
             default_factory=LossFunction.LossFunctionConfig)
 
     def __init__(self, config: "GaussianPointCloudTrainer.TrainConfig", scene: Scene, train_views: List[View],
-                 rasterisation_factory: Optional[Callable] = None, generator: Optional[torch.Generator] = None):
+                 rasterisation_factory: Optional[Callable] = None, generator: Optional[torch.Generator] = None,
+                 fused_image_loss: bool = False):
+        """``fused_image_loss``: clamp + L1 + D-SSIM and their gradient in two CUDA kernels (``gsb200_image_loss``)
+        instead of ~60 autograd kernels per step; same loss values (CUDA only)."""
         self.config = config
+        self.fused_image_loss = fused_image_loss
         self.scene = scene
         self.train_views = train_views
         self.adaptive_controller = GaussianPointAdaptiveController(
@@ -114,10 +118,16 @@ class GaussianPointCloudTrainer:
                 image_gt, camera_info = downsample_image_and_camera_info(image_gt, camera_info, downsample_factor)
             band = iteration // cfg.increase_color_max_sh_band_interval
             image_pred, _, _ = self.rasterisation(self._input(q, t, camera_info, band))
-            image_pred = torch.clamp(image_pred, min=0, max=1).permute(2, 0, 1)
-            loss, l1_loss, ssim_loss = self.loss_function(
-                image_pred, image_gt, point_invalid_mask=self.scene.point_invalid_mask,
-                pointcloud_features=self.scene.point_cloud_features)
+            if self.fused_image_loss:
+                loss, l1_loss, ssim_loss = self.loss_function.forward_rasterized(
+                    image_pred, image_gt, point_invalid_mask=self.scene.point_invalid_mask,
+                    pointcloud_features=self.scene.point_cloud_features)
+                image_pred = image_pred.detach().clamp(0, 1).permute(2, 0, 1) if log_interval else image_pred
+            else:
+                image_pred = torch.clamp(image_pred, min=0, max=1).permute(2, 0, 1)
+                loss, l1_loss, ssim_loss = self.loss_function(
+                    image_pred, image_gt, point_invalid_mask=self.scene.point_invalid_mask,
+                    pointcloud_features=self.scene.point_cloud_features)
             loss.backward()
             optimizer.step()
             position_optimizer.step()

@@ -163,3 +163,21 @@ def test_python_surface_matches_the_reference_modules():
     for cls, methods in ((C, c["methods"]), (S, s["methods"]), (D, ref["dataset"]["methods"])):
         for m in methods:
             assert callable(getattr(cls, m)), (cls, m)
+
+
+def test_fused_image_loss_has_no_cpu_path_and_validates_its_arguments():
+    lib = _lib.load()
+    from taichi_3d_gaussian_splatting_b200 import fused_image_loss, fused_image_loss_with_grad
+    # ticket block, one double per CTA of each kernel (3 channels x 16 x 16 tiles), nine (H-10) x (W-10) derivative planes
+    H, W = 544, 976
+    tiles_m, tiles_i = ((H - 10 + 15) // 16) * ((W - 10 + 15) // 16), ((H + 15) // 16) * ((W + 15) // 16)
+    head = 16 + 8 * 3 * tiles_m + 8 * 3 * tiles_i
+    assert lib.gsb200_image_loss_temp_bytes(H, W) == (head + 255) // 256 * 256 + 4 * 9 * (H - 10) * (W - 10)
+    assert lib.gsb200_image_loss_temp_bytes(10, 64) == 0  # not larger than the 11-tap window
+    a, b = torch.zeros(32, 32, 3), torch.zeros(3, 32, 32)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        fused_image_loss_with_grad(a, b)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        fused_image_loss(a.requires_grad_(True), b)
+    assert lib.gsb200_image_loss(None, None, 32, 32, 0.2, 1.0, None, None, None, 0, None) == -1
+    assert b"image_loss" in lib.gsb200_last_error()

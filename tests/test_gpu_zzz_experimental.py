@@ -1,10 +1,12 @@
-"""EXPERIMENTAL blend backward (``backward_impl="transposed"``, csrc/blend_bwd_transposed.cu) on the GPU.
+"""Opt-in kernels written after this round's GPU minutes were spent, on the GPU: the EXPERIMENTAL blend backward
+(``backward_impl="transposed"``, csrc/blend_bwd_transposed.cu) and the fused image loss (``gsb200_image_loss``,
+csrc/image_loss.cu).
 
-The kernel's logic is verified on the CPU (tests/test_simt_blend_cpu.py: the unmodified kernel source under a
-lock-step SIMT emulator, against the oracle and against the default kernel).  It was written after this round's GPU
-minutes were spent, it is NOT the default path and no measured number depends on it; these tests are therefore marked
-``xfail(strict=False)`` until their first B200 run has been seen (they are expected to XPASS), and the module sorts
-after every other GPU module."""
+Their logic is verified on the CPU (tests/test_simt_blend_cpu.py, tests/test_simt_pipeline_cpu.py,
+tests/test_simt_image_loss_cpu.py: the unmodified kernel sources under a lock-step SIMT emulator, against the oracle /
+the torch loss).  Neither is on the default path and no measured number depends on them; these tests are therefore
+marked ``xfail(strict=False)`` until their first B200 run has been seen (they are expected to XPASS), and the module
+sorts after every other GPU module."""
 import numpy as np
 import pytest
 import torch
@@ -62,3 +64,26 @@ def test_transposed_backward_vs_oracle():
     assert grad_close(gx, bwd.grad_pointcloud)[0], grad_close(gx, bwd.grad_pointcloud)
     for sl in (slice(0, 4), slice(4, 7), slice(7, 8), slice(8, 56)):
         assert grad_close(gf[:, sl], bwd.grad_pointcloud_features[:, sl])[0], sl
+
+
+@pytest.mark.parametrize("H,W,lam", [(64, 96, 0.2), (37, 29, 0.2), (544, 976, 0.2), (32, 32, 1.0)])
+def test_fused_image_loss_matches_the_torch_loss(H, W, lam):
+    """gsb200_image_loss (csrc/image_loss.cu; logic verified on the CPU in tests/test_simt_image_loss_cpu.py) vs the
+    torch restatement of the reference's loss with autograd, on the GPU."""
+    from taichi_3d_gaussian_splatting_b200.loss import LossFunction, fused_image_loss
+    g = torch.Generator().manual_seed(H + W)
+    gt = torch.rand((3, H, W), generator=g).cuda()
+    pred = (gt.permute(1, 2, 0) + 0.3 * torch.randn((H, W, 3), generator=g).cuda()).contiguous()
+    fn = LossFunction(LossFunction.LossFunctionConfig(lambda_value=lam, enable_regularization=False))
+    a = pred.clone().requires_grad_(True)
+    loss_a, l1_a, ds_a = fn(torch.clamp(a, min=0, max=1).permute(2, 0, 1), gt)
+    (3.0 * loss_a).backward()
+    b = pred.clone().requires_grad_(True)
+    loss_b, l1_b, ds_b = fused_image_loss(b, gt, lam)
+    (3.0 * loss_b).backward()
+    assert abs(float(loss_a) - float(loss_b)) <= 2e-6 * max(1.0, abs(float(loss_a)))
+    assert abs(float(l1_a) - float(l1_b)) <= 2e-6 and abs(float(ds_a) - float(ds_b)) <= 1e-5
+    scale = float(a.grad.abs().max())
+    assert float((a.grad - b.grad).abs().max()) <= 5e-5 * scale
+    loss_c, _, _ = fn.forward_rasterized(pred, gt)
+    assert abs(float(loss_c) - float(loss_b)) <= 1e-7

@@ -1,0 +1,51 @@
+"""The fused image loss of the trainer step (``csrc/image_loss.cu``: clamp + L1 + D-SSIM and the gradient w.r.t. the
+rasterised image, two kernels) executed on the CPU under the SIMT emulator -- the unmodified kernel source -- and compared
+with the package's torch restatement of the reference's loss (``loss.py``: GaussianPointTrainer.py:168-175 clamp / permute,
+LossFunction.py:20-38 with the published pytorch_msssim algorithm) and torch autograd.  Test infrastructure."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from taichi_3d_gaussian_splatting_b200.loss import LossFunction
+from test_simt_preprocess_cpu import build_emulator
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return build_emulator()
+
+
+def _torch_reference(pred_hwc, gt_chw, lam, upstream):
+    pred = torch.tensor(pred_hwc, requires_grad=True)
+    loss_fn = LossFunction(LossFunction.LossFunctionConfig(lambda_value=lam, enable_regularization=False))
+    image = torch.clamp(pred, min=0, max=1).permute(2, 0, 1)  # GaussianPointTrainer.py:168-171
+    loss, l1, dssim = loss_fn(image, torch.tensor(gt_chw))
+    (loss * upstream).backward()
+    return float(loss), float(l1), float(dssim), pred.grad.numpy()
+
+
+@pytest.mark.parametrize("H,W,lam,upstream", [(32, 48, 0.2, 1.0), (37, 29, 0.2, 1.0), (16, 16, 1.0, 0.5), (64, 21, 0.0, 2.0)])
+def test_fused_image_loss_source_matches_the_torch_loss(emu, H, W, lam, upstream):
+    rng = np.random.default_rng(H * 100 + W)
+    # smooth-ish images with values outside [0, 1] (the clamp must stop their gradient) and exact ties with the target
+    gt = rng.random((3, H, W)).astype(np.float32)
+    pred = (gt.transpose(1, 2, 0) + 0.3 * rng.standard_normal((H, W, 3))).astype(np.float32)
+    pred[::5, ::3] = gt.transpose(1, 2, 0)[::5, ::3]
+    pred = np.ascontiguousarray(pred)
+    temp = np.zeros(int(emu.emu_image_loss_temp_bytes(H, W)) + 16, np.uint8)
+    out, grad = np.zeros(3, np.float32), np.full((H, W, 3), 9.0, np.float32)
+    c = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    f = ctypes.c_float
+    for _ in range(2):  # second call on the same temp buffer: the ticket must have been re-armed
+        assert emu.emu_image_loss(c(pred), c(gt), H, W, f(lam), f(upstream), c(out), c(grad), c(temp)) > 0
+    loss, l1, dssim, ref_grad = _torch_reference(pred, gt, lam, upstream)
+    assert abs(out[0] - loss) <= 2e-6 * max(1.0, abs(loss)) and abs(out[1] - l1) <= 2e-6 and abs(out[2] - dssim) <= 5e-6
+    scale = np.abs(ref_grad).max()
+    assert np.abs(grad - ref_grad).max() <= 2e-5 * scale
+    assert (grad[(pred < 0) | (pred > 1)] == 0).all()
+    # loss only (validation): no gradient buffer
+    out2 = np.zeros(3, np.float32)
+    assert emu.emu_image_loss(c(pred), c(gt), H, W, f(lam), f(upstream), c(out2), None, c(temp)) > 0
+    assert np.array_equal(out2, out)

@@ -27,7 +27,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "taichi_3d_gaussian_splatting_b200", 
 
 def build_emulator():
     out = os.path.join(SIMT, "libsimt_emu.so")
-    tus = [os.path.join(SIMT, f) for f in ("emu_blend.cpp", "emu_preprocess.cpp", "emu_sort.cpp")]
+    tus = [os.path.join(SIMT, f) for f in ("emu_blend.cpp", "emu_preprocess.cpp", "emu_sort.cpp", "emu_image_loss.cpp")]
     deps = tus + [os.path.join(SIMT, "simt_emu.h")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(s) for s in deps):
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
@@ -39,6 +39,8 @@ def build_emulator():
     L.emu_preprocess.restype = ctypes.c_longlong
     L.emu_backward_points.restype = ctypes.c_longlong
     L.emu_sort_pairs.restype = ctypes.c_longlong
+    L.emu_image_loss.restype = ctypes.c_longlong
+    L.emu_image_loss_temp_bytes.restype = ctypes.c_longlong
     return L
 
 
