@@ -238,6 +238,15 @@ int gsb200_image_loss(const float *rasterized_image, const float *ground_truth_i
                       int32_t camera_width, float lambda_value, float upstream_grad, float *loss_out3,
                       float *grad_rasterized_image, void *temp, int64_t temp_bytes, void *stream);
 
+/* One Adam step on a flat float32 tensor in ONE kernel: the update of torch.optim.Adam as the reference
+ * trainer configures it (GaussianPointTrainer.py:126-129: betas given, eps 1e-8, no weight decay, no amsgrad; stepped at
+ * :176-177) -- m += (g - m)(1 - b1); v = v b2 + (1 - b2) g^2; p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps).
+ * `step` is the 1-based step count t.  All pointers device memory, 16-byte aligned; exp_avg / exp_avg_sq are the
+ * caller-owned state (zero before the first step).  lr / betas / eps are doubles like torch's Python floats (1 - beta is
+ * formed in double).  HBM-bound: 28 B per element. */
+int gsb200_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t num_elements, double lr,
+                     double beta1, double beta2, double eps, int32_t step, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

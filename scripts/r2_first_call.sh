@@ -16,6 +16,7 @@ for wl in C3 C2; do
 done
 echo "== bench default"; timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline | tee gpurun_out/r2_bench_default.json | cut -c1-400
 echo "== bench transposed"; GSB200_BACKWARD_IMPL=transposed timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline | tee gpurun_out/r2_bench_transposed.json | cut -c1-400
+echo "== C5 trainer, torch step vs fused step"; timeout 300 python scripts/train_c5.py 1000; timeout 300 python scripts/train_c5.py 1000 --fused
 echo "== ncu transposed kernel"
 GSB200_BACKWARD_IMPL=transposed timeout 600 ncu --set full --clock-control none --import-source on -k regex:blend_backward_transposed -s 2 -c 1 \
   -o gpurun_out/r2_bwd_transposed python scripts/bench_stages.py C3 > gpurun_out/r2_ncu.log 2>&1; tail -3 gpurun_out/r2_ncu.log

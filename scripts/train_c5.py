@@ -51,13 +51,14 @@ ac.num_iterations_warm_up, ac.num_iterations_densify = 1000, 100
 ac.densification_view_space_position_gradients_threshold = 3e-6
 ac.transparent_alpha_threshold, ac.reset_alpha_value, ac.num_iterations_reset_alpha = -2.0, -1.9, 4000
 cfg.loss_function_config.enable_regularization = False
-trainer = GaussianPointCloudTrainer(cfg, scene, views)
+fused = "--fused" in sys.argv  # fused image loss (gsb200_image_loss) + fused Adam (gsb200_adam_step) in the step
+trainer = GaussianPointCloudTrainer(cfg, scene, views, fused_image_loss=fused, fused_adam=fused)
 psnr0 = trainer.validation(views[::5])
 torch.cuda.synchronize(); t0 = time.perf_counter()
 hist = trainer.train(log_interval=50)
 torch.cuda.synchronize(); dt = time.perf_counter() - t0
 psnr1 = trainer.validation(views[::5])
-print(json.dumps({"config": "C5 tat_truck_every_8_test.yaml shapes, synthetic targets", "iterations": iters,
+print(json.dumps({"config": "C5 tat_truck_every_8_test.yaml shapes, synthetic targets", "iterations": iters, "fused_step": fused,
                   "seconds": round(dt, 2), "iterations_per_s": round(iters / dt, 1), "psnr_before": round(psnr0, 2),
                   "psnr_after": round(psnr1, 2), "points_allocated": int(scene.point_cloud.shape[0]),
                   "points_valid_start": hist[0]["num_valid_points"], "points_valid_end": hist[-1]["num_valid_points"],

@@ -7,6 +7,7 @@ from .Camera import CameraInfo, CameraView  # noqa: F401
 from .densification import GaussianPointAdaptiveController  # noqa: F401
 from .loss import (LossFunction, fused_image_loss, fused_image_loss_with_grad, fused_l1_loss,  # noqa: F401
                    fused_l1_loss_with_grad)
+from .optim import FusedAdam  # noqa: F401
 from .scene_io import GaussianPointCloudScene  # noqa: F401
 from .image_pose_dataset import ImagePoseDataset  # noqa: F401
 from .GaussianPointCloudRasterisation import (  # noqa: F401
@@ -18,5 +19,5 @@ from .GaussianPointCloudRasterisation import (  # noqa: F401
 )
 
 __all__ = ["CameraInfo", "CameraView", "GaussianPointCloudRasterisation", "GaussianPointAdaptiveController",
-           "LossFunction", "fused_l1_loss", "fused_l1_loss_with_grad", "fused_image_loss", "fused_image_loss_with_grad", "GaussianPointCloudScene", "ImagePoseDataset", "find_tile_start_and_end",
+           "LossFunction", "fused_l1_loss", "fused_l1_loss_with_grad", "fused_image_loss", "fused_image_loss_with_grad", "FusedAdam", "GaussianPointCloudScene", "ImagePoseDataset", "find_tile_start_and_end",
            "TILE_WIDTH", "TILE_HEIGHT", "BOUNDARY_TILES"]

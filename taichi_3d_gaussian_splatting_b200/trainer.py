@@ -76,11 +76,13 @@ class GaussianPointCloudTrainer:
 
     def __init__(self, config: "GaussianPointCloudTrainer.TrainConfig", scene: Scene, train_views: List[View],
                  rasterisation_factory: Optional[Callable] = None, generator: Optional[torch.Generator] = None,
-                 fused_image_loss: bool = False):
+                 fused_image_loss: bool = False, fused_adam: bool = False):
         """``fused_image_loss``: clamp + L1 + D-SSIM and their gradient in two CUDA kernels (``gsb200_image_loss``)
-        instead of ~60 autograd kernels per step; same loss values (CUDA only)."""
+        instead of ~60 autograd kernels per step; same loss values (CUDA only).  ``fused_adam``: the two Adam updates as
+        one kernel each (``optim.FusedAdam`` / ``gsb200_adam_step``) instead of torch's foreach path (CUDA only)."""
         self.config = config
         self.fused_image_loss = fused_image_loss
+        self.fused_adam = fused_adam
         self.scene = scene
         self.train_views = train_views
         self.adaptive_controller = GaussianPointAdaptiveController(
@@ -104,8 +106,12 @@ class GaussianPointCloudTrainer:
 
     def train(self, log_interval: int = 0):
         cfg = self.config
-        optimizer = torch.optim.Adam([self.scene.point_cloud_features], lr=cfg.feature_learning_rate, betas=(0.9, 0.999))
-        position_optimizer = torch.optim.Adam([self.scene.point_cloud], lr=cfg.position_learning_rate, betas=(0.9, 0.999))
+        if self.fused_adam:
+            from .optim import FusedAdam as Adam
+        else:
+            Adam = torch.optim.Adam
+        optimizer = Adam([self.scene.point_cloud_features], lr=cfg.feature_learning_rate, betas=(0.9, 0.999))
+        position_optimizer = Adam([self.scene.point_cloud], lr=cfg.position_learning_rate, betas=(0.9, 0.999))
         scheduler = torch.optim.lr_scheduler.ExponentialLR(position_optimizer, gamma=cfg.position_learning_rate_decay_rate)
         downsample_factor = cfg.initial_downsample_factor
         for iteration in range(cfg.num_iterations):

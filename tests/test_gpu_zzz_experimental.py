@@ -87,3 +87,38 @@ def test_fused_image_loss_matches_the_torch_loss(H, W, lam):
     assert float((a.grad - b.grad).abs().max()) <= 5e-5 * scale
     loss_c, _, _ = fn.forward_rasterized(pred, gt)
     assert abs(float(loss_c) - float(loss_b)) <= 1e-7
+
+
+@pytest.mark.parametrize("shape", [(1000, 56), (1000, 3), (7,)])
+def test_fused_adam_follows_torch_adam(shape):
+    """optim.FusedAdam (gsb200_adam_step) vs torch.optim.Adam as the reference trainer configures it, with the
+    ExponentialLR schedule of the position optimiser (GaussianPointTrainer.py:126-132)."""
+    from taichi_3d_gaussian_splatting_b200 import FusedAdam
+    g = torch.Generator().manual_seed(3)
+    w0 = torch.randn(shape, generator=g).cuda()
+    a, b = w0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+    oa, ob = torch.optim.Adam([a], lr=5e-3, betas=(0.9, 0.999)), FusedAdam([b], lr=5e-3, betas=(0.9, 0.999))
+    sa, sb = (torch.optim.lr_scheduler.ExponentialLR(o, gamma=0.97) for o in (oa, ob))
+    for step in range(8):
+        grad = (torch.randn(shape, generator=g) * 10.0 ** (step % 4 - 2)).cuda()
+        a.grad, b.grad = grad.clone(), grad.clone()
+        oa.step(); ob.step(); sa.step(); sb.step()
+        assert float((a - b).abs().max()) <= 1e-6 * max(1.0, float(w0.abs().max()))
+    assert torch.allclose(oa.state[a]["exp_avg_sq"], ob.state[b]["exp_avg_sq"], rtol=1e-5, atol=0)
+
+
+def test_trainer_with_the_fused_step_follows_the_torch_step():
+    """The trainer loop with fused_image_loss + fused_adam vs the same loop with torch's loss / autograd / Adam."""
+    from trainer_helpers import hidden_scene, initial_scene, render_views, train_config
+    from taichi_3d_gaussian_splatting_b200.trainer import GaussianPointCloudTrainer
+    hidden = hidden_scene(n=400)
+    views = render_views(GPCR(Config()), hidden, device="cuda")
+    histories, psnrs = [], []
+    for fused in (False, True):
+        tr = GaussianPointCloudTrainer(train_config(40), initial_scene(hidden, device="cuda"), views,
+                                       fused_image_loss=fused, fused_adam=fused)
+        histories.append(tr.train(log_interval=1))
+        psnrs.append(tr.validation())
+    for ha, hb in zip(*histories):
+        assert abs(ha["loss"] - hb["loss"]) <= 2e-3 * abs(ha["loss"]), (ha, hb)
+    assert abs(psnrs[0] - psnrs[1]) < 0.1, psnrs

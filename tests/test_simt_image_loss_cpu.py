@@ -49,3 +49,31 @@ def test_fused_image_loss_source_matches_the_torch_loss(emu, H, W, lam, upstream
     out2 = np.zeros(3, np.float32)
     assert emu.emu_image_loss(c(pred), c(gt), H, W, f(lam), f(upstream), c(out2), None, c(temp)) > 0
     assert np.array_equal(out2, out)
+
+
+@pytest.mark.parametrize("n", [7, 4096, 59 * 37])
+def test_fused_adam_source_follows_torch_adam(emu, n):
+    """csrc/adam.cu under the emulator vs torch.optim.Adam as the reference trainer configures it
+    (GaussianPointTrainer.py:126-129), five steps with a decaying learning rate, grid-stride and tail paths."""
+    rng = np.random.default_rng(n)
+    w0 = rng.standard_normal(n).astype(np.float32)
+    ref = torch.tensor(w0, requires_grad=True)
+    opt = torch.optim.Adam([ref], lr=5e-3, betas=(0.9, 0.999))
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.97)
+    w, m, v = w0.copy(), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    c = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    d = ctypes.c_double
+    for step in range(1, 6):
+        g = (rng.standard_normal(n) * (10.0 ** rng.integers(-3, 2))).astype(np.float32)
+        g[::9] = 0.0
+        ref.grad = torch.tensor(g)
+        lr = opt.param_groups[0]["lr"]
+        opt.step()
+        sched.step()
+        emu.emu_adam_step(c(w), c(g), c(m), c(v), ctypes.c_longlong(n), d(lr), d(0.9), d(0.999), d(1e-8), step, 2)
+        assert np.abs(w - ref.detach().numpy()).max() <= 1e-6 * max(1.0, float(np.abs(w0).max()))
+        st = opt.state[ref]
+        # same formulas, float32: torch's CPU lerp / addcmul may fuse multiply-adds, so allow a few ulps
+        em, ev = st["exp_avg"].numpy(), st["exp_avg_sq"].numpy()
+        assert np.allclose(m, em, rtol=2e-6, atol=1e-6 * np.abs(em).max())
+        assert np.allclose(v, ev, rtol=2e-6, atol=1e-6 * np.abs(ev).max())
