@@ -12,21 +12,13 @@ import pytest
 
 from helpers import grad_close, oracle_backward, oracle_forward
 from taichi_3d_gaussian_splatting_b200.synthetic import make_scene
-from test_simt_preprocess_cpu import _large_splats, _run as run_preprocess, build_emulator
+from simt_helpers import c, emu_sort, emulated_operator
+from test_simt_preprocess_cpu import _large_splats, build_emulator
 
 
 @pytest.fixture(scope="module")
 def emu():
     return build_emulator()
-
-
-def emu_sort(emu, keys, vals, end_bit):
-    keys, vals = np.ascontiguousarray(keys), np.ascontiguousarray(vals, dtype=np.int32)
-    ko, vo = np.empty_like(keys), np.empty_like(vals)
-    c = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
-    if keys.shape[0]:
-        assert emu.emu_sort_pairs(c(keys), c(vals), c(ko), c(vo), ctypes.c_longlong(keys.shape[0]), keys.dtype.itemsize, end_bit) > 0
-    return ko, vo
 
 
 @pytest.mark.parametrize("dtype,end_bit", [(np.uint32, 30), (np.uint32, 13), (np.uint64, 45), (np.uint64, 64)])
@@ -49,43 +41,8 @@ def test_emulated_tile_ranges_known_answer(emu):
     tiles = np.array([0, 0, 0, 2, 2, 5, 5, 5, 5, 7], np.uint64)
     keys = (tiles << np.uint64(32)) | np.arange(10, dtype=np.uint64)
     start, end = np.zeros(9, np.int32), np.zeros(9, np.int32)
-    c = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
     emu.emu_tile_ranges(c(keys), ctypes.c_longlong(10), 8, 32, 9, c(start), c(end))
     assert start.tolist() == [0, 0, 3, 0, 0, 5, 0, 9, 0] and end.tolist() == [3, 0, 5, 0, 0, 9, 0, 10, 0]
-
-
-def _pipeline(emu, scene, transposed, exact, band):
-    c = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
-    pre = run_preprocess(emu, scene, {}, key64=False, filter_tiles=True)
-    M, Kk = int(pre.counters[0]), int(pre.counters[1])
-    sk, sv = emu_sort(emu, pre.keys[:Kk], pre.vals[:Kk], pre.tile_bits + pre.depth_bits)
-    order = np.argsort(pre.keys[:Kk], kind="stable")
-    assert np.array_equal(sk, pre.keys[:Kk][order]) and np.array_equal(sv, pre.vals[:Kk][order])
-    start, end = np.zeros(pre.T, np.int32), np.zeros(pre.T, np.int32)
-    emu.emu_tile_ranges(c(sk), ctypes.c_longlong(Kk), sk.dtype.itemsize, pre.depth_bits, pre.T, c(start), c(end))
-    tile = sk.astype(np.int64) >> pre.depth_bits
-    assert np.array_equal(end - start, np.bincount(tile, minlength=pre.T)) and (start[end > start] == np.searchsorted(tile, np.flatnonzero(end > start))).all()
-    H, W = pre.H, pre.W
-    image, depth, acc = np.zeros((H, W, 3), np.float32), np.zeros((H, W), np.float32), np.zeros((H, W), np.float32)
-    last, cnt = np.zeros((H, W), np.int32), np.zeros((H, W), np.int32)
-    emu.emu_blend_forward(0, int(exact), H, W, c(start), c(end), c(sv), c(pre.records), c(image), c(depth), c(acc), c(last), c(cnt))
-    g = np.random.default_rng(77).standard_normal((H, W, 3)).astype(np.float32)
-    accum, mag = np.zeros((max(M, 1), 12), np.float32), np.zeros((H, W, 2), np.float32)
-    emu.emu_blend_backward(int(transposed), int(exact), 1, H, W, c(start), c(end), c(sv), c(pre.records), c(g), c(acc), c(last),
-                           c(accum), c(mag))
-    N = pre.point_offset.shape[0]
-    q = scene.q_pointcloud_camera.numpy().astype(np.float32).copy()
-    t = scene.t_pointcloud_camera.numpy().astype(np.float32).copy()
-    poses = np.zeros((q.shape[0], 20), np.float32)
-    emu.emu_pose(q.shape[0], c(q), c(t), c(poses))
-    xyz = scene.point_cloud.numpy().astype(np.float32).copy()
-    K = scene.camera_info.camera_intrinsics.numpy().astype(np.float32).copy()
-    obj = scene.point_object_id.numpy().astype(np.int32).copy()
-    gx, gf = np.full((N, 3), 7.0, np.float32), np.full((N, 56), 7.0, np.float32)  # every row must be overwritten
-    f = ctypes.c_float
-    emu.emu_backward_points(ctypes.c_longlong(N), c(pre.point_offset), c(pre.records), c(pre.pic), c(accum), c(poses), c(xyz),
-                            c(pre.feats), c(obj), c(t), c(K), band, f(1.0), f(0.5), f(20.0), f(5.0), f(1.0), c(gx), c(gf))
-    return image, cnt, g, gx, gf
 
 
 @pytest.mark.parametrize("transposed", [False, True])
@@ -97,9 +54,11 @@ def test_emulated_cuda_path_reproduces_the_oracle_end_to_end(emu, which, band, t
     else:
         scene = _large_splats(0.3)
     o, fwd, feats_n = oracle_forward(scene)
-    image, cnt, g, gx, gf = _pipeline(emu, scene, transposed, True, band)
-    assert np.abs(image - fwd.image).max() <= 1e-4
-    assert int((cnt != fwd.pixel_valid_point_count).sum()) == 0
+    g = np.random.default_rng(77).standard_normal(fwd.image.shape).astype(np.float32)
+    out = emulated_operator(emu, scene, g, band=band, transposed=transposed)
+    gx, gf = out.grad_pointcloud, out.grad_pointcloud_features
+    assert np.abs(out.image - fwd.image).max() <= 1e-4
+    assert int((out.count != fwd.pixel_valid_point_count).sum()) == 0
     bwd = oracle_backward(o, fwd, scene, feats_n, g, band)
     loose = which == "large"  # deep lists: the criterion of tests/test_gpu_zz_large_splats.py
     kw = dict(rtol=2e-3, floor_frac=5e-5) if loose else {}
