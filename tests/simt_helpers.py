@@ -21,11 +21,8 @@ def emu_sort(emu, keys, vals, end_bit):
     return ko, vo
 
 
-def emulated_operator(emu, scene, grad_image, band=3, transposed=False, exact=True, cfg=None, filter_tiles=True,
-                      factors=(1.0, 0.5, 20.0, 5.0, 1.0)):
-    """Forward + backward of the CUDA path under the emulator.  ``scene``: CPU tensors with the operator's input fields;
-    ``cfg``: near_plane / far_plane / depth_to_sort_key_scale; ``factors``: grad q, s, alpha, colour, high-order colour
-    (GPCR:782-786).  Returns the outputs, the per-point stage tensors, the dense gradients and the hook tensors."""
+def emulated_forward(emu, scene, cfg=None, exact=True, filter_tiles=True):
+    """Forward of the CUDA path under the emulator; returns the saved-for-backward state with the outputs."""
     cfg = cfg or {}
     pre = run_preprocess(emu, scene, cfg, key64=False, filter_tiles=filter_tiles)
     M, Kk = int(pre.counters[0]), int(pre.counters[1])
@@ -39,11 +36,22 @@ def emulated_operator(emu, scene, grad_image, band=3, transposed=False, exact=Tr
     H, W = pre.H, pre.W
     image, depth, acc = np.zeros((H, W, 3), np.float32), np.zeros((H, W), np.float32), np.zeros((H, W), np.float32)
     last, cnt = np.zeros((H, W), np.int32), np.zeros((H, W), np.int32)
-    emu.emu_blend_forward(0, int(exact), H, W, c(start), c(end), c(sv), c(pre.records), c(image), c(depth), c(acc), c(last), c(cnt))
+    if Kk:
+        emu.emu_blend_forward(0, int(exact), H, W, c(start), c(end), c(sv), c(pre.records), c(image), c(depth), c(acc), c(last),
+                              c(cnt))
+    return SimpleNamespace(pre=pre, M=M, K=Kk, start=start, end=end, sorted_vals=sv, image=image, depth=depth, acc_alpha=acc,
+                           last_effective=last, count=cnt, exact=exact, scene=scene)
+
+
+def emulated_backward(emu, st, grad_image, band=3, transposed=False, factors=(1.0, 0.5, 20.0, 5.0, 1.0), stats=True):
+    """Backward for a state of :func:`emulated_forward`: dense gradients + the hook tensors."""
+    pre, scene, M = st.pre, st.scene, st.M
+    H, W = pre.H, pre.W
     g = np.ascontiguousarray(grad_image, dtype=np.float32)
     accum, mag = np.zeros((max(M, 1), 12), np.float32), np.zeros((H, W, 2), np.float32)
-    emu.emu_blend_backward(int(transposed), int(exact), 1, H, W, c(start), c(end), c(sv), c(pre.records), c(g), c(acc), c(last),
-                           c(accum), c(mag))
+    if st.K:
+        emu.emu_blend_backward(int(transposed), int(st.exact), int(stats), H, W, c(st.start), c(st.end), c(st.sorted_vals),
+                               c(pre.records), c(g), c(st.acc_alpha), c(st.last_effective), c(accum), c(mag))
     N = pre.point_offset.shape[0]
     q = scene.q_pointcloud_camera.numpy().astype(np.float32).copy()
     t = scene.t_pointcloud_camera.numpy().astype(np.float32).copy()
@@ -58,12 +66,84 @@ def emulated_operator(emu, scene, grad_image, band=3, transposed=False, exact=Tr
                             c(pre.feats), c(obj), c(t), c(K), int(band) if band in (0, 1, 2) else 3, *(f(v) for v in factors),
                             c(gx), c(gf))
     ids = pre.point_id[:M]
+    hook = SimpleNamespace(grad_point_in_camera=gx[ids], grad_pointfeatures_in_camera=gf[ids], grad_viewspace=accum[:M, 0:2].copy(),
+                           magnitude_grad_viewspace=accum[:M, 9].copy(), magnitude_grad_viewspace_on_image=mag,
+                           num_affected_pixels=np.round(accum[:M, 10]).astype(np.int32))
+    return gx, gf, hook
+
+
+def emulated_operator(emu, scene, grad_image, band=3, transposed=False, exact=True, cfg=None, filter_tiles=True,
+                      factors=(1.0, 0.5, 20.0, 5.0, 1.0)):
+    """Forward + backward of the CUDA path under the emulator.  ``scene``: CPU tensors with the operator's input fields;
+    ``cfg``: near_plane / far_plane / depth_to_sort_key_scale; ``factors``: grad q, s, alpha, colour, high-order colour
+    (GPCR:782-786).  Returns the outputs, the per-point stage tensors, the dense gradients and the hook tensors."""
+    st = emulated_forward(emu, scene, cfg, exact, filter_tiles)
+    gx, gf, hook = emulated_backward(emu, st, grad_image, band, transposed, factors)
+    pre, M = st.pre, st.M
+    ids = pre.point_id[:M]
     r = pre.records[:M]
     return SimpleNamespace(
-        image=image, depth=depth, count=cnt, acc_alpha=acc, last_effective=last, features_after_forward=pre.feats,
-        point_id_in_camera_list=ids, num_overlap_tiles=pre.num_tiles[:M], point_uv=r[:, 0:2].copy(),
-        point_uv_conic_and_rescale=r[:, 2:6].copy(), point_alpha_after_activation=r[:, 6].copy(), point_color=r[:, 8:11].copy(),
-        point_radii=r[:, 11].copy(), point_in_camera=pre.pic[:M], grad_pointcloud=gx, grad_pointcloud_features=gf,
-        hook=SimpleNamespace(grad_point_in_camera=gx[ids], grad_pointfeatures_in_camera=gf[ids], grad_viewspace=accum[:M, 0:2],
-                             magnitude_grad_viewspace=accum[:M, 9], magnitude_grad_viewspace_on_image=mag,
-                             num_affected_pixels=np.round(accum[:M, 10]).astype(np.int32)))
+        image=st.image, depth=st.depth, count=st.count, acc_alpha=st.acc_alpha, last_effective=st.last_effective,
+        features_after_forward=pre.feats, point_id_in_camera_list=ids, num_overlap_tiles=pre.num_tiles[:M],
+        point_uv=r[:, 0:2].copy(), point_uv_conic_and_rescale=r[:, 2:6].copy(), point_alpha_after_activation=r[:, 6].copy(),
+        point_color=r[:, 8:11].copy(), point_radii=r[:, 11].copy(), point_in_camera=pre.pic[:M], grad_pointcloud=gx,
+        grad_pointcloud_features=gf, hook=hook)
+
+
+class EmulatedCudaRasterisationModule:
+    """TEST HELPER: the emulated CUDA path behind the operator's module / autograd surface (CPU tensors), so that the
+    behavioural tests and the optimisation-trajectory golden can run on the CUDA kernel sources without a GPU."""
+
+    def __init__(self, config, backward_valid_point_hook=None, backward_impl="butterfly", exact_exp=True):
+        import torch
+
+        from taichi_3d_gaussian_splatting_b200 import GaussianPointCloudRasterisation as GPCR
+        from test_simt_preprocess_cpu import build_emulator
+        self.config, self.hook = config, backward_valid_point_hook
+        emu = build_emulator()
+        outer = self
+
+        class _Fn(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, pc, feat, mask, obj, q, t, camera_info, band):
+                scene = SimpleNamespace(point_cloud=pc.detach(), point_cloud_features=feat.detach(), point_invalid_mask=mask,
+                                        point_object_id=obj, camera_info=camera_info, q_pointcloud_camera=q,
+                                        t_pointcloud_camera=t)
+                cfg = dict(near_plane=config.near_plane, far_plane=config.far_plane,
+                           depth_to_sort_key_scale=config.depth_to_sort_key_scale)
+                st = emulated_forward(emu, scene, cfg, exact=exact_exp)
+                with torch.no_grad():  # in-place quaternion normalisation of the in-frustum rows, GPCR:264-266
+                    feat.copy_(torch.from_numpy(st.pre.feats))
+                st.scene.point_cloud_features = feat.detach()
+                ctx.st, ctx.band = st, band
+                image, depth, count = torch.from_numpy(st.image), torch.from_numpy(st.depth), torch.from_numpy(st.count)
+                ctx.mark_non_differentiable(depth, count)
+                return image, depth, count
+
+            @staticmethod
+            def backward(ctx, g_image, g_depth, g_count):
+                st = ctx.st
+                gx, gf, h = emulated_backward(
+                    emu, st, g_image.contiguous().numpy(), ctx.band, transposed=backward_impl == "transposed",
+                    factors=(config.grad_q_factor, config.grad_s_factor, config.grad_alpha_factor, config.grad_color_factor,
+                             config.grad_high_order_color_factor))
+                if outer.hook is not None:
+                    pre, M = st.pre, st.M
+                    outer.hook(GPCR.BackwardValidPointHookInput(
+                        point_id_in_camera_list=torch.from_numpy(pre.point_id[:M].copy()),
+                        grad_point_in_camera=torch.from_numpy(h.grad_point_in_camera),
+                        grad_pointfeatures_in_camera=torch.from_numpy(h.grad_pointfeatures_in_camera),
+                        grad_viewspace=torch.from_numpy(h.grad_viewspace),
+                        magnitude_grad_viewspace=torch.from_numpy(h.magnitude_grad_viewspace),
+                        magnitude_grad_viewspace_on_image=torch.from_numpy(h.magnitude_grad_viewspace_on_image),
+                        num_overlap_tiles=torch.from_numpy(pre.num_tiles[:M].copy()),
+                        num_affected_pixels=torch.from_numpy(h.num_affected_pixels),
+                        point_depth=torch.from_numpy(pre.pic[:M, 2].copy()),
+                        point_uv_in_camera=torch.from_numpy(pre.records[:M, 0:2].copy())))
+                return torch.from_numpy(gx), torch.from_numpy(gf), None, None, None, None, None, None
+
+        self._fn = _Fn
+
+    def __call__(self, inp):
+        return self._fn.apply(inp.point_cloud, inp.point_cloud_features, inp.point_invalid_mask, inp.point_object_id,
+                              inp.q_pointcloud_camera, inp.t_pointcloud_camera, inp.camera_info, inp.color_max_sh_band)

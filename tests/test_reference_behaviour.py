@@ -18,12 +18,19 @@ from taichi_3d_gaussian_splatting_b200 import GaussianPointCloudRasterisation as
 from taichi_3d_gaussian_splatting_b200.utils import SE3_to_quaternion_and_translation_torch
 
 BACKENDS = [pytest.param("oracle", id="oracle-cpu"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
+# + the CUDA kernel sources executed on the CPU under the SIMT emulator of tests/simt (small cases only: it is slow)
+BACKENDS_WITH_SIMT = BACKENDS + [pytest.param("simt", id="cuda-sources-emulated-cpu"),
+                                 pytest.param("simt-transposed", id="cuda-sources-emulated-cpu-transposed-backward")]
 
 
 def _rasteriser(backend, hook=None, **cfg):
     config = GPCR.GaussianPointCloudRasterisationConfig(**cfg)
     if backend == "cuda":
         return GPCR(config=config, backward_valid_point_hook=hook), torch.device("cuda:0")
+    if backend.startswith("simt"):
+        from simt_helpers import EmulatedCudaRasterisationModule
+        impl = "transposed" if backend.endswith("transposed") else "butterfly"
+        return EmulatedCudaRasterisationModule(config, backward_valid_point_hook=hook, backward_impl=impl), torch.device("cpu")
     from oracle_module import OracleRasterisationModule
     return OracleRasterisationModule(config, backward_valid_point_hook=hook), torch.device("cpu")
 
@@ -57,7 +64,7 @@ def _coverage_scene(num_points, device, seed):
     return point_cloud, features, mask, obj, camera_info, q.to(device), t.to(device)
 
 
-@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("backend", BACKENDS_WITH_SIMT[:-1])  # 510 tiles: one emulated variant is enough (35 s)
 def test_rasterisation_basic(backend):
     rasterisation, device = _rasteriser(backend)
     height, width, num_points = 272, 480, 20000  # the reference uses 1088 x 1920 and 1e5 points (8000 of them valid)
@@ -86,7 +93,7 @@ def test_rasterisation_basic(backend):
         assert float(features.grad[:8000].abs().max()) > 0.0
 
 
-@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("backend", BACKENDS_WITH_SIMT)
 def test_backward_hook(backend):
     seen = {}
 
@@ -176,7 +183,7 @@ def test_adaptive_controller_basic(backend):
     assert bool(torch.isfinite(point_cloud).all()) and bool(torch.isfinite(features).all())
 
 
-@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("backend", BACKENDS_WITH_SIMT)
 def test_optimisation_trajectory_matches_the_reference(backend):
     """tests/golden/make_training_golden.py ran 30 iterations of the reference's own optimisation loop
     (GaussianPointAdaptiveController_test.py:15-98: reference operator with its kernels under taichi_shim.py, reference
