@@ -80,8 +80,8 @@ __global__ void __launch_bounds__(L1_THREADS) l1_loss_kernel(const L1Params p) {
     }
 }
 
-int launch_l1_loss(const float *pred, const float *target, long long n, int clamp01, float upstream,
-                   float *loss, float *grad, void *temp, cudaStream_t stream) {
+static inline L1Params l1_params(const float *pred, const float *target, long long n, int clamp01, float upstream,
+                                 float *loss, float *grad, void *temp, long long *blocks_out) {
     L1Params p;
     p.pred = pred;
     p.target = target;
@@ -95,13 +95,24 @@ int launch_l1_loss(const float *pred, const float *target, long long n, int clam
     long long blocks = ((n >> 2) + L1_THREADS - 1) / L1_THREADS;
     if (blocks < 1) blocks = 1;
     if (blocks > L1_MAX_BLOCKS) blocks = L1_MAX_BLOCKS;
+    *blocks_out = blocks;
+    return p;
+}
+
+#ifndef GSB_HOST_EMU
+int launch_l1_loss(const float *pred, const float *target, long long n, int clamp01, float upstream,
+                   float *loss, float *grad, void *temp, cudaStream_t stream) {
+    long long blocks = 1;
+    const L1Params p = l1_params(pred, target, n, clamp01, upstream, loss, grad, temp, &blocks);
     l1_loss_kernel<<<(int)blocks, L1_THREADS, 0, stream>>>(p);
     GSB_CUDA_CHECK(cudaGetLastError());
     return GSB_OK;
 }
+#endif
 
 }  // namespace gsb
 
+#ifndef GSB_HOST_EMU
 extern "C" {
 
 int64_t gsb200_l1_loss_temp_bytes(void) { return (int64_t)(4 + gsb::L1_MAX_BLOCKS) * 4; }
@@ -126,3 +137,4 @@ int gsb200_l1_loss(const float *predicted_image, const float *ground_truth_image
 }
 
 }  // extern "C"
+#endif  // GSB_HOST_EMU

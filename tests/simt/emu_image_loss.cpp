@@ -20,3 +20,16 @@ extern "C" long long emu_image_loss(const float *pred_hwc, const float *gt_chw, 
     simt_emu::launch(image_loss_grad_kernel, 3 * L.tiles_ix * L.tiles_iy, IL_THREADS, p);
     return simt_emu::M().switches;
 }
+
+// the fused clamp + L1 loss + gradient kernel (csrc/loss.cu, gsb200_l1_loss)
+#include "../../taichi_3d_gaussian_splatting_b200/csrc/loss.cu"
+
+extern "C" long long emu_l1_loss_temp_bytes() { return (long long)(4 + gsb::L1_MAX_BLOCKS) * 4; }
+
+extern "C" void emu_l1_loss(const float *pred, const float *target, long long n, int clamp01, float upstream, float *loss,
+                            float *grad, void *temp) {
+    using namespace gsb;
+    long long blocks = 1;
+    const L1Params p = l1_params(pred, target, n, clamp01, upstream, loss, grad, temp, &blocks);
+    simt_emu::launch(l1_loss_kernel, (int)blocks, L1_THREADS, p);
+}
