@@ -247,6 +247,18 @@ int gsb200_image_loss(const float *rasterized_image, const float *ground_truth_i
 int gsb200_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t num_elements, double lr,
                      double beta1, double beta2, double eps, int32_t step, void *stream);
 
+/* The densification controller's per-iteration accumulator update in ONE kernel: what
+ * GaussianPointAdaptiveController.update does with the backward-hook tensors, GaussianPointAdaptiveController.py:130-143
+ * (six indexed accumulations, mag / n_pixels with NaN -> 0, row norm; ~15 torch launches).  The first five arguments are
+ * fields of BackwardValidPointHookInput (M entries), the last six the controller's accumulators (N entries; int32 / float32).
+ * ids must be unique (they are: GPCR:861-864).  All pointers device memory. */
+int gsb200_controller_update(const int32_t *point_id_in_camera_list, int64_t num_points_in_camera,
+                             const int32_t *num_affected_pixels, const float *magnitude_grad_viewspace,
+                             const float *grad_point_in_camera, int32_t *accumulated_num_in_camera,
+                             int32_t *accumulated_num_pixels, float *accumulated_view_space_position_gradients,
+                             float *accumulated_view_space_position_gradients_avg, float *accumulated_position_gradients,
+                             float *accumulated_position_gradients_norm, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,8 +51,8 @@ ac.num_iterations_warm_up, ac.num_iterations_densify = 1000, 100
 ac.densification_view_space_position_gradients_threshold = 3e-6
 ac.transparent_alpha_threshold, ac.reset_alpha_value, ac.num_iterations_reset_alpha = -2.0, -1.9, 4000
 cfg.loss_function_config.enable_regularization = False
-fused = "--fused" in sys.argv  # fused image loss (gsb200_image_loss) + fused Adam (gsb200_adam_step) in the step
-trainer = GaussianPointCloudTrainer(cfg, scene, views, fused_image_loss=fused, fused_adam=fused)
+fused = "--fused" in sys.argv  # fused image loss (gsb200_image_loss), Adam (gsb200_adam_step) and controller update (gsb200_controller_update)
+trainer = GaussianPointCloudTrainer(cfg, scene, views, fused_image_loss=fused, fused_adam=fused, fused_controller_update=fused)
 psnr0 = trainer.validation(views[::5])
 torch.cuda.synchronize(); t0 = time.perf_counter()
 hist = trainer.train(log_interval=50)

@@ -67,7 +67,7 @@ EXPORTS = (
     "gsb200_backward", "gsb200_stage_preprocess", "gsb200_stage_sort", "gsb200_stage_tile_ranges",
     "gsb200_stage_blend", "gsb200_sort_temp_bytes", "gsb200_sort_pairs", "gsb200_render_host", "gsb200_find_tile_start_and_end",
     "gsb200_forward_timed", "gsb200_backward_timed", "gsb200_abi_sizes", "gsb200_l1_loss_temp_bytes", "gsb200_l1_loss",
-    "gsb200_image_loss_temp_bytes", "gsb200_image_loss", "gsb200_adam_step",
+    "gsb200_image_loss_temp_bytes", "gsb200_image_loss", "gsb200_adam_step", "gsb200_controller_update",
 )
 
 _lib = None
@@ -110,6 +110,8 @@ def load() -> ctypes.CDLL:
     lib.gsb200_adam_step.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                      ctypes.c_double, c_i32, c_vp]
     lib.gsb200_adam_step.restype = ctypes.c_int
+    lib.gsb200_controller_update.argtypes = [c_vp, c_i64] + [c_vp] * 10
+    lib.gsb200_controller_update.restype = ctypes.c_int
     sizes = (c_i64 * 3)()
     lib.gsb200_abi_sizes(sizes)
     mine = (ctypes.sizeof(GsbWorkspaceLayout), ctypes.sizeof(GsbForwardArgs), ctypes.sizeof(GsbBackwardArgs))

@@ -31,6 +31,7 @@ SOURCES = {
     "loss.cu": [],
     "image_loss.cu": [],
     "adam.cu": [],
+    "controller.cu": [],
 }
 
 

@@ -90,7 +90,10 @@ class GaussianPointAdaptiveController:
 
     def __init__(self, config: "GaussianPointAdaptiveController.GaussianPointAdaptiveControllerConfig",
                  maintained_parameters: "GaussianPointAdaptiveController.GaussianPointAdaptiveControllerMaintainedParameters",
-                 generator: Optional[torch.Generator] = None, verbose: bool = False):
+                 generator: Optional[torch.Generator] = None, verbose: bool = False, fused_update: bool = False):
+        """``fused_update``: the per-iteration accumulator update of ``update`` as one CUDA kernel
+        (``gsb200_controller_update``) instead of ~15 torch launches (CUDA tensors only)."""
+        self.fused_update = fused_update
         self.iteration_counter = -1
         self.config = config
         self.maintained_parameters = maintained_parameters
@@ -114,6 +117,14 @@ class GaussianPointAdaptiveController:
     # GaussianPointAdaptiveController.py:130-146
     def update(self, input_data: GaussianPointCloudRasterisation.BackwardValidPointHookInput):
         self.iteration_counter += 1
+        if self.fused_update:
+            self._update_fused(input_data)
+            if self.iteration_counter >= self.config.num_iterations_warm_up and \
+                    self.iteration_counter % self.config.num_iterations_densify == 0:
+                with torch.no_grad():
+                    self._find_densify_points(input_data)
+                    self.input_data = input_data
+            return
         with torch.no_grad():
             ids = input_data.point_id_in_camera_list.long()
             self.accumulated_num_in_camera[ids] += 1
@@ -130,6 +141,25 @@ class GaussianPointAdaptiveController:
             elif self.iteration_counter % self.config.num_iterations_densify == 0:
                 self._find_densify_points(input_data)
                 self.input_data = input_data
+
+    def _update_fused(self, h):
+        from . import _lib
+        ids = h.point_id_in_camera_list
+        if not ids.is_cuda:
+            raise RuntimeError("fused_update needs CUDA tensors (there is no CPU path)")
+        ids = ids.to(torch.int32).contiguous()
+        npix = h.num_affected_pixels.to(torch.int32).contiguous()
+        mag = h.magnitude_grad_viewspace.to(torch.float32).contiguous()
+        gxyz = h.grad_point_in_camera.to(torch.float32).contiguous()
+        with torch.cuda.device(ids.device):
+            stream = torch.cuda.current_stream(ids.device).cuda_stream
+            _lib.check(_lib.load().gsb200_controller_update(
+                ids.data_ptr(), ids.shape[0], npix.data_ptr(), mag.data_ptr(), gxyz.data_ptr(),
+                self.accumulated_num_in_camera.data_ptr(), self.accumulated_num_pixels.data_ptr(),
+                self.accumulated_view_space_position_gradients.data_ptr(),
+                self.accumulated_view_space_position_gradients_avg.data_ptr(),
+                self.accumulated_position_gradients.data_ptr(), self.accumulated_position_gradients_norm.data_ptr(),
+                stream), "gsb200_controller_update")
 
     # GaussianPointAdaptiveController.py:148-168
     def refinement(self):

@@ -76,10 +76,12 @@ class GaussianPointCloudTrainer:
 
     def __init__(self, config: "GaussianPointCloudTrainer.TrainConfig", scene: Scene, train_views: List[View],
                  rasterisation_factory: Optional[Callable] = None, generator: Optional[torch.Generator] = None,
-                 fused_image_loss: bool = False, fused_adam: bool = False):
+                 fused_image_loss: bool = False, fused_adam: bool = False, fused_controller_update: bool = False):
         """``fused_image_loss``: clamp + L1 + D-SSIM and their gradient in two CUDA kernels (``gsb200_image_loss``)
         instead of ~60 autograd kernels per step; same loss values (CUDA only).  ``fused_adam``: the two Adam updates as
-        one kernel each (``optim.FusedAdam`` / ``gsb200_adam_step``) instead of torch's foreach path (CUDA only)."""
+        one kernel each (``optim.FusedAdam`` / ``gsb200_adam_step``) instead of torch's foreach path (CUDA only).
+        ``fused_controller_update``: the controller's per-iteration accumulator update as one kernel
+        (``gsb200_controller_update``) instead of ~15 torch launches (CUDA only)."""
         self.config = config
         self.fused_image_loss = fused_image_loss
         self.fused_adam = fused_adam
@@ -90,7 +92,7 @@ class GaussianPointCloudTrainer:
             maintained_parameters=GaussianPointAdaptiveController.GaussianPointAdaptiveControllerMaintainedParameters(
                 pointcloud=scene.point_cloud, pointcloud_features=scene.point_cloud_features,
                 point_invalid_mask=scene.point_invalid_mask, point_object_id=scene.point_object_id),
-            generator=generator)
+            generator=generator, fused_update=fused_controller_update)
         factory = rasterisation_factory or GaussianPointCloudRasterisation
         self.rasterisation = factory(config=config.rasterisation_config,
                                      backward_valid_point_hook=self.adaptive_controller.update)

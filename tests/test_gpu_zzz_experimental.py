@@ -108,7 +108,7 @@ def test_fused_adam_follows_torch_adam(shape):
 
 
 def test_trainer_with_the_fused_step_follows_the_torch_step():
-    """The trainer loop with fused_image_loss + fused_adam vs the same loop with torch's loss / autograd / Adam."""
+    """The trainer loop with the fused image loss, Adam and controller update vs the same loop with torch's ops."""
     from trainer_helpers import hidden_scene, initial_scene, render_views, train_config
     from taichi_3d_gaussian_splatting_b200.trainer import GaussianPointCloudTrainer
     hidden = hidden_scene(n=400)
@@ -116,9 +116,38 @@ def test_trainer_with_the_fused_step_follows_the_torch_step():
     histories, psnrs = [], []
     for fused in (False, True):
         tr = GaussianPointCloudTrainer(train_config(40), initial_scene(hidden, device="cuda"), views,
-                                       fused_image_loss=fused, fused_adam=fused)
+                                       fused_image_loss=fused, fused_adam=fused, fused_controller_update=fused)
         histories.append(tr.train(log_interval=1))
         psnrs.append(tr.validation())
     for ha, hb in zip(*histories):
         assert abs(ha["loss"] - hb["loss"]) <= 2e-3 * abs(ha["loss"]), (ha, hb)
     assert abs(psnrs[0] - psnrs[1]) < 0.1, psnrs
+
+
+def test_fused_controller_update_matches_the_torch_update():
+    """gsb200_controller_update vs GaussianPointAdaptiveController.update's torch ops (GaussianPointAdaptiveController.py:130-143)."""
+    from taichi_3d_gaussian_splatting_b200 import GaussianPointAdaptiveController as C
+    g = torch.Generator().manual_seed(2)
+    N, M = 5000, 1800
+    mp = lambda: C.GaussianPointAdaptiveControllerMaintainedParameters(  # noqa: E731
+        pointcloud=torch.zeros((N, 3), device="cuda"), pointcloud_features=torch.zeros((N, 56), device="cuda"),
+        point_invalid_mask=torch.zeros(N, dtype=torch.int8, device="cuda"), point_object_id=torch.zeros(N, dtype=torch.int32, device="cuda"))
+    cfg = C.GaussianPointAdaptiveControllerConfig(num_iterations_warm_up=10 ** 9)
+    a, b = C(cfg, mp()), C(cfg, mp(), fused_update=True)
+    for it in range(3):
+        ids = torch.randperm(N, generator=g)[:M].sort().values.to(torch.int32).cuda()
+        npix = torch.randint(0, 50, (M,), generator=g, dtype=torch.int32).cuda()
+        mag = (torch.rand(M, generator=g) * (npix.cpu() > 0)).cuda()
+        h = GPCR.BackwardValidPointHookInput(
+            point_id_in_camera_list=ids, grad_point_in_camera=torch.randn((M, 3), generator=g).cuda(),
+            grad_pointfeatures_in_camera=torch.zeros((M, 56), device="cuda"), grad_viewspace=torch.zeros((M, 2), device="cuda"),
+            magnitude_grad_viewspace=mag, magnitude_grad_viewspace_on_image=torch.zeros((16, 16, 2), device="cuda"),
+            num_overlap_tiles=torch.ones(M, dtype=torch.int32, device="cuda"), num_affected_pixels=npix,
+            point_depth=torch.ones(M, device="cuda"), point_uv_in_camera=torch.zeros((M, 2), device="cuda"))
+        a.update(h)
+        b.update(h)
+    for name in ("accumulated_num_in_camera", "accumulated_num_pixels"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    for name in ("accumulated_view_space_position_gradients", "accumulated_view_space_position_gradients_avg",
+                 "accumulated_position_gradients", "accumulated_position_gradients_norm"):
+        assert torch.allclose(getattr(a, name), getattr(b, name), rtol=1e-6, atol=1e-7), name

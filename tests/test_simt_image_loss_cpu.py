@@ -97,3 +97,36 @@ def test_fused_l1_source_matches_torch(emu, n, clamp):
     (2.0 * ref).backward()
     assert abs(float(loss[0]) - float(ref)) <= 1e-6 * max(1.0, float(ref))
     assert np.allclose(grad, p.grad.numpy(), rtol=1e-6, atol=0)
+
+
+def test_fused_controller_update_source_matches_the_torch_update(emu):
+    """csrc/controller.cu under the emulator vs GaussianPointAdaptiveController.update's torch ops
+    (GaussianPointAdaptiveController.py:130-143), incl. the 0/0 -> 0 rule for splats without affected pixels."""
+    from taichi_3d_gaussian_splatting_b200 import GaussianPointAdaptiveController as C
+    from taichi_3d_gaussian_splatting_b200 import GaussianPointCloudRasterisation as GPCR
+    g = torch.Generator().manual_seed(2)
+    N, M = 3000, 1100
+    ctl = C(C.GaussianPointAdaptiveControllerConfig(num_iterations_warm_up=10 ** 9),
+            C.GaussianPointAdaptiveControllerMaintainedParameters(
+                pointcloud=torch.zeros((N, 3)), pointcloud_features=torch.zeros((N, 56)),
+                point_invalid_mask=torch.zeros(N, dtype=torch.int8), point_object_id=torch.zeros(N, dtype=torch.int32)))
+    acc = [np.zeros(N, np.int32), np.zeros(N, np.int32), np.zeros(N, np.float32), np.zeros(N, np.float32),
+           np.zeros((N, 3), np.float32), np.zeros(N, np.float32)]
+    c = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    for it in range(3):
+        ids = torch.randperm(N, generator=g)[:M].sort().values.to(torch.int32)
+        npix = torch.randint(0, 50, (M,), generator=g, dtype=torch.int32)
+        mag = torch.rand(M, generator=g) * (npix > 0)
+        gxyz = torch.randn((M, 3), generator=g)
+        ctl.update(GPCR.BackwardValidPointHookInput(
+            point_id_in_camera_list=ids, grad_point_in_camera=gxyz, grad_pointfeatures_in_camera=torch.zeros((M, 56)),
+            grad_viewspace=torch.zeros((M, 2)), magnitude_grad_viewspace=mag,
+            magnitude_grad_viewspace_on_image=torch.zeros((16, 16, 2)), num_overlap_tiles=torch.ones(M, dtype=torch.int32),
+            num_affected_pixels=npix, point_depth=torch.ones(M), point_uv_in_camera=torch.zeros((M, 2))))
+        emu.emu_controller_update(c(ids.numpy()), ctypes.c_longlong(M), c(npix.numpy()), c(mag.numpy()),
+                                  c(np.ascontiguousarray(gxyz.numpy())), *(c(a) for a in acc), 3)
+    assert np.array_equal(acc[0], ctl.accumulated_num_in_camera.numpy()) and np.array_equal(acc[1], ctl.accumulated_num_pixels.numpy())
+    for got, exp in ((acc[2], ctl.accumulated_view_space_position_gradients), (acc[3], ctl.accumulated_view_space_position_gradients_avg),
+                     (acc[4], ctl.accumulated_position_gradients), (acc[5], ctl.accumulated_position_gradients_norm)):
+        assert np.allclose(got, exp.numpy(), rtol=1e-6, atol=1e-7)
+    assert acc[3].max() > 0 and np.isfinite(acc[3]).all()

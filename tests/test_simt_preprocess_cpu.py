@@ -27,7 +27,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "taichi_3d_gaussian_splatting_b200", 
 
 def build_emulator():
     out = os.path.join(SIMT, "libsimt_emu.so")
-    tus = [os.path.join(SIMT, f) for f in ("emu_blend.cpp", "emu_preprocess.cpp", "emu_sort.cpp", "emu_image_loss.cpp", "emu_adam.cpp")]
+    tus = [os.path.join(SIMT, f) for f in ("emu_blend.cpp", "emu_preprocess.cpp", "emu_sort.cpp", "emu_image_loss.cpp", "emu_adam.cpp", "emu_controller.cpp")]
     deps = tus + [os.path.join(SIMT, "simt_emu.h")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(s) for s in deps):
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
