@@ -9,7 +9,7 @@ mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 {
 echo "== pending GPU tests"; timeout 900 python -m pytest -q -m gpu tests/test_reference_behaviour.py tests/test_reference_path_golden.py tests/test_gpu_zz_large_splats.py 2>&1 | tail -15
-echo "== experimental backward (runxfail)"; timeout 600 python -m pytest -q -m gpu --runxfail tests/test_gpu_zzz_experimental.py 2>&1 | tail -25
+echo "== experimental backward (runxfail)"; timeout 600 python -m pytest -q -m gpu --runxfail tests/test_zzz_experimental_gpu.py 2>&1 | tail -25
 for wl in C3 C2; do
   echo "== stages $wl default"; timeout 300 python scripts/bench_stages.py $wl
   echo "== stages $wl transposed"; GSB200_BACKWARD_IMPL=transposed timeout 300 python scripts/bench_stages.py $wl
