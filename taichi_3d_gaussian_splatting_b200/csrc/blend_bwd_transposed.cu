@@ -4,8 +4,9 @@
 // been timed on a B200 yet.
 //
 // blend_bwd.cu reduces the 11 per-splat partials of every (warp, splat) visit across the 32 pixels of the warp with a
-// 13-shuffle butterfly: ~52 of the ~117 SASS instructions of a visit.  Here a warp walks its culled list in chunks of
-// 16 splats and works in two phases:
+// 13-shuffle butterfly: ~52 of the ~117 SASS instructions of a visit.  Here a warp copies the splats of its culled list,
+// 16 at a time, into a private chunk buffer (a partial chunk at the end of a staging batch is carried over and topped up
+// from the next batch, so only the last chunk of a tile can be short) and works on a chunk in two phases:
 //   phase 1 (lane = pixel, as before): the sequential part of GPCR:609-657 -- alpha, the transmittance recursion and
 //     the colour recursion -- which leaves two numbers per (pixel, splat): G = dL/dalpha * alpha and alpha*T.  They go
 //     to a 32 x 16 exchange buffer in shared memory (row stride 17: conflict-free both ways);
@@ -13,7 +14,7 @@
 //     every lane re-derives d and conic*d for its splat, accumulates the 11 partials over its 16 pixels in registers,
 //     the two halves are added with one shuffle per value, and the 16 finished rows leave through shared memory as
 //     6 row-contiguous RED.ADD.F32 instructions (same 2 sectors per (warp, splat) as the butterfly kernel).
-// Per 32 (pixel, splat) pairs that is ~36 (phase 1) + ~29 (phase 2) + ~3 (epilogue) instructions.
+// Per 32 (pixel, splat) pairs that is ~37 (phase 1) + ~36 (chunk fill, phase 2, epilogue) SASS instructions.
 // STATS = false (GSB_FLAG_NO_HOOK_STATS, the reference's need_extra_info = False, GPCR:521, 690-704) drops the |d/duv|
 // magnitude, the affected-pixel count and the per-pixel magnitude image.
 #include "blend_bwd.cuh"
@@ -24,15 +25,17 @@ constexpr int TB_CHUNK = 16;          // splats per chunk
 constexpr int TB_ROW = TB_CHUNK + 1;  // row stride (floats) of the (pixel, splat) exchange buffers
 constexpr int TB_TR_ROW = 13;         // row stride of the finished rows (12 accumulator words, odd stride)
 
-struct TbShared {  // dynamic shared memory image, 68.6 KB -> 3 CTAs per SM
+struct TbShared {  // dynamic shared memory image, 73.5 KB -> 3 CTAs per SM
     float4 rec[2 * 3 * GSB_TILE_PIXELS];  // [buf][plane][splat] as in blend_bwd.cu
     float4 g[8][32];                      // dL/dimage of the warp's pixels
     float xg[8][32 * TB_ROW];             // G  per (pixel, splat of the chunk); reused for the finished rows
     float xa[8][32 * TB_ROW];             // alpha * T
     int off[2][GSB_TILE_PIXELS];          // in-camera offset of the staged splats
-    int rowoff[8][TB_CHUNK];              // accumulator row of the chunk's splats (-1: nothing to add)
+    float4 chunk[8][3][TB_CHUNK];         // per warp: records of the current chunk's splats [plane][slot]
+    int chunk_idx[8][TB_CHUNK];           //   their position in the tile's sorted list
+    int chunk_off[8][TB_CHUNK];           //   their accumulator row (set to -1 after phase 2 if nothing is to be added)
     unsigned int bits[2][8][8];           // [buf][consumer warp patch][loader warp]
-    unsigned char list[8][GSB_TILE_PIXELS];  // per warp: batch elements to visit, back to front
+    unsigned char list[8][GSB_TILE_PIXELS];  // per warp: elements of the current batch to visit, back to front
     int max_last;
 };
 static_assert(32 * TB_ROW >= TB_CHUNK * TB_TR_ROW, "finished rows must fit into the exchange buffer");
@@ -83,162 +86,190 @@ blend_backward_transposed_kernel(const BlendBwdParams p) {
     __syncthreads();
     const int end = min(p.tile_end[tile], S.max_last);
 
+    float4 *const ck0 = S.chunk[warp][0], *const ck1 = S.chunk[warp][1], *const ck2 = S.chunk[warp][2];
+    int *const ck_idx = S.chunk_idx[warp], *const ck_off = S.chunk_off[warp];
+    int have = 0;  // splats waiting in the chunk buffer (warp-uniform)
+
+    // One barrier per staging batch (double-buffered, see blend_fwd.cu).  After the last batch one more trip through the
+    // loop (real == false: no staging, no barrier) flushes the short chunk that is left.
     int buf = 0;
-    for (int block_end = end; block_end > start; block_end -= GSB_TILE_PIXELS, buf ^= 1) {
-        const int block_start = max(block_end - GSB_TILE_PIXELS, start);
+    for (int block_end = end;; block_end -= GSB_TILE_PIXELS, buf ^= 1) {
+        const bool real = block_end > start;  // CTA-uniform
+        int count = 0;
         float4 *const s_r0 = S.rec + buf * 3 * GSB_TILE_PIXELS;
         float4 *const s_r1 = s_r0 + GSB_TILE_PIXELS, *const s_r2 = s_r0 + 2 * GSB_TILE_PIXELS;
-        {
-            const int idx = block_end - 1 - tid;  // element j <-> sorted index block_end-1-j
-            unsigned int mask = 0;
-            if (idx >= block_start) {
-                const int o = __ldg(&p.sorted_vals[idx]);
-                const float4 *rec = p.records + 3 * (size_t)o;
-                const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
-                s_r0[tid] = r0;
-                s_r1[tid] = EXACT_EXP ? r1 : make_float4(r1.x, r1.y * r1.z, 1.0f - r1.z, r1.w);
-                s_r2[tid] = __ldg(rec + 2);
-                S.off[buf][tid] = o;
-                mask = splat_patch_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y * r1.z, tile_x0, tile_y0);
-            }
+        if (real) {
+            const int block_start = max(block_end - GSB_TILE_PIXELS, start);
+            {
+                const int idx = block_end - 1 - tid;  // element j <-> sorted index block_end-1-j
+                unsigned int mask = 0;
+                if (idx >= block_start) {
+                    const int o = __ldg(&p.sorted_vals[idx]);
+                    const float4 *rec = p.records + 3 * (size_t)o;
+                    const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
+                    s_r0[tid] = r0;
+                    s_r1[tid] = EXACT_EXP ? r1 : make_float4(r1.x, r1.y * r1.z, 1.0f - r1.z, r1.w);
+                    s_r2[tid] = __ldg(rec + 2);
+                    S.off[buf][tid] = o;
+                    mask = splat_patch_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y * r1.z, tile_x0, tile_y0);
+                }
 #pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                const unsigned int bits = __ballot_sync(0xffffffffu, (mask >> w) & 1u);
-                if (lane == 0) S.bits[buf][w][warp] = bits;
+                for (int w = 0; w < 8; ++w) {
+                    const unsigned int bits = __ballot_sync(0xffffffffu, (mask >> w) & 1u);
+                    if (lane == 0) S.bits[buf][w][warp] = bits;
+                }
+            }
+            __syncthreads();
+            if (block_start < warp_last) {  // otherwise every splat of this batch is behind the whole patch (warp-uniform)
+                // ordered visit list of this patch: set bits of the 8 words, minus the first `skip` elements of the batch
+                // (those lie at or behind the patch's deepest effective splat)
+                const int skip = block_end - warp_last;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    unsigned int bits = S.bits[buf][warp][k];
+                    const int lo = skip - 32 * k;
+                    if (lo >= 32) bits = 0u;
+                    else if (lo > 0) bits &= ~((1u << lo) - 1u);
+                    if ((bits >> lane) & 1u)
+                        list[count + __popc(bits & ((1u << lane) - 1u))] = (unsigned char)(k * 32 + lane);
+                    count += __popc(bits);
+                }
+                __syncwarp();
             }
         }
-        __syncthreads();
-        if (block_start >= warp_last) continue;  // every splat of this batch is behind the whole patch (warp-uniform)
 
-        // ordered visit list of this patch: set bits of the 8 words, minus the first `skip` elements of the batch
-        // (those lie at or behind the patch's deepest effective splat)
-        const int skip = block_end - warp_last;
-        int count = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            unsigned int bits = S.bits[buf][warp][k];
-            const int lo = skip - 32 * k;
-            if (lo >= 32) bits = 0u;
-            else if (lo > 0) bits &= ~((1u << lo) - 1u);
-            if ((bits >> lane) & 1u) list[count + __popc(bits & ((1u << lane) - 1u))] = (unsigned char)(k * 32 + lane);
-            count += __popc(bits);
-        }
-        __syncwarp();
-
+        int pos = 0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < count; c0 += TB_CHUNK) {
-            const int n = min(TB_CHUNK, count - c0);
-            // ---- phase 1: lane = pixel; sequential over the chunk's splats (back to front)
+        do {
+            if (pos < count) {  // top the chunk buffer up from this batch's list
+                const int take = min(TB_CHUNK - have, count - pos);
+                if (lane < take) {
+                    const int j = list[pos + lane], slot = have + lane;
+                    ck0[slot] = s_r0[j];
+                    ck1[slot] = s_r1[j];
+                    ck2[slot] = s_r2[j];
+                    ck_idx[slot] = block_end - 1 - j;
+                    ck_off[slot] = S.off[buf][j];
+                }
+                have += take;
+                pos += take;
+                __syncwarp();
+            }
+            if (have == TB_CHUNK || (!real && have > 0)) {
+                const int n = have;
+                have = 0;
+                // ---- phase 1: lane = pixel; sequential over the chunk's splats (back to front)
 #pragma unroll 2
-            for (int i = 0; i < n; ++i) {
-                const int j = list[c0 + i];
-                const int idx = block_end - 1 - j;
-                const float4 r0 = s_r0[j];  // u v a b
-                const float4 r1 = s_r1[j];  // c rescale opacity depth   (fast path: c rescale*opacity 1-opacity depth)
-                const float4 r2 = s_r2[j];  // r g b radius
-                const float d0 = px - r0.x, d1 = py - r0.y;
-                const float q0 = r0.z * d0 + r0.w * d1;
-                const float q1 = r0.w * d0 + r1.x * d1;
-                float G, aT;
-                if (EXACT_EXP) {
-                    const float gp = expf(-0.5f * (d0 * q0 + d1 * q1)) * r1.y;
-                    const float prod_alpha = gp * r1.z;
-                    const bool contributes = (idx < last) && (prod_alpha >= 1.0f / 255.0f);
-                    const float alpha = fminf(prod_alpha, 0.99f);
-                    const float inv = 1.0f / (1.0f - alpha);
-                    const float Tn = T * inv;
-                    aT = contributes ? alpha * Tn : 0.0f;
-                    const float a_grad = contributes ? (r2.x * Tn - w0 * inv) * g0 + (r2.y * Tn - w1 * inv) * g1 +
-                                                           (r2.z * Tn - w2 * inv) * g2
-                                                     : 0.0f;
-                    T = contributes ? Tn : T;
-                    w0 = fmaf(r2.x, aT, w0);
-                    w1 = fmaf(r2.y, aT, w1);
-                    w2 = fmaf(r2.z, aT, w2);
-                    G = a_grad * r1.z * gp;
-                } else {
-                    // one-scalar colour recursion, see blend_bwd.cu
-                    const float P = ex2_approx_b(-0.72134752044448170368f * (d0 * q0 + d1 * q1)) * r1.y;
-                    const bool contributes = (idx < last) && (P >= 1.0f / 255.0f);
-                    const float alpha = fminf(P, 0.99f);
-                    const float inv = rcp_approx(1.0f - alpha);
-                    const float Tn = T * inv;
-                    aT = contributes ? alpha * Tn : 0.0f;
-                    const float cg = fmaf(r2.z, g2, fmaf(r2.y, g1, r2.x * g0));
-                    const float a_grad = contributes ? fmaf(cg, Tn, -(w0 * inv)) : 0.0f;
-                    T = contributes ? Tn : T;
-                    w0 = fmaf(cg, aT, w0);
-                    G = a_grad * P;
+                for (int i = 0; i < n; ++i) {
+                    const int idx = ck_idx[i];
+                    const float4 r0 = ck0[i];  // u v a b
+                    const float4 r1 = ck1[i];  // c rescale opacity depth   (fast path: c rescale*opacity 1-opacity depth)
+                    const float4 r2 = ck2[i];  // r g b radius
+                    const float d0 = px - r0.x, d1 = py - r0.y;
+                    const float q0 = r0.z * d0 + r0.w * d1;
+                    const float q1 = r0.w * d0 + r1.x * d1;
+                    float G, aT;
+                    if (EXACT_EXP) {
+                        const float gp = expf(-0.5f * (d0 * q0 + d1 * q1)) * r1.y;
+                        const float prod_alpha = gp * r1.z;
+                        const bool contributes = (idx < last) && (prod_alpha >= 1.0f / 255.0f);
+                        const float alpha = fminf(prod_alpha, 0.99f);
+                        const float inv = 1.0f / (1.0f - alpha);
+                        const float Tn = T * inv;
+                        aT = contributes ? alpha * Tn : 0.0f;
+                        const float a_grad = contributes ? (r2.x * Tn - w0 * inv) * g0 + (r2.y * Tn - w1 * inv) * g1 +
+                                                               (r2.z * Tn - w2 * inv) * g2
+                                                         : 0.0f;
+                        T = contributes ? Tn : T;
+                        w0 = fmaf(r2.x, aT, w0);
+                        w1 = fmaf(r2.y, aT, w1);
+                        w2 = fmaf(r2.z, aT, w2);
+                        G = a_grad * r1.z * gp;
+                    } else {
+                        // one-scalar colour recursion, see blend_bwd.cu
+                        const float P = ex2_approx_b(-0.72134752044448170368f * (d0 * q0 + d1 * q1)) * r1.y;
+                        const bool contributes = (idx < last) && (P >= 1.0f / 255.0f);
+                        const float alpha = fminf(P, 0.99f);
+                        const float inv = rcp_approx(1.0f - alpha);
+                        const float Tn = T * inv;
+                        aT = contributes ? alpha * Tn : 0.0f;
+                        const float cg = fmaf(r2.z, g2, fmaf(r2.y, g1, r2.x * g0));
+                        const float a_grad = contributes ? fmaf(cg, Tn, -(w0 * inv)) : 0.0f;
+                        T = contributes ? Tn : T;
+                        w0 = fmaf(cg, aT, w0);
+                        G = a_grad * P;
+                    }
+                    if (STATS) {
+                        mag0 += fabsf(G * q0);
+                        mag1 += fabsf(G * q1);
+                    }
+                    xg[lane * TB_ROW + i] = G;
+                    xa[lane * TB_ROW + i] = aT;
                 }
-                if (STATS) {
-                    mag0 += fabsf(G * q0);
-                    mag1 += fabsf(G * q1);
-                }
-                xg[lane * TB_ROW + i] = G;
-                xa[lane * TB_ROW + i] = aT;
-            }
-            __syncwarp();
+                __syncwarp();
 
-            // ---- phase 2: lane = splat ci of the chunk, over 16 pixels
-            const bool active = ci < n;
-            const int j2 = list[c0 + (active ? ci : 0)];
-            const float4 s0 = s_r0[j2];
-            const float4 s1 = s_r1[j2];
-            float dxs[8], dys[2];
+                // ---- phase 2: lane = splat ci of the chunk, over 16 pixels
+                const bool active = ci < n;
+                const float4 s0 = ck0[active ? ci : 0];
+                const float4 s1 = ck1[active ? ci : 0];
+                float dxs[8], dys[2];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) dxs[k] = (pxb + (float)k) - s0.x;
-            dys[0] = pyb - s0.y;
-            dys[1] = (pyb + 1.0f) - s0.y;
-            float acc[11];
+                for (int k = 0; k < 8; ++k) dxs[k] = (pxb + (float)k) - s0.x;
+                dys[0] = pyb - s0.y;
+                dys[1] = (pyb + 1.0f) - s0.y;
+                float acc[11];
 #pragma unroll
-            for (int k = 0; k < 11; ++k) acc[k] = 0.0f;
-            unsigned int nz = 0u;
+                for (int k = 0; k < 11; ++k) acc[k] = 0.0f;
+                unsigned int nz = 0u;
 #pragma unroll
-            for (int t = 0; t < 16; ++t) {
-                const int pp = t + 16 * half;  // the pixel = phase-1 lane
-                const float G = xg[pp * TB_ROW + ci], aT = xa[pp * TB_ROW + ci];
-                const float4 gp = S.g[warp][pp];
-                const float d0 = dxs[t & 7], d1 = dys[t >> 3];
-                const float q0 = s0.z * d0 + s0.w * d1;
-                const float q1 = s0.w * d0 + s1.x * d1;
-                const float vs0 = G * q0, vs1 = G * q1;
-                acc[0] += vs0;
-                acc[1] += vs1;
-                acc[2] = fmaf(vs0, q0, acc[2]);  // the 1/2 of UT:345 is applied once per point in the epilogue kernel
-                acc[3] = fmaf(vs0, q1, acc[3]);
-                acc[4] = fmaf(vs1, q1, acc[4]);
-                acc[5] = fmaf(aT, gp.x, acc[5]);
-                acc[6] = fmaf(aT, gp.y, acc[6]);
-                acc[7] = fmaf(aT, gp.z, acc[7]);
-                acc[8] += G;
-                if (STATS) {
-                    const float m2 = vs0 * vs0 + vs1 * vs1;
-                    acc[9] += EXACT_EXP ? sqrtf(m2) : sqrt_approx(m2);
-                    acc[10] += aT > 0.0f ? 1.0f : 0.0f;  // alpha >= 1/255 and T > 0: alpha*T > 0 exactly for the contributing pixels
+                for (int t = 0; t < 16; ++t) {
+                    const int pp = t + 16 * half;  // the pixel = phase-1 lane
+                    const float G = xg[pp * TB_ROW + ci], aT = xa[pp * TB_ROW + ci];
+                    const float4 gp = S.g[warp][pp];
+                    const float d0 = dxs[t & 7], d1 = dys[t >> 3];
+                    const float q0 = s0.z * d0 + s0.w * d1;
+                    const float q1 = s0.w * d0 + s1.x * d1;
+                    const float vs0 = G * q0, vs1 = G * q1;
+                    acc[0] += vs0;
+                    acc[1] += vs1;
+                    acc[2] = fmaf(vs0, q0, acc[2]);  // the 1/2 of UT:345 is applied once per point in the epilogue kernel
+                    acc[3] = fmaf(vs0, q1, acc[3]);
+                    acc[4] = fmaf(vs1, q1, acc[4]);
+                    acc[5] = fmaf(aT, gp.x, acc[5]);
+                    acc[6] = fmaf(aT, gp.y, acc[6]);
+                    acc[7] = fmaf(aT, gp.z, acc[7]);
+                    acc[8] += G;
+                    if (STATS) {
+                        const float m2 = vs0 * vs0 + vs1 * vs1;
+                        acc[9] += EXACT_EXP ? sqrtf(m2) : sqrt_approx(m2);
+                        acc[10] += aT > 0.0f ? 1.0f : 0.0f;  // alpha >= 1/255 and T > 0: alpha*T > 0 exactly for the contributing pixels
+                    }
+                    nz |= __float_as_uint(aT);
                 }
-                nz |= __float_as_uint(aT);
-            }
-            // rows 0..1 + rows 2..3 of the patch
+                // rows 0..1 + rows 2..3 of the patch
 #pragma unroll
-            for (int k = 0; k < NV; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
-            nz |= __shfl_xor_sync(0xffffffffu, nz, 16);
-            acc[8] *= EXACT_EXP ? (1.0f - s1.z) : s1.z;  // d alpha / d logit = alpha (1 - opacity)
-            __syncwarp();  // every lane has consumed its xg / xa entries: xg now takes the finished rows
-            if (lane < TB_CHUNK) {
-                S.rowoff[warp][ci] = (active && nz != 0u) ? S.off[buf][j2] : -1;
+                for (int k = 0; k < NV; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
+                nz |= __shfl_xor_sync(0xffffffffu, nz, 16);
+                acc[8] *= EXACT_EXP ? (1.0f - s1.z) : s1.z;  // d alpha / d logit = alpha (1 - opacity)
+                __syncwarp();  // every lane has consumed its xg / xa entries: xg now takes the finished rows
+                if (lane < TB_CHUNK) {
+                    if (!(active && nz != 0u)) ck_off[ci] = -1;
 #pragma unroll
-                for (int k = 0; k < NV; ++k) xg[ci * TB_TR_ROW + k] = acc[k];
-            }
-            __syncwarp();
+                    for (int k = 0; k < NV; ++k) xg[ci * TB_TR_ROW + k] = acc[k];
+                }
+                __syncwarp();
 #pragma unroll
-            for (int r = 0; r < (TB_CHUNK * GSB_ACCUM_FLOATS) / 32; ++r) {
-                const int e = r * 32 + lane;
-                const int row = e / GSB_ACCUM_FLOATS, word = e - row * GSB_ACCUM_FLOATS;
-                const int o = S.rowoff[warp][row];
-                if (word < NV && o >= 0) atomicAdd(p.accum + (size_t)o * GSB_ACCUM_FLOATS + word, xg[row * TB_TR_ROW + word]);
+                for (int r = 0; r < (TB_CHUNK * GSB_ACCUM_FLOATS) / 32; ++r) {
+                    const int e = r * 32 + lane;
+                    const int row = e / GSB_ACCUM_FLOATS, word = e - row * GSB_ACCUM_FLOATS;
+                    const int o = ck_off[row];
+                    if (word < NV && o >= 0)
+                        atomicAdd(p.accum + (size_t)o * GSB_ACCUM_FLOATS + word, xg[row * TB_TR_ROW + word]);
+                }
+                __syncwarp();  // the next chunk overwrites the chunk buffer and xg
             }
-            __syncwarp();  // the next chunk's phase 1 overwrites xg
-        }
+        } while (pos < count);
+        if (!real) break;
     }
     if (STATS) {
         p.mag_image[2 * pix] = mag0;  // GPCR:700-704
