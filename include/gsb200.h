@@ -54,7 +54,7 @@ enum {
 #define GSB_FLAG_BACKWARD_TRANSPOSED 16u /* backward only, EXPERIMENTAL (not the default, not yet timed on a B200): loop A
                                             accumulates per splat in registers after a shared-memory transposition instead
                                             of a warp butterfly per (warp, splat), see csrc/blend_bwd_transposed.cu */
-#define GSB_FLAG_NO_HOOK_STATS 32u       /* backward only, honoured by the transposed kernel: skip the statistics only a
+#define GSB_FLAG_NO_HOOK_STATS 32u       /* backward only, opt-in: skip the statistics only a
                                             backward hook reads (|d/duv| magnitude, affected-pixel count, magnitude image) --
                                             the reference's need_extra_info = False, GPCR:521, 690-704.  accum[:, 9:11] and
                                             magnitude_grad_viewspace_on_image are then left untouched (the pointer must still be valid) */

@@ -12,6 +12,7 @@ echo "== pending GPU tests"; timeout 900 python -m pytest -q -m gpu tests/test_r
 echo "== experimental backward (runxfail)"; timeout 600 python -m pytest -q -m gpu --runxfail tests/test_zzz_experimental_gpu.py 2>&1 | tail -25
 for wl in C3 C2; do
   echo "== stages $wl default"; timeout 300 python scripts/bench_stages.py $wl
+  echo "== stages $wl default kernel without hook statistics"; GSB200_SKIP_HOOK_STATS=1 timeout 300 python scripts/bench_stages.py $wl
   echo "== stages $wl transposed"; GSB200_BACKWARD_IMPL=transposed timeout 300 python scripts/bench_stages.py $wl
 done
 echo "== bench default"; timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline | tee gpurun_out/r2_bench_default.json | cut -c1-400

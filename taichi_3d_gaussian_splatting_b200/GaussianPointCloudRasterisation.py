@@ -224,6 +224,7 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
         initial_key_capacity: Optional[int] = None,
         keep_all_tile_pairs: bool = False,
         backward_impl: Optional[str] = None,
+        skip_unused_hook_statistics: Optional[bool] = None,
     ):
         """``exact_exp``: blend kernels use ``expf`` instead of ``ex2.approx`` (parity debugging).
         ``force_key64``: sort the reference's 64-bit ``tile << 32 | depth`` keys even when the live
@@ -234,7 +235,10 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
         ``backward_impl``: ``"butterfly"`` (default; ``csrc/blend_bwd.cu``) or ``"transposed"`` -- the EXPERIMENTAL
         second implementation of the blend backward (``csrc/blend_bwd_transposed.cu``; logic verified on the CPU under
         ``tests/simt``, not yet timed on a B200), which also skips the hook-only statistics when no hook is installed.
-        ``None`` reads the environment variable ``GSB200_BACKWARD_IMPL``."""
+        ``None`` reads the environment variable ``GSB200_BACKWARD_IMPL``.
+        ``skip_unused_hook_statistics``: with no backward hook installed, do not compute the statistics only a hook reads
+        (the reference's ``need_extra_info = False``, GPCR:521) in the default backward kernel either (opt-in until timed on
+        a B200; ``None`` reads ``GSB200_SKIP_HOOK_STATS``; the transposed kernel always skips them)."""
         super().__init__()
         self.config = config
         self.backward_valid_point_hook = backward_valid_point_hook
@@ -244,6 +248,9 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
         if backward_impl not in ("butterfly", "transposed"):
             raise ValueError(f"backward_impl must be 'butterfly' or 'transposed', got {backward_impl!r}")
         self.backward_impl = backward_impl
+        if skip_unused_hook_statistics is None:
+            skip_unused_hook_statistics = os.environ.get("GSB200_SKIP_HOOK_STATS", "0") not in ("", "0")
+        self.skip_unused_hook_statistics = bool(skip_unused_hook_statistics)
         self._key_capacity = int(initial_key_capacity) if initial_key_capacity else 0
         self.last_frame: Optional[Frame] = None
         self.last_gradient_buffer: Optional[torch.Tensor] = None  # flat storage behind the latest backward's grads
@@ -446,8 +453,8 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
         """Flags of the backward call for a frame rendered with ``frame_flags`` (adds the experimental kernel selection)."""
         if self.backward_impl == "transposed":
             frame_flags |= _lib.GSB_FLAG_BACKWARD_TRANSPOSED
-            if self.backward_valid_point_hook is None:  # the reference's need_extra_info = False, GPCR:521
-                frame_flags |= _lib.GSB_FLAG_NO_HOOK_STATS
+        if self.backward_valid_point_hook is None and (self.backward_impl == "transposed" or self.skip_unused_hook_statistics):
+            frame_flags |= _lib.GSB_FLAG_NO_HOOK_STATS  # the reference's need_extra_info = False, GPCR:521
         return frame_flags
 
     # ------------------------------------------------------------------ public forward (GPCR:1184-1204)

@@ -66,7 +66,10 @@ __device__ __forceinline__ bool reduce11_writer(int lane) {
 #ifndef GSB_BWD_MIN_BLOCKS
 #define GSB_BWD_MIN_BLOCKS 4
 #endif
-template <bool EXACT_EXP>
+// STATS = false (GSB_FLAG_NO_HOOK_STATS, opt-in): the |d/duv| magnitude, the affected-pixel count and the per-pixel magnitude
+// image -- read only by a backward hook, the reference's need_extra_info (GPCR:521, 690-704) -- are not computed; slots 9 and
+// 10 of the butterfly then carry zeros.
+template <bool EXACT_EXP, bool STATS = true>
 __global__ void __launch_bounds__(GSB_TILE_PIXELS, GSB_BWD_MIN_BLOCKS)
 blend_backward_kernel(const BlendBwdParams p) {
     // double-buffered staging area: [buf][plane][splat]; planes: u v a b | c rescale opacity depth | r g b radius
@@ -177,8 +180,10 @@ blend_backward_kernel(const BlendBwdParams p) {
                             w2 = fmaf(r2.z, aT, w2);
                             const float G = a_grad * opa * gp;
                             const float vs0 = G * q0, vs1 = G * q1;
-                            mag0 += fabsf(vs0);
-                            mag1 += fabsf(vs1);
+                            if (STATS) {
+                                mag0 += fabsf(vs0);
+                                mag1 += fabsf(vs1);
+                            }
                             v[0] = vs0;
                             v[1] = vs1;
                             v[2] = vs0 * q0;  // the 1/2 of UT:345 is applied once per point in the epilogue
@@ -188,7 +193,7 @@ blend_backward_kernel(const BlendBwdParams p) {
                             v[6] = aT * g1;
                             v[7] = aT * g2;
                             v[8] = a_grad * gp * (1.0f - opa) * opa;
-                            v[9] = sqrtf(vs0 * vs0 + vs1 * vs1);
+                            v[9] = STATS ? sqrtf(vs0 * vs0 + vs1 * vs1) : 0.0f;
                         } else {
                             // r1 = c | rescale*opacity | 1-opacity | depth.  The colour recursion of GPCR:653-657,
                             // sum_c (col_c T - w_c/(1-a)) g_c, is carried as ONE scalar: with cg = sum_c col_c g_c and
@@ -205,8 +210,10 @@ blend_backward_kernel(const BlendBwdParams p) {
                             w0 = fmaf(cg, aT, w0);
                             const float G = a_grad * P;  // d L / d gaussian exponent weight: a_grad * opacity * p
                             const float vs0 = G * q0, vs1 = G * q1;
-                            mag0 += fabsf(vs0);
-                            mag1 += fabsf(vs1);
+                            if (STATS) {
+                                mag0 += fabsf(vs0);
+                                mag1 += fabsf(vs1);
+                            }
                             v[0] = vs0;
                             v[1] = vs1;
                             v[2] = vs0 * q0;
@@ -216,22 +223,24 @@ blend_backward_kernel(const BlendBwdParams p) {
                             v[6] = aT * g1;
                             v[7] = aT * g2;
                             v[8] = G * r1.z;  // a_grad * p * opacity * (1 - opacity)
-                            v[9] = sqrt_approx(vs0 * vs0 + vs1 * vs1);
+                            v[9] = STATS ? sqrt_approx(vs0 * vs0 + vs1 * vs1) : 0.0f;
                         }
-                        v[10] = contributes ? 1.0f : 0.0f;
+                        v[10] = (STATS && contributes) ? 1.0f : 0.0f;
                     }
                     if (__any_sync(0xffffffffu, contributes)) {
                         // 11 partials of this (warp, splat) -> 11 lanes -> one RED.ADD.F32 row update
                         warp_transpose_reduce11(v, lane);
-                        if (red_writer)
+                        if (red_writer && (STATS || red_slot < 9))
                             atomicAdd(p.accum + (size_t)s_off[buf][j] * GSB_ACCUM_FLOATS + red_slot, v[0]);
                     }
                 }
             }
         }
     }
-    p.mag_image[2 * pix] = mag0;      // GPCR:700-704
-    p.mag_image[2 * pix + 1] = mag1;
+    if (STATS) {
+        p.mag_image[2 * pix] = mag0;  // GPCR:700-704
+        p.mag_image[2 * pix + 1] = mag1;
+    }
 }
 
 #ifndef GSB_HOST_EMU
@@ -255,10 +264,15 @@ int launch_blend_backward(const GsbBackwardArgs &a, const Workspace &ws, cudaStr
     if (a.flags & GSB_FLAG_BACKWARD_TRANSPOSED)  // experimental, see blend_bwd_transposed.cu
         return launch_blend_backward_transposed(p, tiles, (a.flags & GSB_FLAG_EXACT_EXP) != 0,
                                                 (a.flags & GSB_FLAG_NO_HOOK_STATS) == 0, stream);
-    if (a.flags & GSB_FLAG_EXACT_EXP)
+    const bool exact = (a.flags & GSB_FLAG_EXACT_EXP) != 0;
+    if (a.flags & GSB_FLAG_NO_HOOK_STATS) {  // opt-in
+        if (exact) blend_backward_kernel<true, false><<<tiles, GSB_TILE_PIXELS, 0, stream>>>(p);
+        else blend_backward_kernel<false, false><<<tiles, GSB_TILE_PIXELS, 0, stream>>>(p);
+    } else if (exact) {
         blend_backward_kernel<true><<<tiles, GSB_TILE_PIXELS, 0, stream>>>(p);
-    else
+    } else {
         blend_backward_kernel<false><<<tiles, GSB_TILE_PIXELS, 0, stream>>>(p);
+    }
     GSB_CUDA_CHECK(cudaGetLastError());
     return GSB_OK;
 }

@@ -31,8 +31,10 @@ extern "C" long long emu_blend_backward(int transposed, int exact_exp, int stats
     const int tiles = p.tiles_x * (H / GSB_TILE_HEIGHT);
     simt_emu::M().switches = 0;
     if (!transposed) {
-        if (exact_exp) simt_emu::launch(blend_backward_kernel<true>, tiles, GSB_TILE_PIXELS, p);
-        else simt_emu::launch(blend_backward_kernel<false>, tiles, GSB_TILE_PIXELS, p);
+        if (exact_exp && stats) simt_emu::launch(blend_backward_kernel<true, true>, tiles, GSB_TILE_PIXELS, p);
+        else if (exact_exp) simt_emu::launch(blend_backward_kernel<true, false>, tiles, GSB_TILE_PIXELS, p);
+        else if (stats) simt_emu::launch(blend_backward_kernel<false, true>, tiles, GSB_TILE_PIXELS, p);
+        else simt_emu::launch(blend_backward_kernel<false, false>, tiles, GSB_TILE_PIXELS, p);
     } else if (exact_exp) {
         if (stats) simt_emu::launch(blend_backward_transposed_kernel<true, true>, tiles, GSB_TILE_PIXELS, p);
         else simt_emu::launch(blend_backward_transposed_kernel<true, false>, tiles, GSB_TILE_PIXELS, p);

@@ -130,6 +130,11 @@ def test_transposed_kernel_matches_the_butterfly_kernel(emu, scene, exact):
     ok, nbad, worst = _close(lean[:, :9], got[:, :9], 1e-6, 1e-7)
     assert ok, (nbad, worst)
     assert (lean[:, 9:] == 0).all() and (lean_img == -1.0).all()
+    # the same switch in the butterfly kernel
+    lean_ref, lean_ref_img = _run(emu, fwd, rec, g, False, exact, False)
+    ok, nbad, worst = _close(lean_ref[:, :9], ref[:, :9], 1e-6, 1e-7)
+    assert ok, (nbad, worst)
+    assert (lean_ref[:, 9:] == 0).all() and (lean_ref_img == -1.0).all()
 
 
 @pytest.mark.parametrize("scene", SCENES)

@@ -145,6 +145,20 @@ def test_transposed_backward_matches_the_default_backward(scene_args, exact):
     assert grad_close(gx_c, gx_b, rtol=1e-5, floor_frac=1e-6)[0] and grad_close(gf_c, gf_b, rtol=1e-5, floor_frac=1e-6)[0]
 
 
+def test_default_backward_without_hook_statistics():
+    """GSB_FLAG_NO_HOOK_STATS in the butterfly kernel: same gradients, no statistics work."""
+    scene = make_scene(num_points=4000, height=64, width=96, sigma_med=0.05, seed=11, sh_degree=3)
+    grads = []
+    for skip in (False, True):
+        sc = cuda_scene(scene, requires_grad=True)
+        op = GPCR(Config(), skip_unused_hook_statistics=skip)
+        image, _, _ = run_forward(op, sc)
+        image.backward(torch.randn(image.shape, generator=torch.Generator().manual_seed(5)).cuda())
+        grads.append((n(sc.point_cloud.grad), n(sc.point_cloud_features.grad)))
+    assert grad_close(grads[1][0], grads[0][0], rtol=1e-5, floor_frac=1e-6)[0]
+    assert grad_close(grads[1][1], grads[0][1], rtol=1e-5, floor_frac=1e-6)[0]
+
+
 def test_transposed_backward_vs_oracle():
     scene = make_scene(num_points=4000, height=64, width=96, sigma_med=0.05, seed=11, sh_degree=3)
     o, fwd, feats_n = oracle_forward(scene)
