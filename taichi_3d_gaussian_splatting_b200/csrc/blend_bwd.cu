@@ -227,7 +227,10 @@ blend_backward_kernel(const BlendBwdParams p) {
                         }
                         v[10] = (STATS && contributes) ? 1.0f : 0.0f;
                     }
+                    if (lane == 0) GSB_EMU_COUNT(EC_BF_VISITS, 1);
+                    GSB_EMU_COUNT(EC_BF_PAIRS, contributes ? 1 : 0);
                     if (__any_sync(0xffffffffu, contributes)) {
+                        if (lane == 0) GSB_EMU_COUNT(EC_BF_VISITS_ANY, 1);
                         // 11 partials of this (warp, splat) -> 11 lanes -> one RED.ADD.F32 row update
                         warp_transpose_reduce11(v, lane);
                         if (red_writer && (STATS || red_slot < 9))

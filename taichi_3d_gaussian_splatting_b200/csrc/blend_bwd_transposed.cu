@@ -120,6 +120,7 @@ blend_backward_transposed_kernel(const BlendBwdParams p) {
                 }
             }
             __syncthreads();
+            if (tid == 0) GSB_EMU_COUNT(EC_BATCHES, 1);
             if (block_start < warp_last) {  // otherwise every splat of this batch is behind the whole patch (warp-uniform)
                 // ordered visit list of this patch: set bits of the 8 words, minus the first `skip` elements of the batch
                 // (those lie at or behind the patch's deepest effective splat)
@@ -158,6 +159,10 @@ blend_backward_transposed_kernel(const BlendBwdParams p) {
             if (have == TB_CHUNK || (!real && have > 0)) {
                 const int n = have;
                 have = 0;
+                if (lane == 0) {
+                    GSB_EMU_COUNT(EC_TB_SPLATS, n);
+                    GSB_EMU_COUNT(EC_TB_CHUNKS, 1);
+                }
                 // ---- phase 1: lane = pixel; sequential over the chunk's splats (back to front)
 #pragma unroll 2
                 for (int i = 0; i < n; ++i) {
@@ -254,6 +259,7 @@ blend_backward_transposed_kernel(const BlendBwdParams p) {
                 __syncwarp();  // every lane has consumed its xg / xa entries: xg now takes the finished rows
                 if (lane < TB_CHUNK) {
                     if (!(active && nz != 0u)) ck_off[ci] = -1;
+                    else GSB_EMU_COUNT(EC_TB_ROWS, 1);
 #pragma unroll
                     for (int k = 0; k < NV; ++k) xg[ci * TB_TR_ROW + k] = acc[k];
                 }

@@ -107,3 +107,35 @@ extern "C" long long emu_backward_points(long long N, const int *point_offset, c
     if (N > 0) simt_emu::launch(backward_points_kernel, blocks, GSB_POINTS_THREADS, p);
     return simt_emu::M().switches;
 }
+
+// Loop A of the backward on the tiles [tile_first, tile_last) only, with the work counters of blend_bwd.cuh (EmuCounter)
+// returned in counters_out[8]: lets scripts/emu_work_stats.py shard a full-size frame over processes.
+extern "C" void emu_blend_backward_stats(int transposed, int stats, int H, int W, int tile_first, int tile_last,
+                                         const int *tile_start, const int *tile_end, const int *sorted_vals,
+                                         const float *records, const float *grad_image, const float *acc_alpha,
+                                         const int *last_effective, float *accum, float *mag_image, long long *counters_out) {
+    using namespace gsb;
+    BlendBwdParams p;
+    p.H = H;
+    p.W = W;
+    p.tiles_x = W / GSB_TILE_WIDTH;
+    p.tile_start = tile_start;
+    p.tile_end = tile_end;
+    p.sorted_vals = sorted_vals;
+    p.records = reinterpret_cast<const float4 *>(records);
+    p.grad_image = grad_image;
+    p.acc_alpha = acc_alpha;
+    p.last_effective = last_effective;
+    p.accum = accum;
+    p.mag_image = mag_image;
+    const int tiles = p.tiles_x * (H / GSB_TILE_HEIGHT);
+    for (int k = 0; k < 16; ++k) simt_emu::counters()[k] = 0;
+    if (!transposed) {
+        if (stats) simt_emu::launch_range(blend_backward_kernel<false, true>, tiles, tile_first, tile_last, GSB_TILE_PIXELS, p);
+        else simt_emu::launch_range(blend_backward_kernel<false, false>, tiles, tile_first, tile_last, GSB_TILE_PIXELS, p);
+    } else {
+        if (stats) simt_emu::launch_range(blend_backward_transposed_kernel<false, true>, tiles, tile_first, tile_last, GSB_TILE_PIXELS, p);
+        else simt_emu::launch_range(blend_backward_transposed_kernel<false, false>, tiles, tile_first, tile_last, GSB_TILE_PIXELS, p);
+    }
+    for (int k = 0; k < 8; ++k) counters_out[k] = simt_emu::counters()[k];
+}

@@ -74,6 +74,10 @@ inline unsigned char *dynamic_smem() {
     alignas(16) static unsigned char buf[232448];
     return buf;
 }
+inline long long *counters() {  // work counters a kernel source may bump through GSB_EMU_COUNT (emulation only)
+    static long long c[16];
+    return c;
+}
 inline void yield() {
     Machine &m = M();
     ++m.switches;
@@ -116,9 +120,9 @@ inline int block_barrier(int pred) {
     return b.conj[g & 1];
 }
 
-// Run kernel(p) for every CTA of a 1-D grid of 1-D blocks.
+// Run kernel(p) for the CTAs [first, last) of a 1-D grid of `grid` 1-D blocks (launch(): all of them).
 template <class Kernel, class Params>
-void launch(Kernel kernel, int grid, int block, const Params &p) {
+void launch_range(Kernel kernel, int grid, int first, int last, int block, const Params &p) {
     Machine &m = M();
     assert(block % 32 == 0 && block <= 1024);
     m.nthreads = block;
@@ -128,7 +132,7 @@ void launch(Kernel kernel, int grid, int block, const Params &p) {
     for (auto &f : m.fibers)
         if (f.stack.empty()) f.stack.resize(256 * 1024);
     m.body = [&]() { kernel(p); };
-    for (int b = 0; b < grid; ++b) {
+    for (int b = first; b < last; ++b) {
         m.bid.x = b;
         for (auto &w : m.warps) w = WarpState();
         m.block = BlockState();
@@ -156,6 +160,11 @@ void launch(Kernel kernel, int grid, int block, const Params &p) {
             assert(progressed > 0);
         }
     }
+}
+
+template <class Kernel, class Params>
+void launch(Kernel kernel, int grid, int block, const Params &p) {
+    launch_range(kernel, grid, 0, grid, block, p);
 }
 
 }  // namespace simt_emu
