@@ -47,8 +47,11 @@ extern __shared__ __align__(16) unsigned char gsb_tb_dynamic_smem[];
 __device__ __forceinline__ unsigned char *tb_dynamic_smem() { return gsb_tb_dynamic_smem; }
 #endif
 
+#ifndef GSB_TB_MIN_BLOCKS
+#define GSB_TB_MIN_BLOCKS 3  // 73.5 KB of shared memory per CTA allow 3; tuning knob (GSB200_DEFINES="-DGSB_TB_MIN_BLOCKS=2")
+#endif
 template <bool EXACT_EXP, bool STATS>
-__global__ void __launch_bounds__(GSB_TILE_PIXELS, 3)
+__global__ void __launch_bounds__(GSB_TILE_PIXELS, GSB_TB_MIN_BLOCKS)
 blend_backward_transposed_kernel(const BlendBwdParams p) {
     TbShared &S = *reinterpret_cast<TbShared *>(tb_dynamic_smem());
     constexpr int NV = STATS ? 11 : 9;
