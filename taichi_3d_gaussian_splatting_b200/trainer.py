@@ -98,6 +98,7 @@ class GaussianPointCloudTrainer:
                                      backward_valid_point_hook=self.adaptive_controller.update)
         self.loss_function = LossFunction(config=config.loss_function_config)
         self.history: List[dict] = []
+        self._downsampled = {}
 
     def _input(self, q, t, camera_info, band):
         s = self.scene
@@ -121,9 +122,15 @@ class GaussianPointCloudTrainer:
                 downsample_factor //= 2
             optimizer.zero_grad()
             position_optimizer.zero_grad()
-            image_gt, q, t, camera_info = self.train_views[iteration % len(self.train_views)]
+            view_index = iteration % len(self.train_views)
+            image_gt, q, t, camera_info = self.train_views[view_index]
             if downsample_factor > 1:
-                image_gt, camera_info = downsample_image_and_camera_info(image_gt, camera_info, downsample_factor)
+                # the reference resizes the full-resolution frame in every iteration (GaussianPointTrainer.py:146-148); the
+                # result depends only on (view, factor), so it is computed once per pair (same tensors, ~10 launches less)
+                key = (view_index, downsample_factor)
+                if key not in self._downsampled:
+                    self._downsampled[key] = downsample_image_and_camera_info(image_gt, camera_info, downsample_factor)
+                image_gt, camera_info = self._downsampled[key]
             band = iteration // cfg.increase_color_max_sh_band_interval
             image_pred, _, _ = self.rasterisation(self._input(q, t, camera_info, band))
             if self.fused_image_loss:
