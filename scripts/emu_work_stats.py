@@ -46,7 +46,7 @@ STATE = None
 
 def _work(args):
     transposed, tiles = args
-    from test_simt_preprocess_cpu import build_emulator
+    from simt_helpers import build_emulator
     emu = build_emulator()
     s = STATE
     c = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
@@ -66,7 +66,7 @@ def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "C3"
     sample = int(sys.argv[2]) if len(sys.argv) > 2 else 400
     procs = int(sys.argv[3]) if len(sys.argv) > 3 else 6
-    from test_simt_preprocess_cpu import build_emulator
+    from simt_helpers import build_emulator
     build_emulator()
     STATE = _state(name)
     T = STATE["start"].shape[0]

@@ -2,11 +2,78 @@
 chained exactly as ``csrc/api.cu`` chains them -- preprocess -> radix sort -> tile ranges -> forward blend -> loop A of
 the backward -> per-point chain rule -- through the library's own buffers.  Test infrastructure."""
 import ctypes
+import os
+import subprocess
 from types import SimpleNamespace
 
 import numpy as np
 
-from test_simt_preprocess_cpu import _run as run_preprocess
+HERE = os.path.dirname(os.path.abspath(__file__))
+SIMT = os.path.join(HERE, "simt")
+CSRC = os.path.join(os.path.dirname(HERE), "taichi_3d_gaussian_splatting_b200", "csrc")
+
+
+def build_emulator():
+    out = os.path.join(SIMT, "libsimt_emu.so")
+    tus = [os.path.join(SIMT, f) for f in ("emu_blend.cpp", "emu_preprocess.cpp", "emu_sort.cpp", "emu_image_loss.cpp", "emu_adam.cpp", "emu_controller.cpp")]
+    deps = tus + [os.path.join(SIMT, "simt_emu.h")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(s) for s in deps):
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", cuda_inc, "-o", out, *tus],
+                       check=True)
+    L = ctypes.CDLL(out)
+    L.emu_blend_backward.restype = ctypes.c_longlong
+    L.emu_blend_forward.restype = ctypes.c_longlong
+    L.emu_preprocess.restype = ctypes.c_longlong
+    L.emu_backward_points.restype = ctypes.c_longlong
+    L.emu_sort_pairs.restype = ctypes.c_longlong
+    L.emu_image_loss.restype = ctypes.c_longlong
+    L.emu_image_loss_temp_bytes.restype = ctypes.c_longlong
+    return L
+
+
+
+def _bit_width(v):
+    return int(v).bit_length()
+
+
+def run_preprocess(emu, scene, fwd_cfg, key64, filter_tiles):
+    """The fused per-point stage (csrc/preprocess.cu) under the emulator on a scene of CPU tensors; returns its raw buffers."""
+    xyz = scene.point_cloud.numpy().astype(np.float32).copy()
+    feats = scene.point_cloud_features.detach().numpy().astype(np.float32).copy()
+    N = xyz.shape[0]
+    ci = scene.camera_info
+    H, W = ci.camera_height, ci.camera_width
+    far, scale, near = fwd_cfg.get("far_plane", 1000.0), fwd_cfg.get("depth_to_sort_key_scale", 100.0), fwd_cfg.get("near_plane", 0.8)
+    T = (H // 16) * (W // 16)
+    tile_bits = _bit_width(max(T - 1, 0))
+    mk = np.float32(far) * np.float32(scale)
+    depth_bits = max(_bit_width(int(mk)), 1)  # csrc/api.cu compute_layout
+    if key64 or tile_bits + depth_bits > 32:
+        key_bytes, depth_bits = 8, 32
+    else:
+        key_bytes = 4
+    cap = 64 * N + 4096
+    counters = np.zeros(8, np.int64)
+    point_id, point_offset, num_tiles = (np.full(N, -9, np.int32) for _ in range(3))
+    records, pic = np.zeros((N, 12), np.float32), np.zeros((N, 3), np.float32)
+    keys = np.zeros(cap, np.uint32 if key_bytes == 4 else np.uint64)
+    vals = np.zeros(cap, np.int32)
+    c = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    q = scene.q_pointcloud_camera.numpy().astype(np.float32).copy()
+    t = scene.t_pointcloud_camera.numpy().astype(np.float32).copy()
+    K = ci.camera_intrinsics.numpy().astype(np.float32).copy()
+    inv = scene.point_invalid_mask.numpy().astype(np.int8).copy()
+    obj = scene.point_object_id.numpy().astype(np.int32).copy()
+    sw = emu.emu_preprocess(
+        ctypes.c_longlong(N), c(xyz), c(feats), c(inv), c(obj), q.shape[0], c(q), c(t), c(K), W, H, ctypes.c_float(near),
+        ctypes.c_float(far), ctypes.c_float(scale), depth_bits, key_bytes, int(filter_tiles), 0, ctypes.c_longlong(cap),
+        c(counters), c(point_id), c(point_offset), c(num_tiles), c(records), c(pic), c(keys), c(vals))
+    assert sw > 0
+    return SimpleNamespace(feats=feats, counters=counters, point_id=point_id, point_offset=point_offset, num_tiles=num_tiles,
+                           records=records, pic=pic, keys=keys, vals=vals, depth_bits=depth_bits, tile_bits=tile_bits, H=H, W=W, T=T)
+
+
 
 
 def c(a):
@@ -98,7 +165,6 @@ class EmulatedCudaRasterisationModule:
         import torch
 
         from taichi_3d_gaussian_splatting_b200 import GaussianPointCloudRasterisation as GPCR
-        from test_simt_preprocess_cpu import build_emulator
         self.config, self.hook = config, backward_valid_point_hook
         emu = build_emulator()
         outer = self

@@ -18,7 +18,7 @@ import pytest
 from helpers import oracle_forward
 from oracle.gs_oracle import lib as oracle_lib, _p
 from taichi_3d_gaussian_splatting_b200.synthetic import make_scene
-from test_simt_preprocess_cpu import build_emulator
+from simt_helpers import build_emulator
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SIMT = os.path.join(HERE, "simt")

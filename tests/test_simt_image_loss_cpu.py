@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from taichi_3d_gaussian_splatting_b200.loss import LossFunction
-from test_simt_preprocess_cpu import build_emulator
+from simt_helpers import build_emulator
 
 
 @pytest.fixture(scope="module")

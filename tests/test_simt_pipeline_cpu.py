@@ -13,7 +13,8 @@ import pytest
 from helpers import grad_close, oracle_backward, oracle_forward
 from taichi_3d_gaussian_splatting_b200.synthetic import make_scene
 from simt_helpers import c, emu_sort, emulated_operator
-from test_simt_preprocess_cpu import _large_splats, build_emulator
+from simt_helpers import build_emulator
+from test_simt_preprocess_cpu import _large_splats
 
 
 @pytest.fixture(scope="module")
