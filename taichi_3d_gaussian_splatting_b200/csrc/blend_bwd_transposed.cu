@@ -14,7 +14,7 @@
 //     every lane re-derives d and conic*d for its splat, accumulates the 11 partials over its 16 pixels in registers,
 //     the two halves are added with one shuffle per value, and the 16 finished rows leave through shared memory as
 //     6 row-contiguous RED.ADD.F32 instructions (same 2 sectors per (warp, splat) as the butterfly kernel).
-// Per 32 (pixel, splat) pairs that is ~37 (phase 1) + ~36 (chunk fill, phase 2, epilogue) SASS instructions.
+// Per 32 (pixel, splat) pairs that is ~36 (phase 1) + ~36 (chunk fill, phase 2, epilogue) SASS instructions.
 // STATS = false (GSB_FLAG_NO_HOOK_STATS, the reference's need_extra_info = False, GPCR:521, 690-704) drops the |d/duv|
 // magnitude, the affected-pixel count and the per-pixel magnitude image.
 #include "blend_bwd.cuh"
@@ -25,14 +25,14 @@ constexpr int TB_CHUNK = 16;          // splats per chunk
 constexpr int TB_ROW = TB_CHUNK + 1;  // row stride (floats) of the (pixel, splat) exchange buffers
 constexpr int TB_TR_ROW = 13;         // row stride of the finished rows (12 accumulator words, odd stride)
 
-struct TbShared {  // dynamic shared memory image, 73.5 KB -> 3 CTAs per SM
+struct TbShared {  // dynamic shared memory image, 73 KB -> 3 CTAs per SM
     float4 rec[2 * 3 * GSB_TILE_PIXELS];  // [buf][plane][splat] as in blend_bwd.cu
     float4 g[8][32];                      // dL/dimage of the warp's pixels
     float xg[8][32 * TB_ROW];             // G  per (pixel, splat of the chunk); reused for the finished rows
     float xa[8][32 * TB_ROW];             // alpha * T
     int off[2][GSB_TILE_PIXELS];          // in-camera offset of the staged splats
-    float4 chunk[8][3][TB_CHUNK];         // per warp: records of the current chunk's splats [plane][slot]
-    int chunk_idx[8][TB_CHUNK];           //   their position in the tile's sorted list
+    float4 chunk[8][3][TB_CHUNK];         // per warp: records of the current chunk's splats [plane][slot]; the unused
+                                          //   radius word of plane 2 carries the splat's position in the tile's sorted list
     int chunk_off[8][TB_CHUNK];           //   their accumulator row (set to -1 after phase 2 if nothing is to be added)
     unsigned int bits[2][8][8];           // [buf][consumer warp patch][loader warp]
     unsigned char list[8][GSB_TILE_PIXELS];  // per warp: elements of the current batch to visit, back to front
@@ -48,7 +48,7 @@ __device__ __forceinline__ unsigned char *tb_dynamic_smem() { return gsb_tb_dyna
 #endif
 
 #ifndef GSB_TB_MIN_BLOCKS
-#define GSB_TB_MIN_BLOCKS 3  // 73.5 KB of shared memory per CTA allow 3; tuning knob (GSB200_DEFINES="-DGSB_TB_MIN_BLOCKS=2")
+#define GSB_TB_MIN_BLOCKS 3  // 73 KB of shared memory per CTA allow 3; tuning knob (GSB200_DEFINES="-DGSB_TB_MIN_BLOCKS=2")
 #endif
 template <bool EXACT_EXP, bool STATS>
 __global__ void __launch_bounds__(GSB_TILE_PIXELS, GSB_TB_MIN_BLOCKS)
@@ -90,7 +90,7 @@ blend_backward_transposed_kernel(const BlendBwdParams p) {
     const int end = min(p.tile_end[tile], S.max_last);
 
     float4 *const ck0 = S.chunk[warp][0], *const ck1 = S.chunk[warp][1], *const ck2 = S.chunk[warp][2];
-    int *const ck_idx = S.chunk_idx[warp], *const ck_off = S.chunk_off[warp];
+    int *const ck_off = S.chunk_off[warp];
     int have = 0;  // splats waiting in the chunk buffer (warp-uniform)
 
     // One barrier per staging batch (double-buffered, see blend_fwd.cu).  After the last batch one more trip through the
@@ -151,8 +151,9 @@ blend_backward_transposed_kernel(const BlendBwdParams p) {
                     const int j = list[pos + lane], slot = have + lane;
                     ck0[slot] = s_r0[j];
                     ck1[slot] = s_r1[j];
-                    ck2[slot] = s_r2[j];
-                    ck_idx[slot] = block_end - 1 - j;
+                    float4 r2 = s_r2[j];
+                    r2.w = __int_as_float(block_end - 1 - j);  // sorted index instead of the radius (unused here)
+                    ck2[slot] = r2;
                     ck_off[slot] = S.off[buf][j];
                 }
                 have += take;
@@ -169,10 +170,10 @@ blend_backward_transposed_kernel(const BlendBwdParams p) {
                 // ---- phase 1: lane = pixel; sequential over the chunk's splats (back to front)
 #pragma unroll 2
                 for (int i = 0; i < n; ++i) {
-                    const int idx = ck_idx[i];
                     const float4 r0 = ck0[i];  // u v a b
                     const float4 r1 = ck1[i];  // c rescale opacity depth   (fast path: c rescale*opacity 1-opacity depth)
-                    const float4 r2 = ck2[i];  // r g b radius
+                    const float4 r2 = ck2[i];  // r g b | sorted index
+                    const int idx = __float_as_int(r2.w);
                     const float d0 = px - r0.x, d1 = py - r0.y;
                     const float q0 = r0.z * d0 + r0.w * d1;
                     const float q1 = r0.w * d0 + r1.x * d1;

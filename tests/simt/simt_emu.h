@@ -275,4 +275,14 @@ inline unsigned int __float_as_uint(float f) {
     std::memcpy(&u, &f, 4);
     return u;
 }
+inline float __int_as_float(int i) {
+    float f;
+    std::memcpy(&f, &i, 4);
+    return f;
+}
+inline int __float_as_int(float f) {
+    int i;
+    std::memcpy(&i, &f, 4);
+    return i;
+}
 inline float __logf(float x) { return logf(x); }
