@@ -44,6 +44,22 @@ def _state(name):
 STATE = None
 
 
+def _work_forward(tiles):
+    from simt_helpers import build_emulator
+    emu = build_emulator()
+    s = STATE
+    c = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    H, W = s["H"], s["W"]
+    image, depth, acc = np.zeros((H, W, 3), np.float32), np.zeros((H, W), np.float32), np.zeros((H, W), np.float32)
+    last, cnt = np.zeros((H, W), np.int32), np.zeros((H, W), np.int32)
+    total, out = np.zeros(16, np.int64), np.zeros(16, np.int64)
+    for t in tiles:
+        emu.emu_blend_forward_stats(H, W, int(t), int(t) + 1, c(s["start"]), c(s["end"]), c(s["vals"]), c(s["rec"]), c(image),
+                                    c(depth), c(acc), c(last), c(cnt), c(out))
+        total += out
+    return total
+
+
 def _work(args):
     transposed, tiles = args
     from simt_helpers import build_emulator
@@ -78,6 +94,8 @@ def main():
     tot = {0: np.zeros(8, np.int64), 1: np.zeros(8, np.int64)}
     for tr, c in res:
         tot[tr] += c
+    with Pool(procs) as pool:
+        fw = sum(pool.map(_work_forward, [tiles[k::procs] for k in range(procs)]))
     bf, tb = tot[0], tot[1]
     # SASS instruction counts (cuobjdump, fast path without hook statistics)
     BF_VISIT_ANY, BF_VISIT_NONE = 107, 55      # butterfly kernel per (warp, splat) visit: with / without the butterfly + RED
@@ -89,6 +107,8 @@ def main():
         "butterfly": {"visits": int(bf[0]), "visits_with_a_contributing_pixel": int(bf[1]), "contributing_pairs": int(bf[2]),
                       "contributing_lanes_per_visit": round(float(bf[2]) / max(int(bf[0]), 1), 2),
                       "visits_per_list_entry": round(float(bf[0]) / max(pairs_sampled, 1), 3)},
+        "forward": {"visits": int(fw[7]), "pairs_with_alpha_above_cutoff_on_live_pixels": int(fw[8]),
+                    "evaluated_pixel_splat_pairs": int(fw[7]) * 32, "scale_to_frame": round(float(T) / tiles.shape[0], 2)},
         "transposed": {"splat_visits": int(tb[3]), "chunks": int(tb[4]), "mean_chunk_fill": round(float(tb[3]) / max(int(tb[4]), 1), 2),
                        "rows_flushed": int(tb[5]), "staging_batches": int(tb[6])},
         "estimated_warp_instructions_in_the_visit_loops": {"butterfly": int(est_bf), "transposed": int(est_tb),

@@ -102,6 +102,7 @@ blend_forward_kernel(const BlendFwdParams p) {
             while (bits) {
                 const int j = lw * 32 + __ffs(bits) - 1;
                 bits &= bits - 1;
+                if (lane == 0) GSB_EMU_COUNT(EC_FW_VISITS, 1);
                 const unsigned int ja = sb + j * 16;
                 const float4 r0 = lds128<0>(ja);      // u v a b      (fast: u v A B)
                 const float4 r1 = lds128<PLANE>(ja);  // c rescale opacity depth (fast: C ro - depth)
@@ -114,6 +115,7 @@ blend_forward_kernel(const BlendFwdParams p) {
                     alpha = ex2_approx(dx * (r0.z * dx + r0.w * dy) + r1.x * dy * dy) * r1.y;
                 }
                 if (!(alpha < 1.0f / 255.0f)) {             // GPCR:451 (same comparison as the reference)
+                    GSB_EMU_COUNT(EC_FW_PAIRS, 1);
                     alpha = fminf(alpha, 0.99f);            // GPCR:453
                     const float nT = T * (1.0f - alpha);
                     if (nT >= 0.0001f) {

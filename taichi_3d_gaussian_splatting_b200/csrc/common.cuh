@@ -195,6 +195,24 @@ __device__ __forceinline__ unsigned int splat_patch_mask(float u, float v, float
 }
 #endif
 
+// Work counters for the CPU-side emulation only (tests/simt, scripts/emu_work_stats.py); nothing in a device build.
+#ifdef GSB_HOST_EMU
+#define GSB_EMU_COUNT(slot, n) (simt_emu::counters()[slot] += (long long)(n))
+#else
+#define GSB_EMU_COUNT(slot, n) ((void)0)
+#endif
+enum EmuCounter {
+    EC_BF_VISITS = 0,       // butterfly kernel: (warp, splat) visits
+    EC_BF_VISITS_ANY = 1,   //   ... with at least one contributing pixel (these pay the butterfly + RED)
+    EC_BF_PAIRS = 2,        //   contributing (pixel, splat) pairs
+    EC_TB_SPLATS = 3,       // transposed kernel: (warp, splat) list entries
+    EC_TB_CHUNKS = 4,       //   chunks processed
+    EC_TB_ROWS = 5,         //   accumulator rows flushed (splats with a contributing pixel)
+    EC_BATCHES = 6,         // staging batches (per CTA)
+    EC_FW_VISITS = 7,       // forward blend: (warp, splat) visits
+    EC_FW_PAIRS = 8,        //   (pixel, splat) pairs with alpha >= 1/255 on a live pixel (blended or saturating)
+};
+
 static inline int num_sms() {
     static int n = 0;
     if (n == 0) {

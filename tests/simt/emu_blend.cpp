@@ -139,3 +139,27 @@ extern "C" void emu_blend_backward_stats(int transposed, int stats, int H, int W
     }
     for (int k = 0; k < 8; ++k) counters_out[k] = simt_emu::counters()[k];
 }
+
+// The forward blend on the tiles [tile_first, tile_last) only, with the work counters (EmuCounter) in counters_out[16].
+extern "C" void emu_blend_forward_stats(int H, int W, int tile_first, int tile_last, const int *tile_start, const int *tile_end,
+                                        const int *sorted_vals, const float *records, float *image, float *depth,
+                                        float *acc_alpha, int *last_effective, int *valid_count, long long *counters_out) {
+    using namespace gsb;
+    BlendFwdParams p;
+    p.H = H;
+    p.W = W;
+    p.tiles_x = W / GSB_TILE_WIDTH;
+    p.tile_start = tile_start;
+    p.tile_end = tile_end;
+    p.sorted_vals = sorted_vals;
+    p.records = reinterpret_cast<const float4 *>(records);
+    p.image = image;
+    p.depth = depth;
+    p.acc_alpha = acc_alpha;
+    p.last_effective = last_effective;
+    p.valid_count = valid_count;
+    const int tiles = p.tiles_x * (H / GSB_TILE_HEIGHT);
+    for (int k = 0; k < 16; ++k) simt_emu::counters()[k] = 0;
+    simt_emu::launch_range(blend_forward_kernel<false, false>, tiles, tile_first, tile_last, GSB_TILE_PIXELS, p);
+    for (int k = 0; k < 16; ++k) counters_out[k] = simt_emu::counters()[k];
+}
