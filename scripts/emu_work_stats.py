@@ -99,7 +99,7 @@ def main():
     bf, tb = tot[0], tot[1]
     # SASS instruction counts (cuobjdump, fast path without hook statistics)
     BF_VISIT_ANY, BF_VISIT_NONE = 107, 55      # butterfly kernel per (warp, splat) visit: with / without the butterfly + RED
-    TB_PHASE1, TB_CHUNK = 36, 569              # transposed kernel: per splat (phase 1), per chunk (fill + phase 2 + epilogue)
+    TB_PHASE1, TB_CHUNK = 36, 548              # transposed kernel: per splat (phase 1), per chunk (fill + phase 2 + epilogue)
     est_bf = BF_VISIT_ANY * bf[1] + BF_VISIT_NONE * (bf[0] - bf[1])
     est_tb = TB_PHASE1 * tb[3] + TB_CHUNK * tb[4]
     print(json.dumps({

@@ -13,7 +13,7 @@
 //   phase 2 (lane = splat; lanes 0..15 take pixels 0..15 of the patch, lanes 16..31 the same splats for pixels 16..31):
 //     every lane re-derives d and conic*d for its splat, accumulates the 11 partials over its 16 pixels in registers,
 //     the two halves are added with one shuffle per value, and the 16 finished rows leave through shared memory as
-//     6 row-contiguous RED.ADD.F32 instructions (same 2 sectors per (warp, splat) as the butterfly kernel).
+//     8 RED.ADD.F32 instructions of two contiguous rows each (same 2 sectors per (warp, splat) as the butterfly kernel).
 // Per 32 (pixel, splat) pairs that is ~36 (phase 1) + ~36 (chunk fill, phase 2, epilogue) SASS instructions.
 // STATS = false (GSB_FLAG_NO_HOOK_STATS, the reference's need_extra_info = False, GPCR:521, 690-704) drops the |d/duv|
 // magnitude, the affected-pixel count and the per-pixel magnitude image.
@@ -78,6 +78,12 @@ blend_backward_transposed_kernel(const BlendBwdParams p) {
     const float pxb = tile_x0 + (float)((warp & 1) * 8) + 0.5f;
     const float pyb = tile_y0 + (float)((warp >> 1) * 4 + 2 * half) + 0.5f;
     float *const xg = S.xg[warp], *const xa = S.xa[warp];
+    // flush role of this lane: word fl_word of the even (lanes 0..11) or odd (lanes 12..23) row of a row pair
+    const int fl_row = lane >= GSB_ACCUM_FLOATS ? 1 : 0;
+    const int fl_word = lane - GSB_ACCUM_FLOATS * fl_row;
+    const bool fl_ok = lane < 2 * GSB_ACCUM_FLOATS && fl_word < NV;
+    const int *const fl_off = S.chunk_off[warp] + fl_row;
+    const float *const fl_val = xg + fl_row * TB_TR_ROW + (fl_ok ? fl_word : 0);
     unsigned char *const list = S.list[warp];
 
     int warp_last = last;
@@ -268,13 +274,12 @@ blend_backward_transposed_kernel(const BlendBwdParams p) {
                     for (int k = 0; k < NV; ++k) xg[ci * TB_TR_ROW + k] = acc[k];
                 }
                 __syncwarp();
+                // two rows per step: lanes 0..11 the words of row 2s, lanes 12..23 those of row 2s+1 (no index division)
 #pragma unroll
-                for (int r = 0; r < (TB_CHUNK * GSB_ACCUM_FLOATS) / 32; ++r) {
-                    const int e = r * 32 + lane;
-                    const int row = e / GSB_ACCUM_FLOATS, word = e - row * GSB_ACCUM_FLOATS;
-                    const int o = ck_off[row];
-                    if (word < NV && o >= 0)
-                        atomicAdd(p.accum + (size_t)o * GSB_ACCUM_FLOATS + word, xg[row * TB_TR_ROW + word]);
+                for (int step = 0; step < TB_CHUNK / 2; ++step) {
+                    const int o = fl_off[2 * step];
+                    const float v = fl_val[2 * step * TB_TR_ROW];
+                    if (fl_ok && o >= 0) atomicAdd(p.accum + (size_t)o * GSB_ACCUM_FLOATS + fl_word, v);
                 }
                 __syncwarp();  // the next chunk overwrites the chunk buffer and xg
             }
