@@ -97,7 +97,7 @@ def main():
     todo = dict(scenes())
     if with_c1:
         todo["C1_baseline_config_1"] = baseline_config_1()
-    with_c2r = "--with-c2r" in sys.argv  # reduced BASELINE config 2: about an hour in the interpreter, sampled output
+    with_c2r = "--with-c2r" in sys.argv  # reduced BASELINE config 2: more than two and a half hours in the interpreter (1.2e8 pixel x splat iterations), sampled output
     if with_c2r:
         todo = {"C2R_reduced_config_2": reduced_config_2()} if "--only-c2r" in sys.argv else {**todo, "C2R_reduced_config_2": reduced_config_2()}
     out = {}

@@ -229,7 +229,7 @@ def test_cuda_operator_reproduces_the_reference_kernels_at_baseline_config_1():
 
 
 # ---------------------------------------------------------------- reduced BASELINE config 2 through the reference's kernels
-# reference_path_c2_reduced.npz (generator option --with-c2r, about an hour in the interpreter): 4.3e4 Gaussians at
+# reference_path_c2_reduced.npz (generator option --with-c2r, more than two and a half hours in the interpreter): 4.3e4 Gaussians at
 # 976 x 544 = 2074 tiles with C2's splat density per tile.  Everything that must be bit-equal is stored as a SHA-256,
 # images and gradients as samples (6000 pixels, per-tile sums, 1500 in-frustum rows, global L1 norms).
 def _c2r():
