@@ -308,7 +308,8 @@ def test_cuda_operator_reproduces_the_reference_kernels_at_reduced_config_2():
     assert np.array_equal(digest(keys64), ref.sha256_stage_point_in_camera_sort_key)
     h, w = count.shape
     pix = ref.pixel_index
-    assert np.abs(n(image).reshape(h * w, 3)[pix] - ref.pixel_image).max() <= 1e-4
+    d_pix = np.abs(n(image).reshape(h * w, 3)[pix] - ref.pixel_image)
+    assert (d_pix > 1e-4).sum() <= 3 and d_pix.max() <= 5e-3  # cut-off flips, see the tile sums below
     assert (n(count).reshape(h * w, 1)[pix] != ref.pixel_count).sum() <= 3
     tiles = n(image).reshape(h // 16, 16, w // 16, 16, 3).astype(np.float64).sum(axis=(1, 3))
     # 1.2e8 (pixel, splat) evaluations with CUDA's expf against the reference's correctly rounded exp: a handful of pairs within
