@@ -118,15 +118,16 @@ def test_oracle_reproduces_the_reference_kernels(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("exact_exp", [True, False], ids=["exact_exp", "default_fast_path"])
 @pytest.mark.parametrize("name", list(SCENES))
-def test_cuda_operator_reproduces_the_reference_kernels(name):
+def test_cuda_operator_reproduces_the_reference_kernels(name, exact_exp):
     from gpu_helpers import make_op, n, run_forward
     sc, ref = SCENES[name], _golden(name)
     scene = _as_scene(sc, "cuda")
     scene.point_cloud.requires_grad_(True)
     scene.point_cloud_features.requires_grad_(True)
     hook = {}
-    op = make_op(hook=lambda h: hook.update(h=h), exact_exp=True, near_plane=sc["near_plane"], far_plane=sc["far_plane"],
+    op = make_op(hook=lambda h: hook.update(h=h), exact_exp=exact_exp, near_plane=sc["near_plane"], far_plane=sc["far_plane"],
                  depth_to_sort_key_scale=sc["depth_to_sort_key_scale"])
     image, depth, count = run_forward(op, scene, band=sc["color_max_sh_band"])
     assert np.abs(n(image) - ref.image).max() <= 1e-4
@@ -199,14 +200,15 @@ def test_oracle_reproduces_the_reference_kernels_at_baseline_config_1():
 
 
 @pytest.mark.gpu
-def test_cuda_operator_reproduces_the_reference_kernels_at_baseline_config_1():
+@pytest.mark.parametrize("exact_exp", [True, False], ids=["exact_exp", "default_fast_path"])
+def test_cuda_operator_reproduces_the_reference_kernels_at_baseline_config_1(exact_exp):
     from gpu_helpers import make_op, n, run_forward
     sc, ref = _c1()
     scene = _as_scene(sc, "cuda")
     scene.point_cloud.requires_grad_(True)
     scene.point_cloud_features.requires_grad_(True)
     hook = {}
-    op = make_op(hook=lambda h: hook.update(h=h), exact_exp=True)
+    op = make_op(hook=lambda h: hook.update(h=h), exact_exp=exact_exp)
     image, depth, count = run_forward(op, scene, band=0)
     assert np.abs(n(image) - ref.image).max() <= 1e-4
     assert np.abs(n(depth) - ref.depth).max() <= 1e-3
@@ -281,14 +283,15 @@ def test_oracle_reproduces_the_reference_kernels_at_reduced_config_2():
 
 
 @pytest.mark.gpu
-def test_cuda_operator_reproduces_the_reference_kernels_at_reduced_config_2():
+@pytest.mark.parametrize("exact_exp", [True, False], ids=["exact_exp", "default_fast_path"])
+def test_cuda_operator_reproduces_the_reference_kernels_at_reduced_config_2(exact_exp):
     from gpu_helpers import make_op, n, run_forward
     sc, ref, digest = _c2r()
     scene = _as_scene(sc, "cuda")
     scene.point_cloud.requires_grad_(True)
     scene.point_cloud_features.requires_grad_(True)
     hook = {}
-    op = make_op(hook=lambda h: hook.update(h=h), exact_exp=True, keep_all_tile_pairs=True)
+    op = make_op(hook=lambda h: hook.update(h=h), exact_exp=exact_exp, keep_all_tile_pairs=True)
     image, depth, count = run_forward(op, scene, band=3)
     frame = op.last_frame
     assert (frame.num_points_in_camera, frame.num_keys) == tuple(ref.sizes[:2])
