@@ -7,7 +7,8 @@ from taichi_3d_gaussian_splatting_b200.synthetic import CONFIGS, make_scene
 name = sys.argv[1] if len(sys.argv) > 1 else "C3"
 cfg = CONFIGS[name]
 scene = make_scene(**cfg).to("cuda")
-op = GPCR(GPCR.GaussianPointCloudRasterisationConfig(), keep_all_tile_pairs=bool(int(os.environ.get('GSB_KEEP_ALL', '0'))))
+op = GPCR(GPCR.GaussianPointCloudRasterisationConfig(), keep_all_tile_pairs=bool(int(os.environ.get('GSB_KEEP_ALL', '0'))),
+          backward_impl=os.environ.get('GSB_BENCH_BACKWARD_IMPL') or None)
 inp = GPCR.GaussianPointCloudRasterisationInput(
     point_cloud=scene.point_cloud, point_cloud_features=scene.point_cloud_features,
     point_object_id=scene.point_object_id, point_invalid_mask=scene.point_invalid_mask,

@@ -21,6 +21,7 @@ renders zeros, and with ``rgb_only=True`` the auxiliary outputs are zeros.
 """
 import ctypes
 import os
+import threading
 from dataclasses import dataclass
 from typing import Callable, Optional
 
@@ -56,13 +57,15 @@ def _require(t: torch.Tensor, name: str, dtype: torch.dtype, shape_tail=None) ->
 class _PinnedCounters:
     """Per-device pool of (pinned int64[4] read-back buffer, CUDA event) pairs, one per frame in flight."""
     _free = {}
+    _lock = threading.Lock()  # operators of several threads (one per stream) share the pool
 
     @classmethod
     def acquire(cls, device: torch.device):
         key = device.index if device.index is not None else torch.cuda.current_device()
-        pool = cls._free.setdefault(key, [])
-        if pool:
-            return pool.pop()
+        with cls._lock:
+            pool = cls._free.setdefault(key, [])
+            if pool:
+                return pool.pop()
         event = torch.cuda.Event()
         event.record()  # materialises the underlying cudaEvent_t so that its handle can cross the C ABI
         return torch.zeros(4, dtype=torch.int64).pin_memory(), event
@@ -70,7 +73,8 @@ class _PinnedCounters:
     @classmethod
     def release(cls, device: torch.device, item) -> None:
         key = device.index if device.index is not None else torch.cuda.current_device()
-        cls._free.setdefault(key, []).append(item)
+        with cls._lock:
+            cls._free.setdefault(key, []).append(item)
 
 
 class Frame:
@@ -232,19 +236,19 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
         the buffers grow automatically when a frame needs more.  ``keep_all_tile_pairs``: emit a sort key for
         every tile of the reference's 3-sigma square instead of only the tiles the splat can actually reach with
         alpha >= 1/255 (same outputs, ~1.5x more keys; used by tests that compare the sorted list itself).
-        ``backward_impl``: ``"butterfly"`` (default; ``csrc/blend_bwd.cu``) or ``"transposed"`` -- the EXPERIMENTAL
-        second implementation of the blend backward (``csrc/blend_bwd_transposed.cu``; logic verified on the CPU under
-        ``tests/simt``, not yet timed on a B200), which also skips the hook-only statistics when no hook is installed.
-        ``None`` reads the environment variable ``GSB200_BACKWARD_IMPL``.
-        ``skip_unused_hook_statistics``: with no backward hook installed, do not compute the statistics only a hook reads
-        (the reference's ``need_extra_info = False``, GPCR:521) in the default backward kernel either (opt-in until timed on
-        a B200; ``None`` reads ``GSB200_SKIP_HOOK_STATS``; the transposed kernel always skips them)."""
+        ``backward_impl``: ``"transposed"`` (default; ``csrc/blend_bwd_transposed.cu``: splat-per-lane accumulation after a
+        shared-memory transposition, 769 us at C3 on a B200) or ``"butterfly"`` (``csrc/blend_bwd.cu``: warp butterfly per
+        (warp, splat), 997 us; kept as the second implementation the parity tests cross-check).  Constructor argument only:
+        no environment variable can switch the kernel of a production run.  With no backward hook installed the transposed
+        kernel does not compute the statistics only a hook reads (the reference's ``need_extra_info = False``, GPCR:521).
+        ``skip_unused_hook_statistics``: the same switch for the butterfly kernel (opt-in; ``None`` reads
+        ``GSB200_SKIP_HOOK_STATS``)."""
         super().__init__()
         self.config = config
         self.backward_valid_point_hook = backward_valid_point_hook
         self._flags = (_lib.GSB_FLAG_EXACT_EXP if exact_exp else 0) | (_lib.GSB_FLAG_FORCE_KEY64 if force_key64 else 0) | \
             (_lib.GSB_FLAG_KEEP_ALL_TILE_PAIRS if keep_all_tile_pairs else 0)
-        backward_impl = backward_impl or os.environ.get("GSB200_BACKWARD_IMPL", "butterfly")
+        backward_impl = backward_impl or "transposed"
         if backward_impl not in ("butterfly", "transposed"):
             raise ValueError(f"backward_impl must be 'butterfly' or 'transposed', got {backward_impl!r}")
         self.backward_impl = backward_impl
@@ -347,39 +351,41 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
             readback = _PinnedCounters.acquire(device)
             pinned, event = readback
             retry_flag = 0
-            while True:
-                key_capacity = self._key_capacity
-                layout = self._layout(N, n_obj, key_capacity, H, W)
-                ws = torch.empty((layout.total_bytes,), dtype=torch.uint8, device=device)
-                args = _lib.GsbForwardArgs(
-                    num_points=N, pointcloud=_ptr(pointcloud), pointcloud_features=_ptr(pointcloud_features),
-                    point_invalid_mask=_ptr(point_invalid_mask), point_object_id=_ptr(point_object_id),
-                    num_objects=n_obj, q_pointcloud_camera=_ptr(q_pc), t_pointcloud_camera=_ptr(t_pc),
-                    camera_intrinsics=_ptr(K), camera_height=H, camera_width=W,
-                    near_plane=cfg.near_plane, far_plane=cfg.far_plane,
-                    depth_to_sort_key_scale=cfg.depth_to_sort_key_scale, rgb_only=1 if cfg.rgb_only else 0,
-                    flags=self._flags | retry_flag, workspace=_ptr(ws), workspace_bytes=layout.total_bytes,
-                    key_capacity=key_capacity, rasterized_image=_ptr(image), rasterized_depth=_ptr(depth),
-                    pixel_accumulated_alpha=_ptr(acc_alpha),
-                    pixel_offset_of_last_effective_point=_ptr(last_effective),
-                    pixel_valid_point_count=_ptr(valid_count), stream=stream.cuda_stream,
-                    host_counters=pinned.data_ptr(), host_counters_event=event.cuda_event)
-                # The whole frame is enqueued by this one call; the library copies {M, K, overflow} to pinned
-                # host memory right after the per-point stage and records `event` behind that copy.
-                _lib.check(lib.gsb200_forward(ctypes.byref(args)), "gsb200_forward")
-                frame = Frame(ws, layout, N, key_capacity, H, W, self._flags)
-                # ONE host wait per frame (the reference syncs twice, GPCR:864 and GPCR:916-931), and it ends
-                # when the first kernel is done: sort + blend are still in flight when we return.
-                event.synchronize()
-                frame.num_points_in_camera = int(pinned[0])
-                frame.num_keys = int(pinned[1])
-                if int(pinned[2]) == 0:
-                    break
-                # more (tile, splat) pairs than capacity: grow and redo the frame.  The first pass already
-                # normalised the quaternions in place; the re-run must not normalise them a second time.
-                self._key_capacity = int(frame.num_keys * 1.25) + 4096
-                retry_flag = _lib.GSB_FLAG_Q_ALREADY_NORMALISED
-            _PinnedCounters.release(device, readback)
+            try:
+                while True:
+                    key_capacity = self._key_capacity
+                    layout = self._layout(N, n_obj, key_capacity, H, W)
+                    ws = torch.empty((layout.total_bytes,), dtype=torch.uint8, device=device)
+                    args = _lib.GsbForwardArgs(
+                        num_points=N, pointcloud=_ptr(pointcloud), pointcloud_features=_ptr(pointcloud_features),
+                        point_invalid_mask=_ptr(point_invalid_mask), point_object_id=_ptr(point_object_id),
+                        num_objects=n_obj, q_pointcloud_camera=_ptr(q_pc), t_pointcloud_camera=_ptr(t_pc),
+                        camera_intrinsics=_ptr(K), camera_height=H, camera_width=W,
+                        near_plane=cfg.near_plane, far_plane=cfg.far_plane,
+                        depth_to_sort_key_scale=cfg.depth_to_sort_key_scale, rgb_only=1 if cfg.rgb_only else 0,
+                        flags=self._flags | retry_flag, workspace=_ptr(ws), workspace_bytes=layout.total_bytes,
+                        key_capacity=key_capacity, rasterized_image=_ptr(image), rasterized_depth=_ptr(depth),
+                        pixel_accumulated_alpha=_ptr(acc_alpha),
+                        pixel_offset_of_last_effective_point=_ptr(last_effective),
+                        pixel_valid_point_count=_ptr(valid_count), stream=stream.cuda_stream,
+                        host_counters=pinned.data_ptr(), host_counters_event=event.cuda_event)
+                    # The whole frame is enqueued by this one call; the library copies {M, K, overflow} to pinned
+                    # host memory right after the per-point stage and records `event` behind that copy.
+                    _lib.check(lib.gsb200_forward(ctypes.byref(args)), "gsb200_forward")
+                    frame = Frame(ws, layout, N, key_capacity, H, W, self._flags)
+                    # ONE host wait per frame (the reference syncs twice, GPCR:864 and GPCR:916-931), and it ends
+                    # when the first kernel is done: sort + blend are still in flight when we return.
+                    event.synchronize()
+                    frame.num_points_in_camera = int(pinned[0])
+                    frame.num_keys = int(pinned[1])
+                    if int(pinned[2]) == 0:
+                        break
+                    # more (tile, splat) pairs than capacity: grow and redo the frame.  The first pass already
+                    # normalised the quaternions in place; the re-run must not normalise them a second time.
+                    self._key_capacity = int(frame.num_keys * 1.25) + 4096
+                    retry_flag = _lib.GSB_FLAG_Q_ALREADY_NORMALISED
+            finally:  # also when the library call raises: the pooled pair goes back
+                _PinnedCounters.release(device, readback)
         self.last_frame = frame
         return (image, depth, acc_alpha, last_effective, valid_count), frame, {"camera_intrinsics": K}
 
