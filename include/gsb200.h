@@ -51,9 +51,10 @@ enum {
 #define GSB_FLAG_Q_ALREADY_NORMALISED 4u /* forward only: take q as stored and do not rewrite it.  Used when a
                                             frame is re-run after a key-capacity overflow, so that the second
                                             pass is bit-identical to the first (normalising twice is not). */
-#define GSB_FLAG_BACKWARD_TRANSPOSED 16u /* backward only, EXPERIMENTAL (not the default, not yet timed on a B200): loop A
-                                            accumulates per splat in registers after a shared-memory transposition instead
-                                            of a warp butterfly per (warp, splat), see csrc/blend_bwd_transposed.cu */
+#define GSB_FLAG_BACKWARD_TRANSPOSED 16u /* backward only: loop A accumulates per splat in registers after a shared-memory
+                                            transposition (csrc/blend_bwd_transposed.cu; what the Python operator passes by
+                                            default: 769 us at C3 on a B200) instead of a warp butterfly per (warp, splat)
+                                            (csrc/blend_bwd.cu, 997 us; flag clear) */
 #define GSB_FLAG_NO_HOOK_STATS 32u       /* backward only, opt-in: skip the statistics only a
                                             backward hook reads (|d/duv| magnitude, affected-pixel count, magnitude image) --
                                             the reference's need_extra_info = False, GPCR:521, 690-704.  accum[:, 9:11] and
@@ -189,6 +190,19 @@ int gsb200_stage_blend(const GsbForwardArgs *args);        /* K6 */
  * counterpart is the Taichi kernel profiler, GaussianPointTrainer.py:217-219.) */
 int gsb200_forward_timed(const GsbForwardArgs *args, float *stage_ms_out);
 int gsb200_backward_timed(const GsbBackwardArgs *args, float *stage_ms_out);
+
+/* Diagnostics: the blend kernels' real work, counted on the device (SURVEY 8(d) "E": pixel x splat evaluations).  Call after
+ * gsb200_forward (same args / workspace; re-renders the same outputs) resp. after it with the backward args of the same frame
+ * (adds into accum like gsb200_backward's loop A; pass a scratch accumulator).  host_out2[0] = (warp, splat) visits -- 32
+ * pixel x splat evaluations each --, host_out2[1] = evaluations that contribute (alpha >= 1/255 on a live pixel).  Blocks.
+ * (The reference's counterpart is the Taichi kernel profiler, GaussianPointTrainer.py:217-219.) */
+int gsb200_forward_blend_work(const GsbForwardArgs *args, uint64_t *host_out2);
+int gsb200_backward_blend_work(const GsbBackwardArgs *args, uint64_t *host_out2);
+
+/* Checks the two hardware facts the default arithmetic path relies on: rcp.approx(1.0f) == 1.0f (a non-contributing
+ * (pixel, splat) pair leaves the transmittance untouched in the branch-free backward, csrc/blend_bwd_transposed.cu) and
+ * ex2.approx(0) == 1.  Returns GSB_OK or GSB_EUNSUPPORTED.  Blocks. */
+int gsb200_device_selftest(void *stream);
 
 /* find_tile_start_and_end, GPCR:175-193, on the reference's own key packing: sorted int64 keys
  * (tile << 32 | depth) -> [start, end) per tile; outputs must be zero-initialised (GPCR:954-957). */

@@ -68,6 +68,7 @@ EXPORTS = (
     "gsb200_stage_blend", "gsb200_sort_temp_bytes", "gsb200_sort_pairs", "gsb200_render_host", "gsb200_find_tile_start_and_end",
     "gsb200_forward_timed", "gsb200_backward_timed", "gsb200_abi_sizes", "gsb200_l1_loss_temp_bytes", "gsb200_l1_loss",
     "gsb200_image_loss_temp_bytes", "gsb200_image_loss", "gsb200_adam_step", "gsb200_controller_update",
+    "gsb200_forward_blend_work", "gsb200_backward_blend_work", "gsb200_device_selftest",
 )
 
 _lib = None
@@ -112,6 +113,12 @@ def load() -> ctypes.CDLL:
     lib.gsb200_adam_step.restype = ctypes.c_int
     lib.gsb200_controller_update.argtypes = [c_vp, c_i64] + [c_vp] * 10
     lib.gsb200_controller_update.restype = ctypes.c_int
+    lib.gsb200_forward_blend_work.argtypes = [ctypes.POINTER(GsbForwardArgs), ctypes.POINTER(ctypes.c_uint64)]
+    lib.gsb200_forward_blend_work.restype = ctypes.c_int
+    lib.gsb200_backward_blend_work.argtypes = [ctypes.POINTER(GsbBackwardArgs), ctypes.POINTER(ctypes.c_uint64)]
+    lib.gsb200_backward_blend_work.restype = ctypes.c_int
+    lib.gsb200_device_selftest.argtypes = [c_vp]
+    lib.gsb200_device_selftest.restype = ctypes.c_int
     sizes = (c_i64 * 3)()
     lib.gsb200_abi_sizes(sizes)
     mine = (ctypes.sizeof(GsbWorkspaceLayout), ctypes.sizeof(GsbForwardArgs), ctypes.sizeof(GsbBackwardArgs))

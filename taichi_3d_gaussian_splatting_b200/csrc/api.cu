@@ -347,6 +347,72 @@ int gsb200_backward_timed(const GsbBackwardArgs *a, float *stage_ms_out) {
     return t.finish(stage_ms_out);
 }
 
+int gsb200_forward_blend_work(const GsbForwardArgs *a, uint64_t *host_out2) {
+    Workspace ws;
+    int rc = resolve_fwd(a, &ws);
+    if (rc != GSB_OK) return rc;
+    if (!host_out2 || a->rgb_only) {
+        set_error("forward_blend_work: host_out2 is null or rgb_only is set");
+        return GSB_EINVAL;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+    unsigned long long *cnt = reinterpret_cast<unsigned long long *>(ws.counters + 4);
+    GSB_CUDA_CHECK(cudaMemsetAsync(cnt, 0, 16, st));
+    if ((rc = launch_blend_forward_count(*a, ws, cnt, st)) != GSB_OK) return rc;
+    GSB_CUDA_CHECK(cudaMemcpyAsync(host_out2, cnt, 16, cudaMemcpyDeviceToHost, st));
+    GSB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return GSB_OK;
+}
+
+int gsb200_backward_blend_work(const GsbBackwardArgs *a, uint64_t *host_out2) {
+    if (!a || !host_out2 || !a->grad_rasterized_image || !a->pixel_accumulated_alpha ||
+        !a->pixel_offset_of_last_effective_point || !a->accum) {
+        set_error("backward_blend_work: null pointer argument");
+        return GSB_EINVAL;
+    }
+    Workspace ws;
+    int rc = resolve_workspace(a->workspace, a->workspace_bytes, a->num_points, a->num_objects,
+                               a->key_capacity, a->camera_height, a->camera_width, a->far_plane,
+                               a->depth_to_sort_key_scale, a->flags, &ws);
+    if (rc != GSB_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+    unsigned long long *cnt = reinterpret_cast<unsigned long long *>(ws.counters + 6);
+    GSB_CUDA_CHECK(cudaMemsetAsync(cnt, 0, 16, st));
+    if ((rc = launch_blend_backward_work(*a, ws, cnt, st)) != GSB_OK) return rc;
+    GSB_CUDA_CHECK(cudaMemcpyAsync(host_out2, cnt, 16, cudaMemcpyDeviceToHost, st));
+    GSB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return GSB_OK;
+}
+
+namespace {
+__global__ void selftest_kernel(unsigned int *out) {
+    float one = 1.0f, zero = 0.0f, r, e;
+    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(one));
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(zero));
+    out[0] = __float_as_uint(r);
+    out[1] = __float_as_uint(e);
+}
+}  // namespace
+
+int gsb200_device_selftest(void *stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned int *dev = nullptr, host[2] = {0u, 0u};
+    GSB_CUDA_CHECK(cudaMalloc(&dev, 8));
+    selftest_kernel<<<1, 1, 0, st>>>(dev);
+    cudaError_t e = cudaMemcpyAsync(host, dev, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(dev);
+    if (e != cudaSuccess) {
+        set_error("device_selftest: %s", cudaGetErrorString(e));
+        return GSB_ECUDA;
+    }
+    if (host[0] != 0x3f800000u || host[1] != 0x3f800000u) {
+        set_error("device_selftest: rcp.approx(1) = 0x%08x, ex2.approx(0) = 0x%08x (both must be 1.0f exactly)", host[0], host[1]);
+        return GSB_EUNSUPPORTED;
+    }
+    return GSB_OK;
+}
+
 int gsb200_find_tile_start_and_end(const int64_t *sorted_keys, int64_t num_keys, int32_t *tile_points_start,
                                    int32_t *tile_points_end, int32_t num_tiles, void *stream) {
     if (num_keys < 0 || num_tiles < 0 || (num_keys > 0 && (!sorted_keys || !tile_points_start || !tile_points_end))) {

@@ -198,7 +198,10 @@ blend_backward_kernel(const BlendBwdParams p) {
                             // r1 = c | rescale*opacity | 1-opacity | depth.  The colour recursion of GPCR:653-657,
                             // sum_c (col_c T - w_c/(1-a)) g_c, is carried as ONE scalar: with cg = sum_c col_c g_c and
                             // w0 = sum_c w_c g_c it is  cg T - w0/(1-a),  and w0 += cg a T.
-                            const float P = ex2_approx_b(-0.72134752044448170368f * (d0 * q0 + d1 * q1)) * r1.y;
+                            // alpha exactly as the forward computes it (fast_alpha on the forward's pre-scaled conic, common.cuh): both
+                            // passes take the alpha >= 1/255 decision on identical bits
+                            const float P = fast_alpha(d0, d1, (-0.5f * GSB_L2E) * r0.z, -GSB_L2E * r0.w,
+                                                       (-0.5f * GSB_L2E) * r1.x, r1.y);
                             contributes = (idx < last) && (P >= 1.0f / 255.0f);
                             const float alpha = fminf(P, 0.99f);
                             const float inv = rcp_approx(1.0f - alpha);
@@ -247,6 +250,36 @@ blend_backward_kernel(const BlendBwdParams p) {
 }
 
 #ifndef GSB_HOST_EMU
+static BlendBwdParams make_blend_bwd_params(const GsbBackwardArgs &a, const Workspace &ws);
+
+int launch_blend_backward_work(const GsbBackwardArgs &a, const Workspace &ws, unsigned long long *counters_dev,
+                               cudaStream_t stream) {
+    BlendBwdParams p = make_blend_bwd_params(a, ws);
+    p.work_counters = counters_dev;
+    const int tiles = p.tiles_x * (a.camera_height / GSB_TILE_HEIGHT);
+    if (tiles <= 0) return GSB_OK;
+    return launch_blend_backward_count(p, tiles, stream);
+}
+
+static BlendBwdParams make_blend_bwd_params(const GsbBackwardArgs &a, const Workspace &ws) {
+    const GsbWorkspaceLayout &L = ws.layout;
+    BlendBwdParams p;
+    p.H = a.camera_height;
+    p.W = a.camera_width;
+    p.tiles_x = a.camera_width / GSB_TILE_WIDTH;
+    p.tile_start = ws.tile_start;
+    p.tile_end = ws.tile_end;
+    p.sorted_vals = (L.sort_passes % 2) == 1 ? ws.vals_b : ws.vals_a;
+    p.records = ws.records;
+    p.grad_image = a.grad_rasterized_image;
+    p.acc_alpha = a.pixel_accumulated_alpha;
+    p.last_effective = a.pixel_offset_of_last_effective_point;
+    p.accum = a.accum;
+    p.mag_image = a.magnitude_grad_viewspace_on_image;
+    p.work_counters = nullptr;
+    return p;
+}
+
 int launch_blend_backward(const GsbBackwardArgs &a, const Workspace &ws, cudaStream_t stream) {
     const GsbWorkspaceLayout &L = ws.layout;
     BlendBwdParams p;
@@ -262,6 +295,7 @@ int launch_blend_backward(const GsbBackwardArgs &a, const Workspace &ws, cudaStr
     p.last_effective = a.pixel_offset_of_last_effective_point;
     p.accum = a.accum;
     p.mag_image = a.magnitude_grad_viewspace_on_image;
+    p.work_counters = nullptr;
     const int tiles = p.tiles_x * (a.camera_height / GSB_TILE_HEIGHT);
     if (tiles <= 0) return GSB_OK;
     if (a.flags & GSB_FLAG_BACKWARD_TRANSPOSED)  // experimental, see blend_bwd_transposed.cu

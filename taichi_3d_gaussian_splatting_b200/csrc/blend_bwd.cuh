@@ -16,6 +16,7 @@ struct BlendBwdParams {
     const int *last_effective;
     float *accum;      // rows of 12 floats
     float *mag_image;  // (H,W,2)
+    unsigned long long *work_counters;  // COUNT instantiation only: [0] (warp, splat) visits, [1] contributing (pixel, splat) pairs
 };
 
 #ifdef GSB_HOST_EMU  // tests/simt: the kernels compiled as host C++ under a lock-step SIMT emulator
@@ -42,5 +43,6 @@ __device__ __forceinline__ float sqrt_approx(float x) {  // MUFU.RSQ based, ~1 u
 
 int launch_blend_backward_transposed(const BlendBwdParams &p, int tiles, bool exact_exp, bool stats,
                                      cudaStream_t stream);
+int launch_blend_backward_count(const BlendBwdParams &p, int tiles, cudaStream_t stream);
 
 }  // namespace gsb

@@ -50,7 +50,7 @@ __device__ __forceinline__ unsigned char *tb_dynamic_smem() { return gsb_tb_dyna
 #ifndef GSB_TB_MIN_BLOCKS
 #define GSB_TB_MIN_BLOCKS 3  // 73 KB of shared memory per CTA allow 3; tuning knob (GSB200_DEFINES="-DGSB_TB_MIN_BLOCKS=2")
 #endif
-template <bool EXACT_EXP, bool STATS>
+template <bool EXACT_EXP, bool STATS, bool COUNT = false>
 __global__ void __launch_bounds__(GSB_TILE_PIXELS, GSB_TB_MIN_BLOCKS)
 blend_backward_transposed_kernel(const BlendBwdParams p) {
     TbShared &S = *reinterpret_cast<TbShared *>(tb_dynamic_smem());
@@ -71,6 +71,7 @@ blend_backward_transposed_kernel(const BlendBwdParams p) {
     float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f;
     const float g0 = p.grad_image[3 * pix], g1 = p.grad_image[3 * pix + 1], g2 = p.grad_image[3 * pix + 2];
     float mag0 = 0.0f, mag1 = 0.0f;
+    unsigned int n_visits = 0, n_pairs = 0;  // COUNT only
     S.g[warp][lane] = make_float4(g0, g1, g2, 0.0f);
 
     // phase-2 role of this lane: splat `ci` of the chunk, pixels 16*half .. 16*half+15 of the patch (= rows 2*half, 2*half+1)
@@ -116,8 +117,15 @@ blend_backward_transposed_kernel(const BlendBwdParams p) {
                     const int o = __ldg(&p.sorted_vals[idx]);
                     const float4 *rec = p.records + 3 * (size_t)o;
                     const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
-                    s_r0[tid] = r0;
-                    s_r1[tid] = EXACT_EXP ? r1 : make_float4(r1.x, r1.y * r1.z, 1.0f - r1.z, r1.w);
+                    if (EXACT_EXP) {
+                        s_r0[tid] = r0;
+                        s_r1[tid] = r1;
+                    } else {  // the forward's staged planes (common.cuh): u v A B | C rescale*opacity 1-opacity depth
+                        float4 f0, f1;
+                        fast_planes(r0, r1, f0, f1);
+                        s_r0[tid] = f0;
+                        s_r1[tid] = f1;
+                    }
                     s_r2[tid] = __ldg(rec + 2);
                     S.off[buf][tid] = o;
                     mask = splat_patch_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y * r1.z, tile_x0, tile_y0);
@@ -169,6 +177,7 @@ blend_backward_transposed_kernel(const BlendBwdParams p) {
             if (have == TB_CHUNK || (!real && have > 0)) {
                 const int n = have;
                 have = 0;
+                if (COUNT) n_visits += (lane == 0) ? (unsigned int)n : 0u;
                 if (lane == 0) {
                     GSB_EMU_COUNT(EC_TB_SPLATS, n);
                     GSB_EMU_COUNT(EC_TB_CHUNKS, 1);
@@ -176,15 +185,15 @@ blend_backward_transposed_kernel(const BlendBwdParams p) {
                 // ---- phase 1: lane = pixel; sequential over the chunk's splats (back to front)
 #pragma unroll 2
                 for (int i = 0; i < n; ++i) {
-                    const float4 r0 = ck0[i];  // u v a b
-                    const float4 r1 = ck1[i];  // c rescale opacity depth   (fast path: c rescale*opacity 1-opacity depth)
+                    const float4 r0 = ck0[i];  // u v a b                   (fast path: u v A B, conic scaled by -log2(e)/2)
+                    const float4 r1 = ck1[i];  // c rescale opacity depth   (fast path: C rescale*opacity 1-opacity depth)
                     const float4 r2 = ck2[i];  // r g b | sorted index
                     const int idx = __float_as_int(r2.w);
                     const float d0 = px - r0.x, d1 = py - r0.y;
-                    const float q0 = r0.z * d0 + r0.w * d1;
-                    const float q1 = r0.w * d0 + r1.x * d1;
                     float G, aT;
                     if (EXACT_EXP) {
+                        const float q0 = r0.z * d0 + r0.w * d1;
+                        const float q1 = r0.w * d0 + r1.x * d1;
                         const float gp = expf(-0.5f * (d0 * q0 + d1 * q1)) * r1.y;
                         const float prod_alpha = gp * r1.z;
                         const bool contributes = (idx < last) && (prod_alpha >= 1.0f / 255.0f);
@@ -200,24 +209,33 @@ blend_backward_transposed_kernel(const BlendBwdParams p) {
                         w1 = fmaf(r2.y, aT, w1);
                         w2 = fmaf(r2.z, aT, w2);
                         G = a_grad * r1.z * gp;
+                        if (STATS) {
+                            mag0 += fabsf(G * q0);
+                            mag1 += fabsf(G * q1);
+                        }
                     } else {
-                        // one-scalar colour recursion, see blend_bwd.cu
-                        const float P = ex2_approx_b(-0.72134752044448170368f * (d0 * q0 + d1 * q1)) * r1.y;
-                        const bool contributes = (idx < last) && (P >= 1.0f / 255.0f);
+                        // One-scalar colour recursion (see blend_bwd.cu); alpha is the FORWARD's expression on the forward's
+                        // staged values (fast_alpha, common.cuh), so both passes take the 1/255 decision on identical bits.
+                        // A pair that does not contribute gets P = 0: then alpha = 0, 1/(1-alpha) = 1, T and w0 keep their
+                        // values and G = aT = 0 -- no other select is needed.
+                        float P = fast_alpha(d0, d1, r0.z, r0.w, r1.x, r1.y);
+                        P = ((idx < last) && (P >= 1.0f / 255.0f)) ? P : 0.0f;
                         const float alpha = fminf(P, 0.99f);
                         const float inv = rcp_approx(1.0f - alpha);
-                        const float Tn = T * inv;
-                        aT = contributes ? alpha * Tn : 0.0f;
+                        T *= inv;                 // T_i = T_{i+1} / (1 - alpha), GPCR:640
+                        aT = alpha * T;
                         const float cg = fmaf(r2.z, g2, fmaf(r2.y, g1, r2.x * g0));
-                        const float a_grad = contributes ? fmaf(cg, Tn, -(w0 * inv)) : 0.0f;
-                        T = contributes ? Tn : T;
+                        const float a_grad = fmaf(cg, T, -(w0 * inv));
                         w0 = fmaf(cg, aT, w0);
                         G = a_grad * P;
+                        if (STATS) {  // hook only: |d/duv| on the image needs conic * d  (A d0 + B/2 d1 = -log2(e)/2 q0)
+                            const float q0 = (-2.0f / GSB_L2E) * fmaf(r0.z, d0, 0.5f * r0.w * d1);
+                            const float q1 = (-2.0f / GSB_L2E) * fmaf(0.5f * r0.w, d0, r1.x * d1);
+                            mag0 += fabsf(G * q0);
+                            mag1 += fabsf(G * q1);
+                        }
                     }
-                    if (STATS) {
-                        mag0 += fabsf(G * q0);
-                        mag1 += fabsf(G * q1);
-                    }
+                    if (COUNT) n_pairs += aT > 0.0f ? 1u : 0u;
                     xg[lane * TB_ROW + i] = G;
                     xa[lane * TB_ROW + i] = aT;
                 }
@@ -225,8 +243,13 @@ blend_backward_transposed_kernel(const BlendBwdParams p) {
 
                 // ---- phase 2: lane = splat ci of the chunk, over 16 pixels
                 const bool active = ci < n;
-                const float4 s0 = ck0[active ? ci : 0];
-                const float4 s1 = ck1[active ? ci : 0];
+                float4 s0 = ck0[active ? ci : 0];
+                float4 s1 = ck1[active ? ci : 0];
+                if (!EXACT_EXP) {  // back to the conic itself (the chunk holds it scaled by -log2(e)/2 for fast_alpha)
+                    s0.z *= -2.0f / GSB_L2E;
+                    s0.w *= -1.0f / GSB_L2E;
+                    s1.x *= -2.0f / GSB_L2E;
+                }
                 float dxs[8], dys[2];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) dxs[k] = (pxb + (float)k) - s0.x;
@@ -290,6 +313,17 @@ blend_backward_transposed_kernel(const BlendBwdParams p) {
         p.mag_image[2 * pix] = mag0;  // GPCR:700-704
         p.mag_image[2 * pix + 1] = mag1;
     }
+    if (COUNT) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            n_visits += __shfl_xor_sync(0xffffffffu, n_visits, d);
+            n_pairs += __shfl_xor_sync(0xffffffffu, n_pairs, d);
+        }
+        if (lane == 0) {
+            atomicAdd(p.work_counters, (unsigned long long)n_visits);
+            atomicAdd(p.work_counters + 1, (unsigned long long)n_pairs);
+        }
+    }
 }
 
 #ifndef GSB_HOST_EMU
@@ -310,6 +344,16 @@ int launch_blend_backward_transposed(const BlendBwdParams &p, int tiles, bool ex
                                      cudaStream_t stream) {
     if (exact_exp) return stats ? launch_tb<true, true>(p, tiles, stream) : launch_tb<true, false>(p, tiles, stream);
     return stats ? launch_tb<false, true>(p, tiles, stream) : launch_tb<false, false>(p, tiles, stream);
+}
+
+// Diagnostic: loop A with GPU-side work counters (default arithmetic, no hook statistics): counters[0] = (warp, splat)
+// visits of phase 1, [1] = contributing (pixel, splat) pairs.  Adds into p.accum like the normal launch.
+int launch_blend_backward_count(const BlendBwdParams &p, int tiles, cudaStream_t stream) {
+    GSB_CUDA_CHECK(cudaFuncSetAttribute(blend_backward_transposed_kernel<false, false, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TbShared)));
+    blend_backward_transposed_kernel<false, false, true><<<tiles, GSB_TILE_PIXELS, sizeof(TbShared), stream>>>(p);
+    GSB_CUDA_CHECK(cudaGetLastError());
+    return GSB_OK;
 }
 #endif  // GSB_HOST_EMU
 

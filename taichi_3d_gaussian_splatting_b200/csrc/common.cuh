@@ -68,6 +68,10 @@ int launch_tile_ranges_raw(const long long *keys_i64, int64_t n, int *tile_start
 int launch_blend_forward(const GsbForwardArgs &a, const Workspace &ws, cudaStream_t stream);
 int launch_blend_backward(const GsbBackwardArgs &a, const Workspace &ws, cudaStream_t stream);
 int launch_backward_points(const GsbBackwardArgs &a, const Workspace &ws, cudaStream_t stream);
+int launch_blend_forward_count(const GsbForwardArgs &a, const Workspace &ws, unsigned long long *counters_dev,
+                               cudaStream_t stream);
+int launch_blend_backward_work(const GsbBackwardArgs &a, const Workspace &ws, unsigned long long *counters_dev,
+                               cudaStream_t stream);
 
 int sort_radix_bits(int bits);
 int sort_pairs_device(const void *keys_in, const int *vals_in, void *keys_out, int *vals_out,
@@ -192,6 +196,31 @@ __device__ __forceinline__ unsigned int splat_patch_mask(float u, float v, float
         if (rect_reachable(r, X0, X0 + 7.0f, Y0, Y0 + 3.0f)) m |= 1u << w;
     }
     return m;
+}
+#endif
+
+// ---- alpha of the default (fast) arithmetic path, shared by the forward blend and both backward kernels so that the
+// alpha >= 1/255 decision of a (pixel, splat) pair is taken on bit-identical values in both passes.  The staged record
+// carries the conic pre-scaled by -log2(e)/2: A = -log2(e)/2 a, B = -log2(e) b, C = -log2(e)/2 c, and ro = rescale * opacity:
+//   alpha = 2^(A dx^2 + B dx dy + C dy^2) * ro  =  exp(-(a dx^2 + 2 b dx dy + c dy^2) / 2) * rescale * opacity   (UT:275-284)
+#if defined(__CUDACC__) || defined(GSB_HOST_EMU)
+constexpr float GSB_L2E = 1.4426950408889634f;
+#ifdef GSB_HOST_EMU
+__device__ __forceinline__ float ex2_mufu(float x) { return exp2f(x); }
+#else
+__device__ __forceinline__ float ex2_mufu(float x) {  // one MUFU.EX2; rel. error ~2^-22
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+#endif
+__device__ __forceinline__ float fast_alpha(float dx, float dy, float A, float B, float C, float ro) {
+    return ex2_mufu(fmaf(dx, fmaf(A, dx, B * dy), (C * dy) * dy)) * ro;
+}
+// record planes r0 = u v a b, r1 = c rescale opacity depth  ->  staged fast-path planes u v A B | C ro (1 - opacity) depth
+__device__ __forceinline__ void fast_planes(const float4 r0, const float4 r1, float4 &s0, float4 &s1) {
+    s0 = make_float4(r0.x, r0.y, (-0.5f * GSB_L2E) * r0.z, -GSB_L2E * r0.w);
+    s1 = make_float4((-0.5f * GSB_L2E) * r1.x, r1.y * r1.z, 1.0f - r1.z, r1.w);
 }
 #endif
 

@@ -22,14 +22,8 @@ def KERNELS_PER_FORWARD(sort_passes: int) -> int:
 KERNELS_PER_BACKWARD = 2  # blend backward + per-point chain rule (memsets are driver fills, not counted)
 
 
-def stage_times(op: GaussianPointCloudRasterisation, input_data, grad_image: torch.Tensor,
-                iters: int = 5) -> Dict[str, float]:
-    """Average device milliseconds per stage over ``iters`` frames of ``input_data``."""
-    lib = _lib.load()
-    lib.gsb200_forward_timed.argtypes = [ctypes.POINTER(_lib.GsbForwardArgs), ctypes.POINTER(ctypes.c_float)]
-    lib.gsb200_forward_timed.restype = ctypes.c_int
-    lib.gsb200_backward_timed.argtypes = [ctypes.POINTER(_lib.GsbBackwardArgs), ctypes.POINTER(ctypes.c_float)]
-    lib.gsb200_backward_timed.restype = ctypes.c_int
+def _frame_args(op: GaussianPointCloudRasterisation, input_data, grad_image: torch.Tensor):
+    """Argument blocks of one frame of ``input_data`` on buffers of their own (sized by a first run of the operator)."""
     cfg = op.config
     pc, feat = input_data.point_cloud.detach(), input_data.point_cloud_features.detach()
     ci = input_data.camera_info
@@ -41,7 +35,6 @@ def stage_times(op: GaussianPointCloudRasterisation, input_data, grad_image: tor
     M = frame.num_points_in_camera
     layout = frame.layout
     n_obj = input_data.q_pointcloud_camera.shape[0]
-    totals = {k: 0.0 for k in FORWARD_STAGES + BACKWARD_STAGES}
     with torch.cuda.device(device):
         stream = torch.cuda.current_stream(device).cuda_stream
         ws = torch.empty((layout.total_bytes,), dtype=torch.uint8, device=device)
@@ -56,6 +49,7 @@ def stage_times(op: GaussianPointCloudRasterisation, input_data, grad_image: tor
         K = ci.camera_intrinsics.contiguous()
         q = input_data.q_pointcloud_camera.contiguous()
         t = input_data.t_pointcloud_camera.contiguous()
+        g = grad_image.contiguous()
         fa = _lib.GsbForwardArgs(
             num_points=N, pointcloud=_ptr(pc), pointcloud_features=_ptr(feat),
             point_invalid_mask=_ptr(input_data.point_invalid_mask), point_object_id=_ptr(input_data.point_object_id),
@@ -75,10 +69,25 @@ def stage_times(op: GaussianPointCloudRasterisation, input_data, grad_image: tor
             grad_alpha_factor=cfg.grad_alpha_factor, grad_color_factor=cfg.grad_color_factor,
             grad_high_order_color_factor=cfg.grad_high_order_color_factor, flags=op.backward_flags(frame.flags),
             workspace=_ptr(ws), workspace_bytes=layout.total_bytes, key_capacity=frame.key_capacity,
-            grad_rasterized_image=_ptr(grad_image.contiguous()), pixel_accumulated_alpha=_ptr(acc),
+            grad_rasterized_image=_ptr(g), pixel_accumulated_alpha=_ptr(acc),
             pixel_offset_of_last_effective_point=_ptr(last), accum=_ptr(accum), accum_rows=M,
             grad_pointcloud=_ptr(gx), grad_pointcloud_features=_ptr(gf),
             magnitude_grad_viewspace_on_image=_ptr(mag), stream=stream)
+    keepalive = (ws, image, depth, acc, last, cnt, gx, gf, accum, mag, K, q, t, g, pc, feat)
+    return fa, ba, keepalive
+
+
+def stage_times(op: GaussianPointCloudRasterisation, input_data, grad_image: torch.Tensor,
+                iters: int = 5) -> Dict[str, float]:
+    """Average device milliseconds per stage over ``iters`` frames of ``input_data``."""
+    lib = _lib.load()
+    lib.gsb200_forward_timed.argtypes = [ctypes.POINTER(_lib.GsbForwardArgs), ctypes.POINTER(ctypes.c_float)]
+    lib.gsb200_forward_timed.restype = ctypes.c_int
+    lib.gsb200_backward_timed.argtypes = [ctypes.POINTER(_lib.GsbBackwardArgs), ctypes.POINTER(ctypes.c_float)]
+    lib.gsb200_backward_timed.restype = ctypes.c_int
+    fa, ba, keepalive = _frame_args(op, input_data, grad_image)
+    totals = {k: 0.0 for k in FORWARD_STAGES + BACKWARD_STAGES}
+    with torch.cuda.device(input_data.point_cloud.device):
         fms = (ctypes.c_float * 8)()
         bms = (ctypes.c_float * 8)()
         for it in range(iters + 1):
@@ -90,4 +99,26 @@ def stage_times(op: GaussianPointCloudRasterisation, input_data, grad_image: tor
                 totals[name] += fms[i]
             for i, name in enumerate(BACKWARD_STAGES):
                 totals[name] += bms[i]
+    del keepalive
     return {k: v / iters for k, v in totals.items()}
+
+
+def blend_work(op: GaussianPointCloudRasterisation, input_data, grad_image: torch.Tensor) -> Dict[str, int]:
+    """The blend kernels' real work for one frame of ``input_data``, counted on the device by the COUNT instantiations of
+    the two kernels (``gsb200_forward_blend_work`` / ``gsb200_backward_blend_work``): (warp, splat) visits (32 pixel x splat
+    evaluations each) and contributing evaluations -- SURVEY 8(d)'s "E" as a measurement."""
+    lib = _lib.load()
+    fa, ba, keepalive = _frame_args(op, input_data, grad_image)
+    out = {}
+    with torch.cuda.device(input_data.point_cloud.device):
+        _lib.check(lib.gsb200_forward(ctypes.byref(fa)), "gsb200_forward")
+        f = (ctypes.c_uint64 * 2)()
+        _lib.check(lib.gsb200_forward_blend_work(ctypes.byref(fa), f), "gsb200_forward_blend_work")
+        out["forward_warp_splat_visits"], out["forward_contributing_evaluations"] = int(f[0]), int(f[1])
+        ba.flags = (ba.flags | _lib.GSB_FLAG_BACKWARD_TRANSPOSED | _lib.GSB_FLAG_NO_HOOK_STATS) & ~_lib.GSB_FLAG_EXACT_EXP
+        keepalive[8].zero_()  # accum
+        b = (ctypes.c_uint64 * 2)()
+        _lib.check(lib.gsb200_backward_blend_work(ctypes.byref(ba), b), "gsb200_backward_blend_work")
+        out["backward_warp_splat_visits"], out["backward_contributing_evaluations"] = int(b[0]), int(b[1])
+    del keepalive
+    return out

@@ -255,6 +255,11 @@ inline unsigned int atomicAdd(unsigned int *a, unsigned int v) {
     *a = old + v;
     return old;
 }
+inline unsigned long long atomicAdd(unsigned long long *a, unsigned long long v) {
+    const unsigned long long old = *a;
+    *a = old + v;
+    return old;
+}
 inline unsigned int atomicOr(unsigned int *a, unsigned int v) {
     const unsigned int old = *a;
     *a = old | v;

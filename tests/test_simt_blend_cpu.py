@@ -122,8 +122,12 @@ def test_transposed_kernel_matches_the_butterfly_kernel(emu, scene, exact):
     for cols in (slice(0, 2), slice(2, 5), slice(5, 8), slice(8, 9), slice(9, 10)):
         ok, nbad, worst = _close(got[:, cols], ref[:, cols], 1e-4, 2e-6)  # same arithmetic per pixel, other summation order
         assert ok, (cols, nbad, worst)
-    # the per-pixel recursion is the same code in both kernels
-    assert np.array_equal(got_img, ref_img)
+    # the per-pixel recursion is the same code in both kernels (exact path); on the fast path both take alpha from
+    # fast_alpha (common.cuh) but the transposed kernel re-derives conic * d for the magnitude image from the pre-scaled conic
+    if exact:
+        assert np.array_equal(got_img, ref_img)
+    else:
+        assert np.allclose(got_img, ref_img, rtol=2e-6, atol=1e-7 * float(np.abs(ref_img).max()))
     # without the hook statistics: columns 0..8 as in the run with them (the warps interleave differently, so the float
     # atomics of splats shared by several patches land in another order), 9..10 and the magnitude image untouched
     lean, lean_img = _run(emu, fwd, rec, g, True, exact, False)
