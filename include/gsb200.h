@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GSB200_VERSION 100 /* major*100 + minor */
+#define GSB200_VERSION 101 /* major*100 + minor */
 
 #define GSB_TILE_WIDTH 16     /* GPCR:27 */
 #define GSB_TILE_HEIGHT 16    /* GPCR:28 */
@@ -59,6 +59,10 @@ enum {
                                             backward hook reads (|d/duv| magnitude, affected-pixel count, magnitude image) --
                                             the reference's need_extra_info = False, GPCR:521, 690-704.  accum[:, 9:11] and
                                             magnitude_grad_viewspace_on_image are then left untouched (the pointer must still be valid) */
+
+#define GSB_FLAG_COMPACT_GRADS 64u        /* backward only (view-parallel training, parallel.py): the per-point kernel writes
+                                            grad_sum_compact (N,12) and grad_color_compact (N,3) instead of the dense
+                                            gradients; gsb200_expand_view_gradients rebuilds them after the exchange */
 
 /* Byte offsets of the sub-buffers inside the caller-owned workspace blob.  Filled by
  * gsb200_workspace_layout(); the Python shim uses it to expose saved-for-backward tensors as views. */
@@ -149,7 +153,35 @@ typedef struct GsbBackwardArgs {
     float *grad_pointcloud_features;    /* (N,56) fully written, band-masked and factor-scaled */
     float *magnitude_grad_viewspace_on_image; /* (H,W,2) */
     void *stream;
+    /* GSB_FLAG_COMPACT_GRADS only (then grad_pointcloud / grad_pointcloud_features may be NULL): per scene row, zeros outside
+     * the frustum -- grad_sum_compact (N,12) = xyz(3) q(4) s(3) logit(1) pad, factors applied: the columns that add up over
+     * views; grad_color_compact (N,3) = dL/d(SH colour argument) of THIS view (its 48 SH gradients are the outer product
+     * with this view's SH basis, GPCR:749-756). */
+    float *grad_sum_compact;
+    float *grad_color_compact;
 } GsbBackwardArgs;
+
+/* View-parallel training (the reference is single-GPU): after the ranks have exchanged their COMPACT rows --
+ * all-reduce(sum) of grad_sum_compact, all-gather of [grad_color_compact | t_pointcloud_camera] -- rebuild the dense
+ * gradients of the whole batch of views: (N,3) and (N,56) exactly as the sum over views of what gsb200_backward writes
+ * per view (SH gradient of view v = colour-argument gradient (x) SH basis along xyz - camera centre of v, times the
+ * colour factors, masked by color_max_sh_band; GPCR:749-756, 1105-1125, 1167-1182), summed in view order.
+ * 14 instead of 59 floats per Gaussian cross NVLink. */
+typedef struct GsbExpandArgs {
+    int64_t num_points;
+    int32_t num_views, num_objects;
+    const float *grad_sum;          /* (N,12), already summed over the views */
+    const float *grad_color_views;  /* num_views blocks, view_stride floats apart: [N*3 colour-argument gradients |
+                                       num_objects*3 camera centres (that view's t_pointcloud_camera)] */
+    int64_t view_stride;            /* >= 3*N + 3*num_objects */
+    const float *pointcloud;        /* (N,3) */
+    const int32_t *point_object_id; /* (N) */
+    int32_t color_max_sh_band;
+    float grad_color_factor, grad_high_order_color_factor;
+    float *grad_pointcloud;          /* (N,3) out */
+    float *grad_pointcloud_features; /* (N,56) out */
+    void *stream;
+} GsbExpandArgs;
 
 /* version / errors */
 int gsb200_version(void);
@@ -176,6 +208,8 @@ int gsb200_forward(const GsbForwardArgs *args);
  * gaussian_point_rasterisation_backward GPCR:488-772, _clear_grad_by_color_max_sh_band
  * GPCR:1167-1182, factor scaling GPCR:1105-1125). */
 int gsb200_backward(const GsbBackwardArgs *args);
+
+int gsb200_expand_view_gradients(const GsbExpandArgs *args);
 
 /* Individual stages (same workspace), for tests and profiling. */
 int gsb200_stage_preprocess(const GsbForwardArgs *args);   /* K1+P1+K2+K3+P2+K4 fused */

@@ -229,6 +229,7 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
         keep_all_tile_pairs: bool = False,
         backward_impl: Optional[str] = None,
         skip_unused_hook_statistics: Optional[bool] = None,
+        gradient_exchange=None,
     ):
         """``exact_exp``: blend kernels use ``expf`` instead of ``ex2.approx`` (parity debugging).
         ``force_key64``: sort the reference's 64-bit ``tile << 32 | depth`` keys even when the live
@@ -242,7 +243,12 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
         no environment variable can switch the kernel of a production run.  With no backward hook installed the transposed
         kernel does not compute the statistics only a hook reads (the reference's ``need_extra_info = False``, GPCR:521).
         ``skip_unused_hook_statistics``: the same switch for the butterfly kernel (opt-in; ``None`` reads
-        ``GSB200_SKIP_HOOK_STATS``)."""
+        ``GSB200_SKIP_HOOK_STATS``).
+        ``gradient_exchange``: a ``parallel.ViewParallelExchange`` (view-parallel training, one process per GPU): backward
+        then returns the gradients SUMMED over the ranks' views -- the per-point kernel writes compact rows, the ranks
+        exchange 14 instead of 59 floats per Gaussian and ``gsb200_expand_view_gradients`` rebuilds the dense sum.  A
+        backward hook still sees this rank's own view (``grad_pointfeatures_in_camera`` is ``None`` in this mode: the
+        per-view dense feature gradients are never formed)."""
         super().__init__()
         self.config = config
         self.backward_valid_point_hook = backward_valid_point_hook
@@ -255,6 +261,7 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
         if skip_unused_hook_statistics is None:
             skip_unused_hook_statistics = os.environ.get("GSB200_SKIP_HOOK_STATS", "0") not in ("", "0")
         self.skip_unused_hook_statistics = bool(skip_unused_hook_statistics)
+        self.gradient_exchange = gradient_exchange
         self._key_capacity = int(initial_key_capacity) if initial_key_capacity else 0
         self.last_frame: Optional[Frame] = None
         self.last_gradient_buffer: Optional[torch.Tensor] = None  # flat storage behind the latest backward's grads
@@ -420,6 +427,16 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
             magnitude_on_image = torch.empty((H, W, 2), dtype=torch.float32, device=device)
             t_pc = t_pointcloud_camera.contiguous()
             backward_flags = self.backward_flags(frame.flags)
+            exchange = self.gradient_exchange
+            compact = exchange is not None and exchange.world > 1
+            grad_sum = blocks = None
+            if compact:
+                n_obj = ctx.num_objects
+                stride = (3 * N + 3 * n_obj + 3) // 4 * 4
+                grad_sum = torch.empty((N, 12), dtype=torch.float32, device=device)
+                blocks = torch.empty((exchange.world, stride), dtype=torch.float32, device=device)
+                blocks[exchange.rank, 3 * N:3 * N + 3 * n_obj] = t_pc.reshape(-1)
+                backward_flags |= _lib.GSB_FLAG_COMPACT_GRADS
             args = _lib.GsbBackwardArgs(
                 num_points=N, pointcloud=_ptr(pointcloud), pointcloud_features=_ptr(pointcloud_features),
                 point_object_id=_ptr(point_object_id), num_objects=ctx.num_objects,
@@ -433,8 +450,23 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
                 pixel_offset_of_last_effective_point=_ptr(last_effective), accum=_ptr(accum),
                 accum_rows=M, grad_pointcloud=_ptr(grad_pointcloud),
                 grad_pointcloud_features=_ptr(grad_pointcloud_features),
-                magnitude_grad_viewspace_on_image=_ptr(magnitude_on_image), stream=stream.cuda_stream)
+                magnitude_grad_viewspace_on_image=_ptr(magnitude_on_image), stream=stream.cuda_stream,
+                grad_sum_compact=_ptr(grad_sum), grad_color_compact=_ptr(blocks[exchange.rank]) if compact else None)
             _lib.check(lib.gsb200_backward(ctypes.byref(args)), "gsb200_backward")
+            own_view_grad_xyz = None
+            if compact:
+                if self.backward_valid_point_hook is not None:  # the hook sees this rank's own view (before the sum)
+                    own_view_grad_xyz = grad_sum[frame.point_id_in_camera_list.long(), 0:3]
+                exchange.run(grad_sum, blocks)
+                eargs = _lib.GsbExpandArgs(
+                    num_points=N, num_views=exchange.world, num_objects=ctx.num_objects, grad_sum=_ptr(grad_sum),
+                    grad_color_views=_ptr(blocks), view_stride=blocks.shape[1], pointcloud=_ptr(pointcloud),
+                    point_object_id=_ptr(point_object_id), color_max_sh_band=band_i,
+                    grad_color_factor=cfg.grad_color_factor,
+                    grad_high_order_color_factor=cfg.grad_high_order_color_factor,
+                    grad_pointcloud=_ptr(grad_pointcloud), grad_pointcloud_features=_ptr(grad_pointcloud_features),
+                    stream=stream.cuda_stream)
+                _lib.check(lib.gsb200_expand_view_gradients(ctypes.byref(eargs)), "gsb200_expand_view_gradients")
 
             hook = self.backward_valid_point_hook
             if hook is not None:  # GPCR:1127-1142
@@ -443,8 +475,8 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
                 acc = accum[:M]
                 hook(GaussianPointCloudRasterisation.BackwardValidPointHookInput(
                     point_id_in_camera_list=ids,
-                    grad_point_in_camera=grad_pointcloud[ids64],
-                    grad_pointfeatures_in_camera=grad_pointcloud_features[ids64],
+                    grad_point_in_camera=own_view_grad_xyz if compact else grad_pointcloud[ids64],
+                    grad_pointfeatures_in_camera=None if compact else grad_pointcloud_features[ids64],
                     grad_viewspace=acc[:, 0:2].contiguous(),
                     magnitude_grad_viewspace=acc[:, 9].contiguous(),
                     magnitude_grad_viewspace_on_image=magnitude_on_image,

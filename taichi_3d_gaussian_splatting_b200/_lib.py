@@ -15,6 +15,7 @@ GSB_FLAG_Q_ALREADY_NORMALISED = 4
 GSB_FLAG_KEEP_ALL_TILE_PAIRS = 8
 GSB_FLAG_BACKWARD_TRANSPOSED = 16  # experimental, csrc/blend_bwd_transposed.cu
 GSB_FLAG_NO_HOOK_STATS = 32
+GSB_FLAG_COMPACT_GRADS = 64
 
 c_i64, c_i32, c_u32, c_f32, c_vp = (ctypes.c_int64, ctypes.c_int32, ctypes.c_uint32, ctypes.c_float,
                                     ctypes.c_void_p)
@@ -59,6 +60,16 @@ class GsbBackwardArgs(ctypes.Structure):
         ("pixel_offset_of_last_effective_point", c_vp), ("accum", c_vp), ("accum_rows", c_i64),
         ("grad_pointcloud", c_vp), ("grad_pointcloud_features", c_vp),
         ("magnitude_grad_viewspace_on_image", c_vp), ("stream", c_vp),
+        ("grad_sum_compact", c_vp), ("grad_color_compact", c_vp),
+    ]
+
+
+class GsbExpandArgs(ctypes.Structure):
+    _fields_ = [
+        ("num_points", c_i64), ("num_views", c_i32), ("num_objects", c_i32), ("grad_sum", c_vp),
+        ("grad_color_views", c_vp), ("view_stride", c_i64), ("pointcloud", c_vp), ("point_object_id", c_vp),
+        ("color_max_sh_band", c_i32), ("grad_color_factor", c_f32), ("grad_high_order_color_factor", c_f32),
+        ("grad_pointcloud", c_vp), ("grad_pointcloud_features", c_vp), ("stream", c_vp),
     ]
 
 
@@ -68,7 +79,7 @@ EXPORTS = (
     "gsb200_stage_blend", "gsb200_sort_temp_bytes", "gsb200_sort_pairs", "gsb200_render_host", "gsb200_find_tile_start_and_end",
     "gsb200_forward_timed", "gsb200_backward_timed", "gsb200_abi_sizes", "gsb200_l1_loss_temp_bytes", "gsb200_l1_loss",
     "gsb200_image_loss_temp_bytes", "gsb200_image_loss", "gsb200_adam_step", "gsb200_controller_update",
-    "gsb200_forward_blend_work", "gsb200_backward_blend_work", "gsb200_device_selftest",
+    "gsb200_forward_blend_work", "gsb200_backward_blend_work", "gsb200_device_selftest", "gsb200_expand_view_gradients",
 )
 
 _lib = None
@@ -117,6 +128,8 @@ def load() -> ctypes.CDLL:
     lib.gsb200_forward_blend_work.restype = ctypes.c_int
     lib.gsb200_backward_blend_work.argtypes = [ctypes.POINTER(GsbBackwardArgs), ctypes.POINTER(ctypes.c_uint64)]
     lib.gsb200_backward_blend_work.restype = ctypes.c_int
+    lib.gsb200_expand_view_gradients.argtypes = [ctypes.POINTER(GsbExpandArgs)]
+    lib.gsb200_expand_view_gradients.restype = ctypes.c_int
     lib.gsb200_device_selftest.argtypes = [c_vp]
     lib.gsb200_device_selftest.restype = ctypes.c_int
     sizes = (c_i64 * 3)()

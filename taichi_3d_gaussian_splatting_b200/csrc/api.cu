@@ -247,12 +247,18 @@ int gsb200_backward(const GsbBackwardArgs *a) {
         set_error("backward: args is null");
         return GSB_EINVAL;
     }
+    const bool compact = (a->flags & GSB_FLAG_COMPACT_GRADS) != 0;
     if (!a->grad_rasterized_image || !a->pixel_accumulated_alpha ||
         !a->pixel_offset_of_last_effective_point || !a->magnitude_grad_viewspace_on_image ||
-        !a->camera_intrinsics || (a->num_points > 0 && (!a->grad_pointcloud || !a->grad_pointcloud_features ||
-                                                        !a->pointcloud || !a->pointcloud_features ||
-                                                        !a->point_object_id || !a->t_pointcloud_camera))) {
+        !a->camera_intrinsics ||
+        (a->num_points > 0 && (!a->pointcloud || !a->pointcloud_features || !a->point_object_id || !a->t_pointcloud_camera)) ||
+        (a->num_points > 0 && !compact && (!a->grad_pointcloud || !a->grad_pointcloud_features)) ||
+        (a->num_points > 0 && compact && (!a->grad_sum_compact || !a->grad_color_compact))) {
         set_error("backward: null pointer argument");
+        return GSB_EINVAL;
+    }
+    if (compact && reinterpret_cast<uintptr_t>(a->grad_sum_compact) % 16 != 0) {
+        set_error("backward: grad_sum_compact must be 16-byte aligned");
         return GSB_EINVAL;
     }
     if (a->accum_rows > 0 && !a->accum) {
@@ -269,6 +275,21 @@ int gsb200_backward(const GsbBackwardArgs *a) {
         GSB_CUDA_CHECK(cudaMemsetAsync(a->accum, 0, (size_t)a->accum_rows * GSB_ACCUM_FLOATS * 4, st));
     if ((rc = launch_blend_backward(*a, ws, st)) != GSB_OK) return rc;
     return launch_backward_points(*a, ws, st);
+}
+
+int gsb200_expand_view_gradients(const GsbExpandArgs *a) {
+    if (!a || a->num_points < 0 || a->num_views < 1 || a->num_objects < 1 ||
+        (a->num_points > 0 && (!a->grad_sum || !a->grad_color_views || !a->pointcloud || !a->point_object_id ||
+                               !a->grad_pointcloud || !a->grad_pointcloud_features)) ||
+        a->view_stride < 3 * a->num_points + 3 * (int64_t)a->num_objects) {
+        set_error("expand_view_gradients: bad arguments");
+        return GSB_EINVAL;
+    }
+    if (reinterpret_cast<uintptr_t>(a->grad_sum) % 16 != 0 || reinterpret_cast<uintptr_t>(a->grad_pointcloud_features) % 16 != 0) {
+        set_error("expand_view_gradients: grad_sum and grad_pointcloud_features must be 16-byte aligned");
+        return GSB_EINVAL;
+    }
+    return launch_expand_view_gradients(*a, static_cast<cudaStream_t>(a->stream));
 }
 
 // ---- diagnostic variants: same launches as gsb200_forward / gsb200_backward with a CUDA event recorded

@@ -316,6 +316,28 @@ int launch_blend_backward(const GsbBackwardArgs &a, const Workspace &ws, cudaStr
 #endif  // GSB_HOST_EMU
 
 // ------------------------------------------------------------------ loop B + P4
+// Real SH basis up to band 3 along the (un-normalised) direction (dx, dy, dz)  (SH:10-32; GPCR:731-732, 749)
+__device__ __forceinline__ void sh_basis(float dx, float dy, float dz, float (&sh)[16]) {
+    const float dinv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+    dx *= dinv; dy *= dinv; dz *= dinv;
+    sh[0] = 0.28209479177387814f;
+    sh[1] = -0.48860251190291987f * dy;
+    sh[2] = 0.48860251190291987f * dz;
+    sh[3] = -0.48860251190291987f * dx;
+    sh[4] = 1.0925484305920792f * dx * dy;
+    sh[5] = -1.0925484305920792f * dy * dz;
+    sh[6] = 0.94617469575755997f * dz * dz - 0.31539156525251999f;
+    sh[7] = -1.0925484305920792f * dx * dz;
+    sh[8] = 0.54627421529603959f * dx * dx - 0.54627421529603959f * dy * dy;
+    sh[9] = 0.59004358992664352f * dy * (-3.0f * dx * dx + dy * dy);
+    sh[10] = 2.8906114426405538f * dx * dy * dz;
+    sh[11] = 0.45704579946446572f * dy * (1.0f - 5.0f * dz * dz);
+    sh[12] = 0.3731763325901154f * dz * (5.0f * dz * dz - 3.0f);
+    sh[13] = 0.45704579946446572f * dx * (1.0f - 5.0f * dz * dz);
+    sh[14] = 1.4453057213202769f * dz * (dx * dx - dy * dy);
+    sh[15] = 0.59004358992664352f * dx * (-dx * dx + 3.0f * dy * dy);
+}
+
 struct PointsBwdParams {
     long long N;
     const int *point_offset;
@@ -332,12 +354,21 @@ struct PointsBwdParams {
     float q_f, s_f, a_f, c_f, h_f;
     float *grad_xyz;
     float *grad_feat;
+    float *grad_sum_compact;    // COMPACT: (N,12) xyz(3) q(4) s(3) logit(1) pad -- the columns that simply add up over views
+    float *grad_color_compact;  // COMPACT: (N,3) d L / d (SH colour argument), per VIEW (its SH basis depends on the camera centre)
 };
 
 #ifndef GSB_POINTS_THREADS
 #define GSB_POINTS_THREADS 128
 #endif
 constexpr int PT_ROW = 60;  // staged feature row stride in floats: 16-B aligned, float4 stores of 8 lanes hit 32 banks
+constexpr int PT_ROW_COMPACT = 20;  // COMPACT: 16 staged floats per row, same bank property
+// COMPACT = true (GSB_FLAG_COMPACT_GRADS, the view-parallel exchange of parallel.py): instead of the dense (N,3) / (N,56)
+// gradients the kernel writes, per scene row, the 11 values that add up over views -- xyz(3) q(4) s(3) logit(1), factors
+// applied -- and the 3 colour-argument gradients that must stay per view: the 48 SH gradients of a view are their outer product
+// with the view's SH basis, which gsb200_expand_view_gradients rebuilds AFTER the exchange (14 instead of 59 floats per row
+// cross NVLink, and this kernel writes 60 instead of 236 bytes per row).
+template <bool COMPACT>
 __global__ void __launch_bounds__(GSB_POINTS_THREADS, 6)  // 6 x 33 KB of staging per SM
 backward_points_kernel(const PointsBwdParams p) {
     // One thread per scene row: rows outside the frustum get their zeros here (no separate memset of the
@@ -345,19 +376,20 @@ backward_points_kernel(const PointsBwdParams p) {
     // contiguous 7 KB piece of the (N,56) gradient and 384 B of the (N,3) one: each lane stages its row in
     // shared memory and the warp then streams the piece out with full 512-B stores (a lane writing its own
     // 224-B row directly touches 32 different lines per store instruction and stalls on the LSU queue).
-    __shared__ __align__(16) float s_feat[GSB_POINTS_THREADS / 32][32 * PT_ROW];
+    constexpr int ROW = COMPACT ? PT_ROW_COMPACT : PT_ROW;
+    __shared__ __align__(16) float s_feat[GSB_POINTS_THREADS / 32][32 * ROW];
     __shared__ float s_xyz[GSB_POINTS_THREADS / 32][96];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *const my_feat = &s_feat[warp][lane * PT_ROW];
+    float *const my_feat = &s_feat[warp][lane * ROW];
     float *const my_xyz = &s_xyz[warp][lane * 3];
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long base = (long long)blockIdx.x * blockDim.x + warp * 32; base < p.N; base += stride) {
       const long long id = base + lane;
       const int o = id < p.N ? p.point_offset[id] : -1;
       if (o < 0) {
-          my_xyz[0] = 0.0f; my_xyz[1] = 0.0f; my_xyz[2] = 0.0f;
+          if (!COMPACT) { my_xyz[0] = 0.0f; my_xyz[1] = 0.0f; my_xyz[2] = 0.0f; }
 #pragma unroll
-          for (int k = 0; k < GSB_FEATURE_DIM / 4; ++k)
+          for (int k = 0; k < (COMPACT ? 4 : GSB_FEATURE_DIM / 4); ++k)
               reinterpret_cast<float4 *>(my_feat)[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       } else {
         const float4 *accp = reinterpret_cast<const float4 *>(p.accum + (size_t)o * GSB_ACCUM_FLOATS);
@@ -440,30 +472,19 @@ backward_points_kernel(const PointsBwdParams p) {
                 dM[4] * (-4 * sy * qz) + dM[5] * (2 * sz * qy) + dM[6] * (2 * sx * qx) + dM[7] * (2 * sy * qy);
         gq[3] = dM[1] * (-2 * sy * qz) + dM[2] * (2 * sz * qy) + dM[3] * (2 * sx * qz) + dM[5] * (-2 * sz * qx) +
                 dM[6] * (-2 * sx * qy) + dM[7] * (2 * sy * qx);
-        // SH basis along xyz - camera centre (GPCR:731-732, 749; SH:10-32)
-        float dx = x - p.t_pc_cam[3 * ob], dy = y - p.t_pc_cam[3 * ob + 1], dz = z - p.t_pc_cam[3 * ob + 2];
-        const float dinv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-        dx *= dinv; dy *= dinv; dz *= dinv;
-        float sh[16];
-        sh[0] = 0.28209479177387814f;
-        sh[1] = -0.48860251190291987f * dy;
-        sh[2] = 0.48860251190291987f * dz;
-        sh[3] = -0.48860251190291987f * dx;
-        sh[4] = 1.0925484305920792f * dx * dy;
-        sh[5] = -1.0925484305920792f * dy * dz;
-        sh[6] = 0.94617469575755997f * dz * dz - 0.31539156525251999f;
-        sh[7] = -1.0925484305920792f * dx * dz;
-        sh[8] = 0.54627421529603959f * dx * dx - 0.54627421529603959f * dy * dy;
-        sh[9] = 0.59004358992664352f * dy * (-3.0f * dx * dx + dy * dy);
-        sh[10] = 2.8906114426405538f * dx * dy * dz;
-        sh[11] = 0.45704579946446572f * dy * (1.0f - 5.0f * dz * dz);
-        sh[12] = 0.3731763325901154f * dz * (5.0f * dz * dz - 3.0f);
-        sh[13] = 0.45704579946446572f * dx * (1.0f - 5.0f * dz * dz);
-        sh[14] = 1.4453057213202769f * dz * (dx * dx - dy * dy);
-        sh[15] = 0.59004358992664352f * dx * (-dx * dx + 3.0f * dy * dy);
         // sigmoid'(.) from the stored colour: c (1 - c)  (UT:356-359)
         const float gcol[3] = {a1.y * (r2.x * (1.0f - r2.x)), a1.z * (r2.y * (1.0f - r2.y)),
                                a1.w * (r2.z * (1.0f - r2.z))};
+        if (COMPACT) {
+            float4 *gc = reinterpret_cast<float4 *>(my_feat);
+            gc[0] = make_float4(gx[0], gx[1], gx[2], gq[0] * p.q_f);
+            gc[1] = make_float4(gq[1] * p.q_f, gq[2] * p.q_f, gq[3] * p.q_f, gs[0] * p.s_f);
+            gc[2] = make_float4(gs[1] * p.s_f, gs[2] * p.s_f, a2.x * p.a_f, 0.0f);
+            gc[3] = make_float4(gcol[0], gcol[1], gcol[2], 0.0f);
+        } else {
+        // SH basis along xyz - camera centre (GPCR:731-732, 749; SH:10-32)
+        float sh[16];
+        sh_basis(x - p.t_pc_cam[3 * ob], y - p.t_pc_cam[3 * ob + 1], z - p.t_pc_cam[3 * ob + 2], sh);
 
         my_xyz[0] = gx[0]; my_xyz[1] = gx[1]; my_xyz[2] = gx[2];
         float4 *gf = reinterpret_cast<float4 *>(my_feat);
@@ -481,16 +502,31 @@ backward_points_kernel(const PointsBwdParams p) {
             for (int k4 = 0; k4 < 4; ++k4)
                 gf[2 + 4 * ch + k4] = make_float4(o16[4 * k4], o16[4 * k4 + 1], o16[4 * k4 + 2], o16[4 * k4 + 3]);
         }
+        }
       }
       __syncwarp();
-      // stream the warp's 32 rows out: 14 x 512 B of feature gradients, 3 x 128 B of position gradients
       const long long rows = p.N - base < 32 ? p.N - base : 32;
+      if (COMPACT) {
+          // 32 rows -> 3 x 512 B of summable columns, 3 x 128 B of per-view colour gradients
+          float4 *const out_s = reinterpret_cast<float4 *>(p.grad_sum_compact + 12 * (size_t)base);
+          float *const out_c = p.grad_color_compact + 3 * (size_t)base;
+#pragma unroll
+          for (int it = 0; it < 3; ++it) {
+              const int f = it * 32 + lane;
+              const int row = f / 3, c = f - row * 3;
+              if (row < rows) {
+                  out_s[f] = *reinterpret_cast<const float4 *>(&s_feat[warp][row * ROW + 4 * c]);
+                  out_c[f] = s_feat[warp][row * ROW + 12 + c];
+              }
+          }
+      } else {
+      // stream the warp's 32 rows out: 14 x 512 B of feature gradients, 3 x 128 B of position gradients
       float4 *const out_f = reinterpret_cast<float4 *>(p.grad_feat + (size_t)GSB_FEATURE_DIM * base);
 #pragma unroll
       for (int it = 0; it < GSB_FEATURE_DIM / 4; ++it) {
           const int f = it * 32 + lane;           // float4 index inside the piece
           const int row = f / (GSB_FEATURE_DIM / 4), c4 = f - row * (GSB_FEATURE_DIM / 4);
-          if (row < rows) out_f[f] = *reinterpret_cast<const float4 *>(&s_feat[warp][row * PT_ROW + 4 * c4]);
+          if (row < rows) out_f[f] = *reinterpret_cast<const float4 *>(&s_feat[warp][row * ROW + 4 * c4]);
       }
       float *const out_x = p.grad_xyz + 3 * (size_t)base;
 #pragma unroll
@@ -498,11 +534,98 @@ backward_points_kernel(const PointsBwdParams p) {
           const int f = it * 32 + lane;
           if (f < 3 * rows) out_x[f] = s_xyz[warp][f];
       }
+      }
       __syncwarp();
     }
 }
 
+// ------------------------------------------------------------------ view-parallel exchange: rebuild the dense gradients
+// After the exchange of the COMPACT rows (parallel.py): grad_sum holds the sum over views of xyz / q / s / logit gradients,
+// grad_color_views the per-view colour-argument gradients (3 per row) followed by that view's camera centres.  The SH
+// gradient of a view is gcol (x) SH basis(direction from the view's camera centre) * factor (GPCR:749-756, 1105-1125,
+// 1167-1182) -- exactly what the dense kernel writes per view -- summed here over the views in rank order (deterministic).
+struct ExpandParams {
+    long long N;
+    int R;
+    const float *grad_sum;
+    const float *grad_color_views;
+    long long view_stride;  // floats between two views' blocks
+    const float *xyz;
+    const int *obj_id;
+    int first_cleared;
+    float c_f, h_f;
+    float *grad_xyz;
+    float *grad_feat;
+};
+
+__global__ void __launch_bounds__(GSB_POINTS_THREADS, 4)
+expand_view_gradients_kernel(const ExpandParams p) {
+    __shared__ __align__(16) float s_feat[GSB_POINTS_THREADS / 32][32 * PT_ROW];
+    __shared__ float s_xyz[GSB_POINTS_THREADS / 32][96];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *const my_feat = &s_feat[warp][lane * PT_ROW];
+    float *const my_xyz = &s_xyz[warp][lane * 3];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long base = (long long)blockIdx.x * blockDim.x + warp * 32; base < p.N; base += stride) {
+        const long long id = base + lane;
+        if (id < p.N) {
+            const float4 *srow = reinterpret_cast<const float4 *>(p.grad_sum + 12 * (size_t)id);
+            const float4 s0 = __ldg(srow), s1 = __ldg(srow + 1), s2 = __ldg(srow + 2);
+            my_xyz[0] = s0.x; my_xyz[1] = s0.y; my_xyz[2] = s0.z;
+            float4 *gf = reinterpret_cast<float4 *>(my_feat);
+            gf[0] = make_float4(s0.w, s1.x, s1.y, s1.z);
+            gf[1] = make_float4(s1.w, s2.x, s2.y, s2.z);
+            float acc[3][16];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                for (int k = 0; k < 16; ++k) acc[ch][k] = 0.0f;
+            const float x = p.xyz[3 * (size_t)id], y = p.xyz[3 * (size_t)id + 1], z = p.xyz[3 * (size_t)id + 2];
+            const int ob = p.obj_id[id];
+#pragma unroll 1
+            for (int v = 0; v < p.R; ++v) {
+                const float *blk = p.grad_color_views + (size_t)v * p.view_stride;
+                const float g[3] = {__ldg(blk + 3 * (size_t)id), __ldg(blk + 3 * (size_t)id + 1), __ldg(blk + 3 * (size_t)id + 2)};
+                if (g[0] == 0.0f && g[1] == 0.0f && g[2] == 0.0f) continue;  // outside this view's frustum
+                const float *centre = blk + 3 * (size_t)p.N + 3 * ob;
+                float sh[16];
+                sh_basis(x - __ldg(centre), y - __ldg(centre + 1), z - __ldg(centre + 2), sh);
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) acc[ch][k] += g[ch] * sh[k] * (k == 0 ? p.c_f : p.h_f);
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4)
+                    gf[2 + 4 * ch + k4] = make_float4(4 * k4 < p.first_cleared ? acc[ch][4 * k4] : 0.0f,
+                                                      4 * k4 + 1 < p.first_cleared ? acc[ch][4 * k4 + 1] : 0.0f,
+                                                      4 * k4 + 2 < p.first_cleared ? acc[ch][4 * k4 + 2] : 0.0f,
+                                                      4 * k4 + 3 < p.first_cleared ? acc[ch][4 * k4 + 3] : 0.0f);
+        }
+        __syncwarp();
+        const long long rows = p.N - base < 32 ? p.N - base : 32;
+        float4 *const out_f = reinterpret_cast<float4 *>(p.grad_feat + (size_t)GSB_FEATURE_DIM * base);
+#pragma unroll
+        for (int it = 0; it < GSB_FEATURE_DIM / 4; ++it) {
+            const int f = it * 32 + lane;
+            const int row = f / (GSB_FEATURE_DIM / 4), c4 = f - row * (GSB_FEATURE_DIM / 4);
+            if (row < rows) out_f[f] = *reinterpret_cast<const float4 *>(&s_feat[warp][row * PT_ROW + 4 * c4]);
+        }
+        float *const out_x = p.grad_xyz + 3 * (size_t)base;
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const int f = it * 32 + lane;
+            if (f < 3 * rows) out_x[f] = s_xyz[warp][f];
+        }
+        __syncwarp();
+    }
+}
+
 #ifndef GSB_HOST_EMU
+static int first_cleared_of_band(int band) { return band <= 0 ? 1 : band == 1 ? 4 : band == 2 ? 9 : 16; }
+
 int launch_backward_points(const GsbBackwardArgs &a, const Workspace &ws, cudaStream_t stream) {
     if (a.num_points <= 0) return GSB_OK;
     PointsBwdParams p;
@@ -517,8 +640,7 @@ int launch_backward_points(const GsbBackwardArgs &a, const Workspace &ws, cudaSt
     p.obj_id = a.point_object_id;
     p.t_pc_cam = a.t_pointcloud_camera;
     p.K = a.camera_intrinsics;
-    const int band = a.color_max_sh_band;
-    p.first_cleared = band <= 0 ? 1 : band == 1 ? 4 : band == 2 ? 9 : 16;
+    p.first_cleared = first_cleared_of_band(a.color_max_sh_band);
     p.q_f = a.grad_q_factor;
     p.s_f = a.grad_s_factor;
     p.a_f = a.grad_alpha_factor;
@@ -526,11 +648,37 @@ int launch_backward_points(const GsbBackwardArgs &a, const Workspace &ws, cudaSt
     p.h_f = a.grad_high_order_color_factor;
     p.grad_xyz = a.grad_pointcloud;
     p.grad_feat = a.grad_pointcloud_features;
+    p.grad_sum_compact = a.grad_sum_compact;
+    p.grad_color_compact = a.grad_color_compact;
     long long blocks = (a.num_points + GSB_POINTS_THREADS - 1) / GSB_POINTS_THREADS;
     const long long cap = 16LL * num_sms();
     if (blocks > cap) blocks = cap;
     if (blocks <= 0) return GSB_OK;
-    backward_points_kernel<<<(int)blocks, GSB_POINTS_THREADS, 0, stream>>>(p);
+    if (a.flags & GSB_FLAG_COMPACT_GRADS) backward_points_kernel<true><<<(int)blocks, GSB_POINTS_THREADS, 0, stream>>>(p);
+    else backward_points_kernel<false><<<(int)blocks, GSB_POINTS_THREADS, 0, stream>>>(p);
+    GSB_CUDA_CHECK(cudaGetLastError());
+    return GSB_OK;
+}
+
+int launch_expand_view_gradients(const GsbExpandArgs &a, cudaStream_t stream) {
+    if (a.num_points <= 0) return GSB_OK;
+    ExpandParams p;
+    p.N = a.num_points;
+    p.R = a.num_views;
+    p.grad_sum = a.grad_sum;
+    p.grad_color_views = a.grad_color_views;
+    p.view_stride = a.view_stride;
+    p.xyz = a.pointcloud;
+    p.obj_id = a.point_object_id;
+    p.first_cleared = first_cleared_of_band(a.color_max_sh_band);
+    p.c_f = a.grad_color_factor;
+    p.h_f = a.grad_high_order_color_factor;
+    p.grad_xyz = a.grad_pointcloud;
+    p.grad_feat = a.grad_pointcloud_features;
+    long long blocks = (a.num_points + GSB_POINTS_THREADS - 1) / GSB_POINTS_THREADS;
+    const long long cap = 16LL * num_sms();
+    if (blocks > cap) blocks = cap;
+    expand_view_gradients_kernel<<<(int)blocks, GSB_POINTS_THREADS, 0, stream>>>(p);
     GSB_CUDA_CHECK(cudaGetLastError());
     return GSB_OK;
 }

@@ -68,6 +68,7 @@ int launch_tile_ranges_raw(const long long *keys_i64, int64_t n, int *tile_start
 int launch_blend_forward(const GsbForwardArgs &a, const Workspace &ws, cudaStream_t stream);
 int launch_blend_backward(const GsbBackwardArgs &a, const Workspace &ws, cudaStream_t stream);
 int launch_backward_points(const GsbBackwardArgs &a, const Workspace &ws, cudaStream_t stream);
+int launch_expand_view_gradients(const GsbExpandArgs &a, cudaStream_t stream);
 int launch_blend_forward_count(const GsbForwardArgs &a, const Workspace &ws, unsigned long long *counters_dev,
                                cudaStream_t stream);
 int launch_blend_backward_work(const GsbBackwardArgs &a, const Workspace &ws, unsigned long long *counters_dev,

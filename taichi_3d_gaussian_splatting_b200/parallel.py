@@ -3,8 +3,19 @@
 The reference is single-GPU and renders one view per step (GaussianPointTrainer.py:120-166).  The path
 shards naturally by VIEW: every rank holds a full replica of the scene, view ``i`` is
 rendered by rank ``i mod R``, inference needs no communication, and training needs exactly one exchange
-step per optimiser step -- the sum of the dense per-Gaussian gradients (N,3)+(N,56) over ranks, one
-NCCL all-reduce over NVLink (gloo on CPU in the tests).
+step per optimiser step: the sum over ranks of the per-Gaussian gradients (N,3)+(N,56).
+
+Two ways to do that exchange:
+* :func:`exchange_gradients` -- one all-reduce of the dense 59 floats per Gaussian (236 MB at 1e6 Gaussians);
+* :class:`ViewParallelExchange` (what ``bench.py --gpus N`` uses), plugged INTO the operator's backward
+  (``GaussianPointCloudRasterisation(..., gradient_exchange=...)``): 48 of the 56 feature gradients of a view are the
+  outer product of 3 colour-argument gradients with the view's 16 SH basis values, and the basis depends only on the
+  Gaussian's position and the view's camera centre, which every rank knows.  So the per-point kernel writes COMPACT rows
+  (``GSB_FLAG_COMPACT_GRADS``), the ranks all-reduce the 11 columns that simply add up (xyz, q, s, logit) and all-gather
+  the 3 colour-argument gradients plus the camera centres, and ``gsb200_expand_view_gradients`` rebuilds the dense sum on
+  every rank: 14 instead of 59 floats per Gaussian cross NVLink (north_star: "NCCL all-gather only for the per-Gaussian
+  gradient reduction"), and the per-point kernel writes 60 instead of 236 bytes per row.  Exact (same products, summed in
+  rank order), not an approximation.
 """
 from typing import Iterable, List, Optional, Sequence
 
@@ -56,6 +67,31 @@ def exchange_gradients(grads: Iterable[Optional[torch.Tensor]], group=None, aver
                 h.wait()
             g.div_(world)
     return handles if async_op else None
+
+
+class ViewParallelExchange:
+    """The collectives of the compact exchange.  ``gradient_exchange=ViewParallelExchange(group)`` on the operator of every
+    rank makes ``backward`` return -- and ``.grad`` receive -- the gradients summed over the ranks' views.
+
+    ``run(grad_sum, blocks)``: ``grad_sum`` (N,12) f32 is summed over ranks in place; ``blocks`` (R, stride) f32 holds this
+    rank's ``[3N colour-argument gradients | 3 n_obj camera centres]`` in row ``rank`` and receives the other ranks' rows
+    (in-place all-gather: the send buffer is the rank's slot of the receive buffer)."""
+
+    def __init__(self, group=None):
+        if not dist.is_available() or not dist.is_initialized():
+            raise RuntimeError("ViewParallelExchange needs an initialised torch.distributed process group")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def run(self, grad_sum: torch.Tensor, blocks: torch.Tensor) -> None:
+        if blocks.shape[0] != self.world or not blocks.is_contiguous() or not grad_sum.is_contiguous():
+            raise ValueError("blocks must be a contiguous (world, stride) tensor and grad_sum contiguous")
+        dist.all_reduce(grad_sum, op=dist.ReduceOp.SUM, group=self.group)
+        mine = blocks[self.rank]
+        if not mine.is_cuda:  # gloo (CPU tests): no in-place all-gather
+            mine = mine.clone()
+        dist.all_gather_into_tensor(blocks.view(-1), mine, group=self.group)
 
 
 def render_views(op, make_input, view_ids: Sequence[int]):

@@ -74,12 +74,14 @@ extern "C" long long emu_blend_forward(int rgb_only, int exact_exp, int H, int W
     return simt_emu::M().switches;
 }
 
-// loop B + P4 (per-point chain rule, SH-band masking, gradient factors): backward_points_kernel of blend_bwd.cu
+// loop B + P4 (per-point chain rule, SH-band masking, gradient factors): backward_points_kernel of blend_bwd.cu; with
+// grad_sum / grad_col non-null the COMPACT instantiation (view-parallel exchange) instead of the dense one
 extern "C" long long emu_backward_points(long long N, const int *point_offset, const float *records,
                                          const float *point_in_camera, const float *accum, const float *poses,
                                          const float *xyz, const float *features, const int *obj_id,
                                          const float *t_pc_cam, const float *K, int color_max_sh_band, float q_f, float s_f,
-                                         float a_f, float c_f, float h_f, float *grad_xyz, float *grad_feat) {
+                                         float a_f, float c_f, float h_f, float *grad_xyz, float *grad_feat, float *grad_sum,
+                                         float *grad_col) {
     using namespace gsb;
     PointsBwdParams p;
     p.N = N;
@@ -102,9 +104,39 @@ extern "C" long long emu_backward_points(long long N, const int *point_offset, c
     p.h_f = h_f;
     p.grad_xyz = grad_xyz;
     p.grad_feat = grad_feat;
+    p.grad_sum_compact = grad_sum;
+    p.grad_color_compact = grad_col;
     simt_emu::M().switches = 0;
     const int blocks = (int)std::min<long long>((N + GSB_POINTS_THREADS - 1) / GSB_POINTS_THREADS, 16 * 148);
-    if (N > 0) simt_emu::launch(backward_points_kernel, blocks, GSB_POINTS_THREADS, p);
+    if (N > 0) {
+        if (grad_sum) simt_emu::launch(backward_points_kernel<true>, blocks, GSB_POINTS_THREADS, p);
+        else simt_emu::launch(backward_points_kernel<false>, blocks, GSB_POINTS_THREADS, p);
+    }
+    return simt_emu::M().switches;
+}
+
+// gsb200_expand_view_gradients: dense gradients of a batch of views from the exchanged compact rows
+extern "C" long long emu_expand_view_gradients(long long N, int R, const float *grad_sum, const float *grad_color_views,
+                                               long long view_stride, const float *xyz, const int *obj_id,
+                                               int color_max_sh_band, float c_f, float h_f, float *grad_xyz, float *grad_feat) {
+    using namespace gsb;
+    ExpandParams p;
+    p.N = N;
+    p.R = R;
+    p.grad_sum = grad_sum;
+    p.grad_color_views = grad_color_views;
+    p.view_stride = view_stride;
+    p.xyz = xyz;
+    p.obj_id = obj_id;
+    const int band = color_max_sh_band;
+    p.first_cleared = band <= 0 ? 1 : band == 1 ? 4 : band == 2 ? 9 : 16;
+    p.c_f = c_f;
+    p.h_f = h_f;
+    p.grad_xyz = grad_xyz;
+    p.grad_feat = grad_feat;
+    simt_emu::M().switches = 0;
+    const int blocks = (int)std::min<long long>((N + GSB_POINTS_THREADS - 1) / GSB_POINTS_THREADS, 16 * 148);
+    if (N > 0) simt_emu::launch(expand_view_gradients_kernel, blocks, GSB_POINTS_THREADS, p);
     return simt_emu::M().switches;
 }
 

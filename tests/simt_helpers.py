@@ -26,6 +26,7 @@ def build_emulator():
     L.emu_blend_forward.restype = ctypes.c_longlong
     L.emu_preprocess.restype = ctypes.c_longlong
     L.emu_backward_points.restype = ctypes.c_longlong
+    L.emu_expand_view_gradients.restype = ctypes.c_longlong
     L.emu_sort_pairs.restype = ctypes.c_longlong
     L.emu_image_loss.restype = ctypes.c_longlong
     L.emu_image_loss_temp_bytes.restype = ctypes.c_longlong
@@ -110,8 +111,10 @@ def emulated_forward(emu, scene, cfg=None, exact=True, filter_tiles=True):
                            last_effective=last, count=cnt, exact=exact, scene=scene)
 
 
-def emulated_backward(emu, st, grad_image, band=3, transposed=False, factors=(1.0, 0.5, 20.0, 5.0, 1.0), stats=True):
-    """Backward for a state of :func:`emulated_forward`: dense gradients + the hook tensors."""
+def emulated_backward(emu, st, grad_image, band=3, transposed=False, factors=(1.0, 0.5, 20.0, 5.0, 1.0), stats=True,
+                      compact=False):
+    """Backward for a state of :func:`emulated_forward`: dense gradients + the hook tensors; ``compact``: the COMPACT
+    per-point kernel instead (GSB_FLAG_COMPACT_GRADS): returns (grad_sum (N,12), grad_colour (N,3), None)."""
     pre, scene, M = st.pre, st.scene, st.M
     H, W = pre.H, pre.W
     g = np.ascontiguousarray(grad_image, dtype=np.float32)
@@ -129,9 +132,15 @@ def emulated_backward(emu, st, grad_image, band=3, transposed=False, factors=(1.
     obj = scene.point_object_id.numpy().astype(np.int32).copy()
     gx, gf = np.full((N, 3), 7.0, np.float32), np.full((N, 56), 7.0, np.float32)  # every row must be overwritten
     f = ctypes.c_float
+    if compact:
+        gsum, gcol = np.full((N, 12), 7.0, np.float32), np.full((N, 3), 7.0, np.float32)
+        emu.emu_backward_points(ctypes.c_longlong(N), c(pre.point_offset), c(pre.records), c(pre.pic), c(accum), c(poses), c(xyz),
+                                c(pre.feats), c(obj), c(t), c(K), int(band) if band in (0, 1, 2) else 3, *(f(v) for v in factors),
+                                None, None, c(gsum), c(gcol))
+        return gsum, gcol, None
     emu.emu_backward_points(ctypes.c_longlong(N), c(pre.point_offset), c(pre.records), c(pre.pic), c(accum), c(poses), c(xyz),
                             c(pre.feats), c(obj), c(t), c(K), int(band) if band in (0, 1, 2) else 3, *(f(v) for v in factors),
-                            c(gx), c(gf))
+                            c(gx), c(gf), None, None)
     ids = pre.point_id[:M]
     hook = SimpleNamespace(grad_point_in_camera=gx[ids], grad_pointfeatures_in_camera=gf[ids], grad_viewspace=accum[:M, 0:2].copy(),
                            magnitude_grad_viewspace=accum[:M, 9].copy(), magnitude_grad_viewspace_on_image=mag,

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in gsb200.h but not exported by libgsb200.so"
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
-    assert lib.gsb200_version() == 100
+    assert lib.gsb200_version() == 101
 
 
 def test_workspace_layout_arithmetic():

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from taichi_3d_gaussian_splatting_b200.parallel import exchange_gradients, shard_views
+from taichi_3d_gaussian_splatting_b200.parallel import ViewParallelExchange, exchange_gradients, shard_views
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -41,7 +41,15 @@ def _worker(rank, world, port, out_dir):
     handles = exchange_gradients([torch.ones(3)], async_op=True)
     for h in handles:
         h.wait()
-    torch.save({"xyz": g_xyz, "feat": g_feat, "avg": g_avg, "views": shard_views(8, rank, world), "flat": flat, "other": other},
+    # the compact exchange: (N,12) summable columns all-reduced, the per-view blocks all-gathered into their rank's slot
+    ex = ViewParallelExchange()
+    assert (ex.world, ex.rank) == (world, rank)
+    gsum = torch.full((n, 12), float(rank + 1))
+    blocks = torch.full((world, 3 * n + 8), -1.0)
+    blocks[rank] = torch.arange(3 * n + 8, dtype=torch.float32) + 1000.0 * rank
+    ex.run(gsum, blocks)
+    torch.save({"xyz": g_xyz, "feat": g_feat, "avg": g_avg, "views": shard_views(8, rank, world), "flat": flat, "other": other,
+                "gsum": gsum, "blocks": blocks},
                os.path.join(out_dir, f"rank{rank}.pt"))
     dist.destroy_process_group()
 
@@ -59,6 +67,9 @@ def test_gradient_exchange_world2_gloo(tmp_path):
         expect = torch.arange(20, dtype=torch.float32) * 3
         expect[:6] *= 2  # `va` went through the second (per-tensor) exchange: both ranks held x3, sum = x6
         assert torch.equal(o["flat"], expect) and torch.equal(o["other"], torch.full((4,), 3.0))
+        assert torch.equal(o["gsum"], torch.full((n, 12), 3.0))
+        for r in range(world):
+            assert torch.equal(o["blocks"][r], torch.arange(3 * n + 8, dtype=torch.float32) + 1000.0 * r)
     assert sorted(outs[0]["views"] + outs[1]["views"]) == list(range(8))
 
 
