@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--repeats", type=int, default=10, help="extra timed regions of --steps steps each (median / p10 / p90)")
+    ap.add_argument("--exchange-streams", type=int, default=1, choices=[1, 2],
+                    help="N > 1: 2 = the all-gather of the compact exchange on a second NCCL communicator, concurrent with the all-reduce")
     ap.add_argument("--dense-exchange", action="store_true",
                     help="N > 1: one all-reduce of the dense gradients instead of the compact exchange (comparison)")
     return ap.parse_args()
@@ -222,7 +224,9 @@ def run_b200(args):
     warmup = max(args.warmup, 3)
     steps = args.steps
     Input = GPCR.GaussianPointCloudRasterisationInput
-    exchange = ViewParallelExchange() if (world > 1 and not args.dense_exchange) else None
+    exchange = None
+    if world > 1 and not args.dense_exchange:
+        exchange = ViewParallelExchange(gather_group=dist.new_group() if args.exchange_streams == 2 else None)
 
     def barrier():
         if world > 1:
@@ -313,11 +317,22 @@ def run_b200(args):
         image, _, _ = dense_op(wl.dev_input)
         image.backward(wl.grad_image)
         exchange_gradients([scene.point_cloud.grad, scene.point_cloud_features.grad], fused_buffer=dense_op.last_gradient_buffer)
-        ref_x, ref_f = scene.point_cloud.grad, scene.point_cloud_features.grad
-        err = torch.stack([(got_x - ref_x).abs().max() / ref_x.abs().max(), (got_f - ref_f).abs().max() / ref_f.abs().max()])
+        ref_x, ref_f = scene.point_cloud.grad.clone(), scene.point_cloud_features.grad.clone()
+        # the same dense step once more: the run-to-run noise of loop A's float atomics (the yardstick for the error above)
+        scene.point_cloud.grad = None
+        scene.point_cloud_features.grad = None
+        image, _, _ = dense_op(wl.dev_input)
+        image.backward(wl.grad_image)
+        exchange_gradients([scene.point_cloud.grad, scene.point_cloud_features.grad], fused_buffer=dense_op.last_gradient_buffer)
+        ag_x, ag_f = scene.point_cloud.grad, scene.point_cloud_features.grad
+        err = torch.stack([(got_x - ref_x).abs().max() / ref_x.abs().max(), (got_f - ref_f).abs().max() / ref_f.abs().max(),
+                           (ag_x - ref_x).abs().max() / ref_x.abs().max(), (ag_f - ref_f).abs().max() / ref_f.abs().max()])
         dist.all_reduce(err, op=dist.ReduceOp.MAX)
         exchange_check = {"max_abs_err_over_max_abs_grad_xyz": float(err[0]), "max_abs_err_over_max_abs_grad_features": float(err[1]),
-                          "what": "compact exchange vs one NCCL all-reduce of the dense gradients, same step, max over ranks"}
+                          "dense_rerun_noise_xyz": float(err[2]), "dense_rerun_noise_features": float(err[3]),
+                          "what": "compact exchange vs one NCCL all-reduce of the dense gradients of another run of the same step, max "
+                                  "over ranks; *_noise = two runs of the DENSE path against each other (float atomics of loop A land in "
+                                  "a different order every run)"}
         # and the dense exchange timed the same way, for the comparison in the line
         def dense_step():
             scene.point_cloud.grad = None
@@ -549,7 +564,9 @@ def run_b200(args):
         parallelism = "single GPU"
     elif exchange is not None:
         parallelism = (f"view-parallel x{world}: compact gradient exchange inside backward (NCCL all-reduce of (N,12) + all-gather "
-                       f"of (N,3) + camera centres, then gsb200_expand_view_gradients)")
+                       f"of (N,3) + camera centres"
+                       f"{', the two collectives concurrently on two communicators' if args.exchange_streams == 2 else ''}, then "
+                       f"gsb200_expand_view_gradients)")
     else:
         parallelism = f"view-parallel x{world}: one NCCL all-reduce of the dense (N,59) gradients"
     line = {

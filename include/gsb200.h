@@ -159,6 +159,15 @@ typedef struct GsbBackwardArgs {
      * with this view's SH basis, GPCR:749-756). */
     float *grad_sum_compact;
     float *grad_color_compact;
+    /* Optional, all NULL or all set: the densification controller's accumulators (GaussianPointAdaptiveController.py:108-116),
+     * updated for every in-camera point in the epilogue of the per-point kernel exactly as GaussianPointAdaptiveController.update
+     * does from the hook tensors (:130-143) -- no gathers, no extra launch.  (N) each, accumulated_position_gradients (N,3). */
+    int32_t *ctl_accumulated_num_in_camera;
+    int32_t *ctl_accumulated_num_pixels;
+    float *ctl_accumulated_view_space_position_gradients;
+    float *ctl_accumulated_view_space_position_gradients_avg;
+    float *ctl_accumulated_position_gradients;
+    float *ctl_accumulated_position_gradients_norm;
 } GsbBackwardArgs;
 
 /* View-parallel training (the reference is single-GPU): after the ranks have exchanged their COMPACT rows --
@@ -189,6 +198,8 @@ const char *gsb200_last_error(void);
 /* sizeof(GsbWorkspaceLayout), sizeof(GsbForwardArgs), sizeof(GsbBackwardArgs) as compiled: lets a
  * foreign-language binding verify its struct mirrors. */
 void gsb200_abi_sizes(int64_t *out3);
+/* ... and of the first n of {GsbWorkspaceLayout, GsbForwardArgs, GsbBackwardArgs, GsbExpandArgs, GsbTrainStepArgs} */
+void gsb200_abi_sizes_ext(int64_t *out, int32_t n);
 
 /* Workspace sizing.  far_plane*depth_to_sort_key_scale fixes the depth-key width; (H/16)*(W/16)
  * the tile-id width; both <= 32 bits total selects 32-bit sort keys. */
@@ -210,6 +221,30 @@ int gsb200_forward(const GsbForwardArgs *args);
 int gsb200_backward(const GsbBackwardArgs *args);
 
 int gsb200_expand_view_gradients(const GsbExpandArgs *args);
+
+/* One WHOLE training iteration of the reference loop (GaussianPointTrainer.py:138-180) enqueued by one call, without any host
+ * interaction: forward (gsb200_forward) -> clamp + L1 + D-SSIM loss and its gradient (gsb200_image_loss, LossFunction.py:20-38
+ * without the optional scale regulariser) -> backward (gsb200_backward, with the controller accumulators if set) -> Adam on the
+ * features and on the positions (gsb200_adam_step, GaussianPointTrainer.py:126-129, 176-177).  The scene tensors of `forward`
+ * are updated in place.  `backward` must describe the same frame (same scene / workspace / sizes), with
+ * grad_rasterized_image = the (H,W,3) buffer the loss gradient is written to and accum_rows >= num_points (the number of
+ * in-camera points is not known on the host).  If the frame needs more (tile, splat) pairs than forward.key_capacity the
+ * device-side overflow counter makes the accumulator update and both Adam steps no-ops; the host sees it in
+ * forward.host_counters[2] (async copy, never waited on here) and must repeat the iteration with a larger capacity. */
+typedef struct GsbTrainStepArgs {
+    GsbForwardArgs forward;
+    GsbBackwardArgs backward;
+    const float *ground_truth_image; /* (3,H,W) as the dataset yields it */
+    float lambda_value;              /* LossFunction.py:23 */
+    float *loss_out3;                /* device: {loss, L1, 1 - SSIM} */
+    void *loss_temp;                 /* gsb200_image_loss_temp_bytes(H, W), first 16 bytes zero before the first use */
+    int64_t loss_temp_bytes;
+    float *feature_exp_avg, *feature_exp_avg_sq;   /* (N,56) Adam state, zero before the first step */
+    float *position_exp_avg, *position_exp_avg_sq; /* (N,3) */
+    double feature_learning_rate, position_learning_rate, beta1, beta2, eps;
+    int32_t step;                    /* 1-based Adam step count */
+} GsbTrainStepArgs;
+int gsb200_train_step(const GsbTrainStepArgs *args);
 
 /* Individual stages (same workspace), for tests and profiling. */
 int gsb200_stage_preprocess(const GsbForwardArgs *args);   /* K1+P1+K2+K3+P2+K4 fused */

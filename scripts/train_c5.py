@@ -47,19 +47,82 @@ scene = GaussianPointCloudScene.from_parquet(tmp, GaussianPointCloudScene.PointC
 cfg = GaussianPointCloudTrainer.TrainConfig(num_iterations=iters, feature_learning_rate=5e-3, position_learning_rate=1e-5,
                                             position_learning_rate_decay_rate=0.9947, rasterisation_config=rast_cfg)
 ac = cfg.adaptive_controller_config
-ac.num_iterations_warm_up, ac.num_iterations_densify = 1000, 100
+ac.num_iterations_densify = 100
 ac.densification_view_space_position_gradients_threshold = 3e-6
 ac.transparent_alpha_threshold, ac.reset_alpha_value, ac.num_iterations_reset_alpha = -2.0, -1.9, 4000
 cfg.loss_function_config.enable_regularization = False
-fused = "--fused" in sys.argv  # fused image loss (gsb200_image_loss), Adam (gsb200_adam_step) and controller update (gsb200_controller_update)
-trainer = GaussianPointCloudTrainer(cfg, scene, views, fused_image_loss=fused, fused_adam=fused, fused_controller_update=fused)
+def opt(name, default=None, cast=str):
+    return cast(sys.argv[sys.argv.index(name) + 1]) if name in sys.argv else default
+
+
+# modes: autograd (operator + torch loss + torch Adam + hook-fed controller), --fused (fused loss / Adam / controller kernels
+# behind autograd), --fused-step (the whole iteration as ONE library call, gsb200_train_step)
+fused = "--fused" in sys.argv
+fused_step = "--fused-step" in sys.argv
+warm_up = opt("--warm-up", 1000, int)           # 1000 = the Truck YAML (no densification inside 1k iterations); e.g. 300 exercises it
+ac.num_iterations_warm_up = warm_up
+parity_iters = opt("--oracle-parity", 0, int)   # also train the first K iterations with the CPU oracle behind the same trainer
+shuffle = torch.Generator().manual_seed(7) if "--shuffle" in sys.argv else None
+
+
+def make_trainer(scene_, views_, **kw):
+    return GaussianPointCloudTrainer(cfg, scene_, views_, generator=torch.Generator(device=scene_.point_cloud.device).manual_seed(1),
+                                     shuffle_generator=shuffle, **kw)
+
+
+result = {"config": "C5 tat_truck_every_8_test.yaml shapes, synthetic targets", "iterations": iters,
+          "mode": "fused-step" if fused_step else "fused-kernels" if fused else "autograd", "densification_warm_up": warm_up,
+          "view_order": "shuffled per epoch" if shuffle is not None else "fixed"}
+
+if parity_iters:
+    # PSNR parity against the reference arithmetic: the SAME trainer, data and initial state with the CPU oracle behind the
+    # rasteriser interface (tests/oracle_module.py; test infrastructure, imported by this script only) for the first K iterations
+    import copy
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_module import OracleRasterisationModule
+    from taichi_3d_gaussian_splatting_b200.trainer import Scene
+    cfg_k = copy.deepcopy(cfg)
+    cfg_k.num_iterations = parity_iters
+    cpu_scene = Scene(point_cloud=scene.point_cloud.detach().cpu().clone().requires_grad_(True),
+                      point_cloud_features=scene.point_cloud_features.detach().cpu().clone().requires_grad_(True),
+                      point_invalid_mask=scene.point_invalid_mask.cpu().clone(), point_object_id=scene.point_object_id.cpu().clone())
+    cpu_views = [(img.cpu(), q.cpu(), t.cpu(), CameraInfo(cam.camera_intrinsics.cpu(), cam.camera_height, cam.camera_width, 0))
+                 for img, q, t, cam in views]
+    gpu_scene = Scene(point_cloud=scene.point_cloud.detach().clone().requires_grad_(True),
+                      point_cloud_features=scene.point_cloud_features.detach().clone().requires_grad_(True),
+                      point_invalid_mask=scene.point_invalid_mask.clone(), point_object_id=scene.point_object_id.clone())
+    t_cpu = GaussianPointCloudTrainer(cfg_k, cpu_scene, cpu_views, rasterisation_factory=OracleRasterisationModule)
+    t0 = time.perf_counter()
+    h_cpu = t_cpu.train(log_interval=10)
+    cpu_seconds = time.perf_counter() - t0
+    t_gpu = GaussianPointCloudTrainer(cfg_k, gpu_scene, views, fused_image_loss=fused, fused_adam=fused, fused_controller_update=fused,
+                                      fused_step=fused_step)
+    h_gpu = t_gpu.train(log_interval=10)
+    # validation of both parameter sets with ONE renderer (the CUDA operator), at full resolution
+    val = views[::5]
+    psnr_gpu = t_gpu.validation(val)
+    t_gpu.scene.point_cloud.data.copy_(cpu_scene.point_cloud.data.to(dev))
+    t_gpu.scene.point_cloud_features.data.copy_(cpu_scene.point_cloud_features.data.to(dev))
+    psnr_cpu = t_gpu.validation(val)
+    l_cpu, l_gpu = np.array([h["loss"] for h in h_cpu]), np.array([h["loss"] for h in h_gpu])
+    result["oracle_parity"] = {
+        "iterations": parity_iters, "psnr_after_oracle_training": round(psnr_cpu, 3), "psnr_after_cuda_training": round(psnr_gpu, 3),
+        "psnr_difference_dB": round(abs(psnr_cpu - psnr_gpu), 3),
+        "max_relative_loss_difference": round(float(np.abs(l_cpu - l_gpu).max() / l_cpu.max()), 5),
+        "oracle_seconds": round(cpu_seconds, 1),
+        "what": "same trainer, data, initial state; CPU oracle (reference arithmetic restated in C) vs CUDA path; both parameter sets "
+                "validated with the CUDA renderer on every 5th view at 976x544"}
+
+trainer = make_trainer(scene, views, fused_image_loss=fused, fused_adam=fused, fused_controller_update=fused, fused_step=fused_step)
 psnr0 = trainer.validation(views[::5])
 torch.cuda.synchronize(); t0 = time.perf_counter()
 hist = trainer.train(log_interval=50)
 torch.cuda.synchronize(); dt = time.perf_counter() - t0
 psnr1 = trainer.validation(views[::5])
-print(json.dumps({"config": "C5 tat_truck_every_8_test.yaml shapes, synthetic targets", "iterations": iters, "fused_step": fused,
-                  "seconds": round(dt, 2), "iterations_per_s": round(iters / dt, 1), "psnr_before": round(psnr0, 2),
-                  "psnr_after": round(psnr1, 2), "points_allocated": int(scene.point_cloud.shape[0]),
-                  "points_valid_start": hist[0]["num_valid_points"], "points_valid_end": hist[-1]["num_valid_points"],
-                  "loss_first": round(hist[0]["loss"], 4), "loss_last": round(hist[-1]["loss"], 4)}))
+result.update({"seconds": round(dt, 2), "iterations_per_s": round(iters / dt, 1), "psnr_before": round(psnr0, 2),
+               "psnr_after": round(psnr1, 2), "points_allocated": int(scene.point_cloud.shape[0]),
+               "points_valid_start": hist[0]["num_valid_points"], "points_valid_end": int((scene.point_invalid_mask == 0).sum()),
+               "loss_first": round(hist[0]["loss"], 4), "loss_last": round(hist[-1]["loss"], 4)})
+if fused_step:
+    result["skipped_steps"] = trainer.fused_train_step.num_skipped_steps
+print(json.dumps(result))

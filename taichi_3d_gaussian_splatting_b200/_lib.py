@@ -61,6 +61,19 @@ class GsbBackwardArgs(ctypes.Structure):
         ("grad_pointcloud", c_vp), ("grad_pointcloud_features", c_vp),
         ("magnitude_grad_viewspace_on_image", c_vp), ("stream", c_vp),
         ("grad_sum_compact", c_vp), ("grad_color_compact", c_vp),
+        ("ctl_accumulated_num_in_camera", c_vp), ("ctl_accumulated_num_pixels", c_vp),
+        ("ctl_accumulated_view_space_position_gradients", c_vp), ("ctl_accumulated_view_space_position_gradients_avg", c_vp),
+        ("ctl_accumulated_position_gradients", c_vp), ("ctl_accumulated_position_gradients_norm", c_vp),
+    ]
+
+
+class GsbTrainStepArgs(ctypes.Structure):
+    _fields_ = [
+        ("forward", GsbForwardArgs), ("backward", GsbBackwardArgs), ("ground_truth_image", c_vp), ("lambda_value", c_f32),
+        ("loss_out3", c_vp), ("loss_temp", c_vp), ("loss_temp_bytes", c_i64), ("feature_exp_avg", c_vp),
+        ("feature_exp_avg_sq", c_vp), ("position_exp_avg", c_vp), ("position_exp_avg_sq", c_vp),
+        ("feature_learning_rate", ctypes.c_double), ("position_learning_rate", ctypes.c_double), ("beta1", ctypes.c_double),
+        ("beta2", ctypes.c_double), ("eps", ctypes.c_double), ("step", c_i32),
     ]
 
 
@@ -80,6 +93,7 @@ EXPORTS = (
     "gsb200_forward_timed", "gsb200_backward_timed", "gsb200_abi_sizes", "gsb200_l1_loss_temp_bytes", "gsb200_l1_loss",
     "gsb200_image_loss_temp_bytes", "gsb200_image_loss", "gsb200_adam_step", "gsb200_controller_update",
     "gsb200_forward_blend_work", "gsb200_backward_blend_work", "gsb200_device_selftest", "gsb200_expand_view_gradients",
+    "gsb200_train_step", "gsb200_abi_sizes_ext",
 )
 
 _lib = None
@@ -130,6 +144,8 @@ def load() -> ctypes.CDLL:
     lib.gsb200_backward_blend_work.restype = ctypes.c_int
     lib.gsb200_expand_view_gradients.argtypes = [ctypes.POINTER(GsbExpandArgs)]
     lib.gsb200_expand_view_gradients.restype = ctypes.c_int
+    lib.gsb200_train_step.argtypes = [ctypes.POINTER(GsbTrainStepArgs)]
+    lib.gsb200_train_step.restype = ctypes.c_int
     lib.gsb200_device_selftest.argtypes = [c_vp]
     lib.gsb200_device_selftest.restype = ctypes.c_int
     sizes = (c_i64 * 3)()
@@ -138,6 +154,11 @@ def load() -> ctypes.CDLL:
     if tuple(sizes) != mine:
         raise RuntimeError(f"libgsb200.so ABI mismatch: C struct sizes {tuple(sizes)} != ctypes mirrors {mine}; "
                            "rebuild with `python -m taichi_3d_gaussian_splatting_b200.build --force`")
+    sizes5 = (c_i64 * 5)()
+    lib.gsb200_abi_sizes_ext(sizes5, 5)
+    mine5 = mine + (ctypes.sizeof(GsbExpandArgs), ctypes.sizeof(GsbTrainStepArgs))
+    if tuple(sizes5) != mine5:
+        raise RuntimeError(f"libgsb200.so ABI mismatch: C struct sizes {tuple(sizes5)} != ctypes mirrors {mine5}")
     _lib = lib
     return lib
 

@@ -17,6 +17,7 @@ struct AdamParams {
     float one_minus_beta1, beta2, one_minus_beta2, eps;
     float neg_step_size;         // -lr / (1 - beta1^t)
     float bias_correction2_sqrt; // sqrt(1 - beta2^t)
+    const long long *skip_flag;  // optional device flag: non-zero = no-op (fused train step after a key-capacity overflow)
 };
 
 __device__ __forceinline__ void adam_one(const AdamParams &p, float &w, float g, float &m, float &v) {
@@ -28,6 +29,7 @@ __device__ __forceinline__ void adam_one(const AdamParams &p, float &w, float g,
 
 constexpr int ADAM_THREADS = 256;
 __global__ void __launch_bounds__(ADAM_THREADS) adam_step_kernel(const AdamParams p) {
+    if (p.skip_flag != nullptr && *p.skip_flag != 0) return;
     const long long n4 = p.n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
     float4 *w4 = reinterpret_cast<float4 *>(p.param);
@@ -68,8 +70,25 @@ static inline AdamParams adam_params(float *param, const float *grad, float *exp
     const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
     p.neg_step_size = (float)(-lr / bc1);
     p.bias_correction2_sqrt = (float)sqrt(bc2);
+    p.skip_flag = nullptr;
     return p;
 }
+
+#ifndef GSB_HOST_EMU
+int launch_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, double lr, double beta1,
+                     double beta2, double eps, int step, const long long *skip_flag, cudaStream_t stream) {
+    if (n <= 0) return GSB_OK;
+    AdamParams p = adam_params(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step);
+    p.skip_flag = skip_flag;
+    long long blocks = ((n >> 2) + ADAM_THREADS - 1) / ADAM_THREADS;
+    const long long cap = 16LL * num_sms();
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    adam_step_kernel<<<(int)blocks, ADAM_THREADS, 0, stream>>>(p);
+    GSB_CUDA_CHECK(cudaGetLastError());
+    return GSB_OK;
+}
+#endif
 
 }  // namespace gsb
 
@@ -87,13 +106,7 @@ extern "C" int gsb200_adam_step(float *param, const float *grad, float *exp_avg,
         set_error("adam_step: pointers must be 16-byte aligned");
         return GSB_EINVAL;
     }
-    const AdamParams p = adam_params(param, grad, exp_avg, exp_avg_sq, num_elements, lr, beta1, beta2, eps, step);
-    long long blocks = ((num_elements >> 2) + ADAM_THREADS - 1) / ADAM_THREADS;
-    const long long cap = 16LL * num_sms();
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    adam_step_kernel<<<(int)blocks, ADAM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
-    GSB_CUDA_CHECK(cudaGetLastError());
-    return GSB_OK;
+    return launch_adam_step(param, grad, exp_avg, exp_avg_sq, num_elements, lr, beta1, beta2, eps, step, nullptr,
+                            static_cast<cudaStream_t>(stream));
 }
 #endif  // GSB_HOST_EMU

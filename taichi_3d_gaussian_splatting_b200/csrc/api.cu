@@ -187,6 +187,12 @@ void gsb200_abi_sizes(int64_t *out3) {
     out3[2] = (int64_t)sizeof(GsbBackwardArgs);
 }
 
+void gsb200_abi_sizes_ext(int64_t *out, int32_t n) {
+    const int64_t all[5] = {(int64_t)sizeof(GsbWorkspaceLayout), (int64_t)sizeof(GsbForwardArgs), (int64_t)sizeof(GsbBackwardArgs),
+                            (int64_t)sizeof(GsbExpandArgs), (int64_t)sizeof(GsbTrainStepArgs)};
+    for (int i = 0; i < n && i < 5; ++i) out[i] = all[i];
+}
+
 int gsb200_workspace_layout(int64_t num_points, int32_t num_objects, int64_t key_capacity,
                             int32_t camera_height, int32_t camera_width, float far_plane,
                             float depth_to_sort_key_scale, uint32_t flags, GsbWorkspaceLayout *out) {
@@ -242,7 +248,7 @@ int gsb200_forward(const GsbForwardArgs *a) {
     return launch_blend_forward(*a, ws, st);
 }
 
-int gsb200_backward(const GsbBackwardArgs *a) {
+static int backward_impl(const GsbBackwardArgs *a, bool skip_on_overflow) {
     if (!a) {
         set_error("backward: args is null");
         return GSB_EINVAL;
@@ -256,6 +262,22 @@ int gsb200_backward(const GsbBackwardArgs *a) {
         (a->num_points > 0 && compact && (!a->grad_sum_compact || !a->grad_color_compact))) {
         set_error("backward: null pointer argument");
         return GSB_EINVAL;
+    }
+    {
+        const void *ctl[6] = {a->ctl_accumulated_num_in_camera, a->ctl_accumulated_num_pixels,
+                              a->ctl_accumulated_view_space_position_gradients,
+                              a->ctl_accumulated_view_space_position_gradients_avg, a->ctl_accumulated_position_gradients,
+                              a->ctl_accumulated_position_gradients_norm};
+        int set = 0;
+        for (const void *c : ctl) set += c != nullptr;
+        if (set != 0 && set != 6) {
+            set_error("backward: the six controller accumulators must be all NULL or all set");
+            return GSB_EINVAL;
+        }
+        if (set == 6 && (a->flags & GSB_FLAG_NO_HOOK_STATS)) {
+            set_error("backward: the controller accumulators need the hook statistics (GSB_FLAG_NO_HOOK_STATS is set)");
+            return GSB_EINVAL;
+        }
     }
     if (compact && reinterpret_cast<uintptr_t>(a->grad_sum_compact) % 16 != 0) {
         set_error("backward: grad_sum_compact must be 16-byte aligned");
@@ -274,7 +296,46 @@ int gsb200_backward(const GsbBackwardArgs *a) {
     if (a->accum_rows > 0)
         GSB_CUDA_CHECK(cudaMemsetAsync(a->accum, 0, (size_t)a->accum_rows * GSB_ACCUM_FLOATS * 4, st));
     if ((rc = launch_blend_backward(*a, ws, st)) != GSB_OK) return rc;
-    return launch_backward_points(*a, ws, st);
+    return launch_backward_points(*a, ws, st, skip_on_overflow ? ws.counters + CNT_OVERFLOW : nullptr);
+}
+
+int gsb200_backward(const GsbBackwardArgs *a) { return backward_impl(a, false); }
+
+int gsb200_image_loss(const float *rasterized_image, const float *ground_truth_image, int32_t camera_height,
+                      int32_t camera_width, float lambda_value, float upstream_grad, float *loss_out3,
+                      float *grad_rasterized_image, void *temp, int64_t temp_bytes, void *stream);
+
+int gsb200_train_step(const GsbTrainStepArgs *t) {
+    if (!t || !t->ground_truth_image || !t->loss_out3 || !t->loss_temp || !t->feature_exp_avg || !t->feature_exp_avg_sq ||
+        !t->position_exp_avg || !t->position_exp_avg_sq || t->step < 1) {
+        set_error("train_step: null pointer argument or step < 1");
+        return GSB_EINVAL;
+    }
+    const GsbForwardArgs &f = t->forward;
+    const GsbBackwardArgs &b = t->backward;
+    if (f.rgb_only || f.num_points != b.num_points || f.workspace != b.workspace || f.camera_height != b.camera_height ||
+        f.camera_width != b.camera_width || f.stream != b.stream || b.accum_rows < f.num_points ||
+        (b.flags & GSB_FLAG_COMPACT_GRADS) || !b.grad_rasterized_image || !b.grad_pointcloud || !b.grad_pointcloud_features ||
+        b.pointcloud != f.pointcloud || b.pointcloud_features != f.pointcloud_features) {
+        set_error("train_step: forward / backward blocks do not describe one frame (or rgb_only / compact gradients set)");
+        return GSB_EINVAL;
+    }
+    int rc = gsb200_forward(&f);
+    if (rc != GSB_OK) return rc;
+    rc = gsb200_image_loss(f.rasterized_image, t->ground_truth_image, f.camera_height, f.camera_width, t->lambda_value, 1.0f,
+                           t->loss_out3, const_cast<float *>(b.grad_rasterized_image), t->loss_temp, t->loss_temp_bytes, f.stream);
+    if (rc != GSB_OK) return rc;
+    if ((rc = backward_impl(&b, true)) != GSB_OK) return rc;
+    Workspace ws;
+    if ((rc = resolve_fwd(&f, &ws)) != GSB_OK) return rc;
+    const long long *skip = ws.counters + CNT_OVERFLOW;
+    cudaStream_t st = static_cast<cudaStream_t>(f.stream);
+    rc = launch_adam_step(f.pointcloud_features, b.grad_pointcloud_features, t->feature_exp_avg, t->feature_exp_avg_sq,
+                          (long long)f.num_points * GSB_FEATURE_DIM, t->feature_learning_rate, t->beta1, t->beta2, t->eps, t->step,
+                          skip, st);
+    if (rc != GSB_OK) return rc;
+    return launch_adam_step(const_cast<float *>(f.pointcloud), b.grad_pointcloud, t->position_exp_avg, t->position_exp_avg_sq,
+                            (long long)f.num_points * 3, t->position_learning_rate, t->beta1, t->beta2, t->eps, t->step, skip, st);
 }
 
 int gsb200_expand_view_gradients(const GsbExpandArgs *a) {

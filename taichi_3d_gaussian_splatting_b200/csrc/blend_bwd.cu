@@ -354,6 +354,15 @@ struct PointsBwdParams {
     float q_f, s_f, a_f, c_f, h_f;
     float *grad_xyz;
     float *grad_feat;
+    // optional: the densification controller's accumulators, updated in this epilogue (GaussianPointAdaptiveController.py:130-143)
+    int *ctl_num_in_camera;     // (N) or nullptr = not fused
+    int *ctl_num_pixels;        // (N)
+    float *ctl_vs_grad;         // (N)   accumulated_view_space_position_gradients
+    float *ctl_vs_grad_avg;     // (N)   accumulated_view_space_position_gradients_avg
+    float *ctl_pos_grad;        // (N,3) accumulated_position_gradients
+    float *ctl_pos_grad_norm;   // (N)   accumulated_position_gradients_norm
+    const long long *skip_flag; // optional device flag (the frame's key-capacity overflow counter): non-zero = leave the
+                                //   controller accumulators alone (fused train step: the whole step becomes a no-op)
     float *grad_sum_compact;    // COMPACT: (N,12) xyz(3) q(4) s(3) logit(1) pad -- the columns that simply add up over views
     float *grad_color_compact;  // COMPACT: (N,3) d L / d (SH colour argument), per VIEW (its SH basis depends on the camera centre)
 };
@@ -475,6 +484,21 @@ backward_points_kernel(const PointsBwdParams p) {
         // sigmoid'(.) from the stored colour: c (1 - c)  (UT:356-359)
         const float gcol[3] = {a1.y * (r2.x * (1.0f - r2.x)), a1.z * (r2.y * (1.0f - r2.y)),
                                a1.w * (r2.z * (1.0f - r2.z))};
+        if (p.ctl_num_in_camera != nullptr && !(p.skip_flag != nullptr && *p.skip_flag != 0)) {
+            // GaussianPointAdaptiveController.update (:130-143) for this in-camera point: ids are unique, one thread per row,
+            // so plain read-modify-writes.  a2.y = sum |d/duv| over pixels, a2.z = number of affected pixels (exact in f32)
+            const int npix = __float2int_rn(a2.z);
+            p.ctl_num_in_camera[id] += 1;
+            p.ctl_num_pixels[id] += npix;
+            p.ctl_vs_grad[id] += a2.y;
+            float avg = a2.y / (float)npix;  // 0/0 -> NaN -> 0; x/0 stays inf like the reference
+            if (avg != avg) avg = 0.0f;
+            p.ctl_vs_grad_avg[id] += avg;
+            p.ctl_pos_grad[3 * id] += gx[0];
+            p.ctl_pos_grad[3 * id + 1] += gx[1];
+            p.ctl_pos_grad[3 * id + 2] += gx[2];
+            p.ctl_pos_grad_norm[id] += sqrtf(gx[0] * gx[0] + gx[1] * gx[1] + gx[2] * gx[2]);
+        }
         if (COMPACT) {
             float4 *gc = reinterpret_cast<float4 *>(my_feat);
             gc[0] = make_float4(gx[0], gx[1], gx[2], gq[0] * p.q_f);
@@ -626,9 +650,16 @@ expand_view_gradients_kernel(const ExpandParams p) {
 #ifndef GSB_HOST_EMU
 static int first_cleared_of_band(int band) { return band <= 0 ? 1 : band == 1 ? 4 : band == 2 ? 9 : 16; }
 
-int launch_backward_points(const GsbBackwardArgs &a, const Workspace &ws, cudaStream_t stream) {
+int launch_backward_points(const GsbBackwardArgs &a, const Workspace &ws, cudaStream_t stream, const long long *skip_flag) {
     if (a.num_points <= 0) return GSB_OK;
     PointsBwdParams p;
+    p.ctl_num_in_camera = a.ctl_accumulated_num_in_camera;
+    p.ctl_num_pixels = a.ctl_accumulated_num_pixels;
+    p.ctl_vs_grad = a.ctl_accumulated_view_space_position_gradients;
+    p.ctl_vs_grad_avg = a.ctl_accumulated_view_space_position_gradients_avg;
+    p.ctl_pos_grad = a.ctl_accumulated_position_gradients;
+    p.ctl_pos_grad_norm = a.ctl_accumulated_position_gradients_norm;
+    p.skip_flag = skip_flag;
     p.N = a.num_points;
     p.point_offset = ws.point_offset;
     p.records = ws.records;

@@ -67,7 +67,10 @@ int launch_tile_ranges_raw(const long long *keys_i64, int64_t n, int *tile_start
                            int num_tiles, cudaStream_t stream);
 int launch_blend_forward(const GsbForwardArgs &a, const Workspace &ws, cudaStream_t stream);
 int launch_blend_backward(const GsbBackwardArgs &a, const Workspace &ws, cudaStream_t stream);
-int launch_backward_points(const GsbBackwardArgs &a, const Workspace &ws, cudaStream_t stream);
+int launch_backward_points(const GsbBackwardArgs &a, const Workspace &ws, cudaStream_t stream,
+                           const long long *skip_flag = nullptr);
+int launch_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, double lr, double beta1,
+                     double beta2, double eps, int step, const long long *skip_flag, cudaStream_t stream);
 int launch_expand_view_gradients(const GsbExpandArgs &a, cudaStream_t stream);
 int launch_blend_forward_count(const GsbForwardArgs &a, const Workspace &ws, unsigned long long *counters_dev,
                                cudaStream_t stream);

@@ -142,6 +142,18 @@ class GaussianPointAdaptiveController:
                 self._find_densify_points(input_data)
                 self.input_data = input_data
 
+    def after_fused_update(self, make_hook_input):
+        """The accumulators of this iteration were already updated on the device (the fused controller epilogue of the
+        per-point backward kernel, ``GsbBackwardArgs.ctl_*``): advance the iteration counter and, on a densification
+        iteration only, build the hook tensors (``make_hook_input()``) and pick the candidates like ``update`` does."""
+        self.iteration_counter += 1
+        if self.iteration_counter >= self.config.num_iterations_warm_up and \
+                self.iteration_counter % self.config.num_iterations_densify == 0:
+            with torch.no_grad():
+                hook = make_hook_input()
+                self._find_densify_points(hook)
+                self.input_data = hook
+
     def _update_fused(self, h):
         from . import _lib
         ids = h.point_id_in_camera_list

@@ -77,21 +77,33 @@ class ViewParallelExchange:
     rank's ``[3N colour-argument gradients | 3 n_obj camera centres]`` in row ``rank`` and receives the other ranks' rows
     (in-place all-gather: the send buffer is the rank's slot of the receive buffer)."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, gather_group=None):
+        """``gather_group``: optionally a SECOND process group over the same ranks (``dist.new_group()``): the all-gather
+        then runs on its communicator concurrently with the all-reduce (two NCCL kernels in flight hide each other's
+        latency) instead of behind it."""
         if not dist.is_available() or not dist.is_initialized():
             raise RuntimeError("ViewParallelExchange needs an initialised torch.distributed process group")
         self.group = group
+        self.gather_group = gather_group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        if gather_group is not None and dist.get_world_size(gather_group) != self.world:
+            raise ValueError("gather_group must span the same ranks as group")
 
     def run(self, grad_sum: torch.Tensor, blocks: torch.Tensor) -> None:
         if blocks.shape[0] != self.world or not blocks.is_contiguous() or not grad_sum.is_contiguous():
             raise ValueError("blocks must be a contiguous (world, stride) tensor and grad_sum contiguous")
-        dist.all_reduce(grad_sum, op=dist.ReduceOp.SUM, group=self.group)
         mine = blocks[self.rank]
         if not mine.is_cuda:  # gloo (CPU tests): no in-place all-gather
             mine = mine.clone()
-        dist.all_gather_into_tensor(blocks.view(-1), mine, group=self.group)
+        if self.gather_group is None:
+            dist.all_reduce(grad_sum, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_gather_into_tensor(blocks.view(-1), mine, group=self.group)
+        else:
+            w1 = dist.all_reduce(grad_sum, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            w2 = dist.all_gather_into_tensor(blocks.view(-1), mine, group=self.gather_group, async_op=True)
+            w1.wait()
+            w2.wait()
 
 
 def render_views(op, make_input, view_ids: Sequence[int]):

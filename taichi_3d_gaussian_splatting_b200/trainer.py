@@ -76,13 +76,21 @@ class GaussianPointCloudTrainer:
 
     def __init__(self, config: "GaussianPointCloudTrainer.TrainConfig", scene: Scene, train_views: List[View],
                  rasterisation_factory: Optional[Callable] = None, generator: Optional[torch.Generator] = None,
-                 fused_image_loss: bool = False, fused_adam: bool = False, fused_controller_update: bool = False):
+                 fused_image_loss: bool = False, fused_adam: bool = False, fused_controller_update: bool = False,
+                 fused_step: bool = False, shuffle_generator: Optional[torch.Generator] = None):
         """``fused_image_loss``: clamp + L1 + D-SSIM and their gradient in two CUDA kernels (``gsb200_image_loss``)
         instead of ~60 autograd kernels per step; same loss values (CUDA only).  ``fused_adam``: the two Adam updates as
         one kernel each (``optim.FusedAdam`` / ``gsb200_adam_step``) instead of torch's foreach path (CUDA only).
         ``fused_controller_update``: the controller's per-iteration accumulator update as one kernel
-        (``gsb200_controller_update``) instead of ~15 torch launches (CUDA only)."""
+        (``gsb200_controller_update``) instead of ~15 torch launches (CUDA only).
+        ``fused_step``: the WHOLE iteration as one library call (``gsb200_train_step``: forward, image loss, backward with the
+        controller accumulators fused into its epilogue, both Adam updates; no autograd, no host wait; CUDA only).
+        ``shuffle_generator``: a CPU ``torch.Generator``; the views are then visited in a fresh random permutation per
+        epoch like the reference's shuffling DataLoader (GaussianPointTrainer.py:120-124) instead of in fixed order."""
         self.config = config
+        self.fused_step = fused_step
+        if fused_step and config.loss_function_config.enable_regularization:
+            raise ValueError("fused_step does not implement the optional scale regulariser (LossFunction.py:33-37)")
         self.fused_image_loss = fused_image_loss
         self.fused_adam = fused_adam
         self.scene = scene
@@ -99,6 +107,8 @@ class GaussianPointCloudTrainer:
         self.loss_function = LossFunction(config=config.loss_function_config)
         self.history: List[dict] = []
         self._downsampled = {}
+        self._view_generator = shuffle_generator
+        self._view_order = None
 
     def _input(self, q, t, camera_info, band):
         s = self.scene
@@ -107,7 +117,54 @@ class GaussianPointCloudTrainer:
             point_object_id=s.point_object_id, point_invalid_mask=s.point_invalid_mask,
             camera_info=camera_info, q_pointcloud_camera=q, t_pointcloud_camera=t, color_max_sh_band=band)
 
+    def _train_fused(self, log_interval: int = 0):
+        """The loop of ``train`` with the whole iteration enqueued by ONE library call (``fused_step.FusedTrainStep``):
+        no autograd graph, no host wait, the controller's accumulators updated inside the backward kernel."""
+        from .fused_step import FusedTrainStep
+        cfg = self.config
+        step = FusedTrainStep(self.scene, cfg.rasterisation_config, cfg.loss_function_config.lambda_value,
+                              controller=self.adaptive_controller)
+        self.fused_train_step = step
+        position_lr = cfg.position_learning_rate
+        downsample_factor = cfg.initial_downsample_factor
+        for iteration in range(cfg.num_iterations):
+            if iteration % cfg.half_downsample_factor_interval == 0 and iteration > 0 and downsample_factor > 1:
+                downsample_factor //= 2
+            view_index = self._next_view_index(iteration)
+            image_gt, q, t, camera_info = self.train_views[view_index]
+            if downsample_factor > 1:
+                key = (view_index, downsample_factor)
+                if key not in self._downsampled:
+                    self._downsampled[key] = downsample_image_and_camera_info(image_gt, camera_info, downsample_factor)
+                image_gt, camera_info = self._downsampled[key]
+            band = iteration // cfg.increase_color_max_sh_band_interval
+            step.run(image_gt, q, t, camera_info, band, cfg.feature_learning_rate, position_lr)
+            if iteration % cfg.position_learning_rate_decay_interval == 0:  # ExponentialLR.step() after the optimiser step
+                position_lr *= cfg.position_learning_rate_decay_rate
+            self.adaptive_controller.after_fused_update(step.hook_input)
+            self.adaptive_controller.refinement()
+            if log_interval and iteration % log_interval == 0:
+                losses = step.loss.tolist()
+                self.history.append(dict(iteration=iteration, loss=losses[0], l1=losses[1],
+                                         psnr=psnr(step.image.detach().clamp(0, 1).permute(2, 0, 1), image_gt),
+                                         num_valid_points=int((self.scene.point_invalid_mask == 0).sum())))
+        return self.history
+
+    def _next_view_index(self, iteration: int) -> int:
+        """A fresh random permutation of the views every epoch (the reference draws them from a DataLoader with shuffle=True,
+        GaussianPointTrainer.py:120-124), seeded from the injected generator; without a generator: the fixed order
+        ``iteration % len(views)`` (deterministic tests and golden trajectories)."""
+        n = len(self.train_views)
+        if self._view_generator is None:
+            return iteration % n
+        k = iteration % n
+        if k == 0 or self._view_order is None:
+            self._view_order = torch.randperm(n, generator=self._view_generator).tolist()
+        return self._view_order[k]
+
     def train(self, log_interval: int = 0):
+        if self.fused_step:
+            return self._train_fused(log_interval)
         cfg = self.config
         if self.fused_adam:
             from .optim import FusedAdam as Adam
@@ -122,7 +179,7 @@ class GaussianPointCloudTrainer:
                 downsample_factor //= 2
             optimizer.zero_grad()
             position_optimizer.zero_grad()
-            view_index = iteration % len(self.train_views)
+            view_index = self._next_view_index(iteration)
             image_gt, q, t, camera_info = self.train_views[view_index]
             if downsample_factor > 1:
                 # the reference resizes the full-resolution frame in every iteration (GaussianPointTrainer.py:146-148); the

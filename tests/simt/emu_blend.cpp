@@ -81,7 +81,8 @@ extern "C" long long emu_backward_points(long long N, const int *point_offset, c
                                          const float *xyz, const float *features, const int *obj_id,
                                          const float *t_pc_cam, const float *K, int color_max_sh_band, float q_f, float s_f,
                                          float a_f, float c_f, float h_f, float *grad_xyz, float *grad_feat, float *grad_sum,
-                                         float *grad_col) {
+                                         float *grad_col, int *ctl_num_in_camera, int *ctl_num_pixels, float *ctl_vs_grad,
+                                         float *ctl_vs_grad_avg, float *ctl_pos_grad, float *ctl_pos_grad_norm) {
     using namespace gsb;
     PointsBwdParams p;
     p.N = N;
@@ -106,6 +107,13 @@ extern "C" long long emu_backward_points(long long N, const int *point_offset, c
     p.grad_feat = grad_feat;
     p.grad_sum_compact = grad_sum;
     p.grad_color_compact = grad_col;
+    p.ctl_num_in_camera = ctl_num_in_camera;
+    p.ctl_num_pixels = ctl_num_pixels;
+    p.ctl_vs_grad = ctl_vs_grad;
+    p.ctl_vs_grad_avg = ctl_vs_grad_avg;
+    p.ctl_pos_grad = ctl_pos_grad;
+    p.ctl_pos_grad_norm = ctl_pos_grad_norm;
+    p.skip_flag = nullptr;
     simt_emu::M().switches = 0;
     const int blocks = (int)std::min<long long>((N + GSB_POINTS_THREADS - 1) / GSB_POINTS_THREADS, 16 * 148);
     if (N > 0) {

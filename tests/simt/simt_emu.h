@@ -291,3 +291,4 @@ inline int __float_as_int(float f) {
     return i;
 }
 inline float __logf(float x) { return logf(x); }
+inline int __float2int_rn(float x) { return (int)nearbyintf(x); }

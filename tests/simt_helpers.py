@@ -112,9 +112,11 @@ def emulated_forward(emu, scene, cfg=None, exact=True, filter_tiles=True):
 
 
 def emulated_backward(emu, st, grad_image, band=3, transposed=False, factors=(1.0, 0.5, 20.0, 5.0, 1.0), stats=True,
-                      compact=False):
+                      compact=False, controller=None):
     """Backward for a state of :func:`emulated_forward`: dense gradients + the hook tensors; ``compact``: the COMPACT
-    per-point kernel instead (GSB_FLAG_COMPACT_GRADS): returns (grad_sum (N,12), grad_colour (N,3), None)."""
+    per-point kernel instead (GSB_FLAG_COMPACT_GRADS): returns (grad_sum (N,12), grad_colour (N,3), None).
+    ``controller``: six numpy accumulators (num_in_camera i32, num_pixels i32, vs_grad, vs_grad_avg, pos_grad (N,3),
+    pos_grad_norm) updated by the kernel's fused controller epilogue."""
     pre, scene, M = st.pre, st.scene, st.M
     H, W = pre.H, pre.W
     g = np.ascontiguousarray(grad_image, dtype=np.float32)
@@ -136,11 +138,11 @@ def emulated_backward(emu, st, grad_image, band=3, transposed=False, factors=(1.
         gsum, gcol = np.full((N, 12), 7.0, np.float32), np.full((N, 3), 7.0, np.float32)
         emu.emu_backward_points(ctypes.c_longlong(N), c(pre.point_offset), c(pre.records), c(pre.pic), c(accum), c(poses), c(xyz),
                                 c(pre.feats), c(obj), c(t), c(K), int(band) if band in (0, 1, 2) else 3, *(f(v) for v in factors),
-                                None, None, c(gsum), c(gcol))
+                                None, None, c(gsum), c(gcol), *([None] * 6))
         return gsum, gcol, None
     emu.emu_backward_points(ctypes.c_longlong(N), c(pre.point_offset), c(pre.records), c(pre.pic), c(accum), c(poses), c(xyz),
                             c(pre.feats), c(obj), c(t), c(K), int(band) if band in (0, 1, 2) else 3, *(f(v) for v in factors),
-                            c(gx), c(gf), None, None)
+                            c(gx), c(gf), None, None, *([c(a) for a in controller] if controller is not None else [None] * 6))
     ids = pre.point_id[:M]
     hook = SimpleNamespace(grad_point_in_camera=gx[ids], grad_pointfeatures_in_camera=gf[ids], grad_viewspace=accum[:M, 0:2].copy(),
                            magnitude_grad_viewspace=accum[:M, 9].copy(), magnitude_grad_viewspace_on_image=mag,

@@ -59,10 +59,16 @@ def test_exchange_mode_returns_the_sum_over_views(band, with_hook):
 
     hooks = {}
     dense_x, dense_f = torch.zeros_like(xyz), torch.zeros_like(feat)
+    again_x, again_f = torch.zeros_like(xyz), torch.zeros_like(feat)
     for v in range(R):
         gx, gf = run(make_op(hook=(lambda h, v=v: hooks.setdefault(("dense", v), h)) if with_hook else None), v)
         dense_x += gx
         dense_f += gf
+        gx, gf = run(make_op(), v)  # the same thing once more: the float atomics of loop A land in another order every run
+        again_x += gx
+        again_f += gf
+    noise_x = float((again_x - dense_x).abs().max())
+    noise_f = float((again_f - dense_f).abs().max())
     store = {}
     for v in range(R):  # every rank's compact buffers
         op = GPCR(GPCR.GaussianPointCloudRasterisationConfig(), gradient_exchange=_LocalExchange(R, v, store, False))
@@ -72,8 +78,10 @@ def test_exchange_mode_returns_the_sum_over_views(band, with_hook):
         op = GPCR(GPCR.GaussianPointCloudRasterisationConfig(), backward_valid_point_hook=hook,
                   gradient_exchange=_LocalExchange(R, v, store, True))
         gx, gf = run(op, v)
-        assert float((gx - dense_x).abs().max()) <= 2e-6 * float(dense_x.abs().max())
-        assert float((gf - dense_f).abs().max()) <= 2e-6 * float(dense_f.abs().max())
+        # equal up to the run-to-run noise of the float atomics (measured above on the dense path itself) ...
+        assert float((gx - dense_x).abs().max()) <= 4.0 * noise_x + 2e-6 * float(dense_x.abs().max())
+        assert float((gf - dense_f).abs().max()) <= 4.0 * noise_f + 2e-6 * float(dense_f.abs().max())
+        assert noise_x <= 1e-3 * float(dense_x.abs().max()) and noise_f <= 1e-3 * float(dense_f.abs().max())
         cleared = {3: 16, 1: 4}[band]
         sh = gf[:, 8:].reshape(-1, 3, 16)
         assert float(sh[:, :, cleared:].abs().max()) == 0.0 if cleared < 16 else True

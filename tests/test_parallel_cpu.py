@@ -48,6 +48,12 @@ def _worker(rank, world, port, out_dir):
     blocks = torch.full((world, 3 * n + 8), -1.0)
     blocks[rank] = torch.arange(3 * n + 8, dtype=torch.float32) + 1000.0 * rank
     ex.run(gsum, blocks)
+    ex2 = ViewParallelExchange(gather_group=dist.new_group())  # all-gather on a communicator of its own
+    gsum2 = torch.full((n, 12), float(rank + 1))
+    blocks2 = torch.full((world, 3 * n + 8), -1.0)
+    blocks2[rank] = torch.arange(3 * n + 8, dtype=torch.float32) + 1000.0 * rank
+    ex2.run(gsum2, blocks2)
+    assert torch.equal(gsum2, gsum) and torch.equal(blocks2, blocks)
     torch.save({"xyz": g_xyz, "feat": g_feat, "avg": g_avg, "views": shard_views(8, rank, world), "flat": flat, "other": other,
                 "gsum": gsum, "blocks": blocks},
                os.path.join(out_dir, f"rank{rank}.pt"))
