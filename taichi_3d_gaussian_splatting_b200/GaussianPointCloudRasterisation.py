@@ -512,6 +512,29 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
         )
 
 
+@dataclass
+class GaussianPoint3D:
+    """The fields of the reference's ``GaussianPoint3D`` Taichi struct (GaussianPoint3D.py:17-27) as tensors."""
+    translation: torch.Tensor  # (3,)
+    cov_rotation: torch.Tensor  # (4,) xyzw
+    cov_scale: torch.Tensor  # (3,) log-scale
+    alpha: torch.Tensor  # () opacity logit
+    color_r: torch.Tensor  # (16,)
+    color_g: torch.Tensor  # (16,)
+    color_b: torch.Tensor  # (16,)
+
+
+def load_point_cloud_row_into_gaussian_point_3d(pointcloud: torch.Tensor, pointcloud_features: torch.Tensor,
+                                                point_id: int) -> GaussianPoint3D:
+    """Same name, arguments and row layout as the reference's ``@ti.func`` (GPCR:208-236; imported by its controller,
+    GaussianPointAdaptiveController.py:4, and pinned by its test ``test_load_point_cloud_row_into_gaussian_point_3d``):
+    row ``point_id`` of the (N,3) / (N,56) tensors as a ``GaussianPoint3D`` -- q xyzw | log-scale | opacity logit |
+    R, G, B SH x 16.  Host-side views; inside the kernels the same split is done by ``preprocess_kernel``."""
+    f = pointcloud_features[point_id]
+    return GaussianPoint3D(translation=pointcloud[point_id], cov_rotation=f[0:4], cov_scale=f[4:7], alpha=f[7],
+                           color_r=f[8:24], color_g=f[24:40], color_b=f[40:56])
+
+
 def find_tile_start_and_end(point_in_camera_sort_key: torch.Tensor, tile_points_start: torch.Tensor,
                             tile_points_end: torch.Tensor) -> None:
     """Same call shape as the reference kernel (GPCR:175-193; used by its tests): sorted int64 keys

@@ -14,10 +14,12 @@ from .GaussianPointCloudRasterisation import (  # noqa: F401
     BOUNDARY_TILES,
     TILE_HEIGHT,
     TILE_WIDTH,
+    GaussianPoint3D,
     GaussianPointCloudRasterisation,
     find_tile_start_and_end,
+    load_point_cloud_row_into_gaussian_point_3d,
 )
 
 __all__ = ["CameraInfo", "CameraView", "GaussianPointCloudRasterisation", "GaussianPointAdaptiveController",
            "LossFunction", "fused_l1_loss", "fused_l1_loss_with_grad", "fused_image_loss", "fused_image_loss_with_grad", "FusedAdam", "GaussianPointCloudScene", "ImagePoseDataset", "find_tile_start_and_end",
-           "TILE_WIDTH", "TILE_HEIGHT", "BOUNDARY_TILES"]
+           "load_point_cloud_row_into_gaussian_point_3d", "GaussianPoint3D", "TILE_WIDTH", "TILE_HEIGHT", "BOUNDARY_TILES"]

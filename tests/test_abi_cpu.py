@@ -181,3 +181,23 @@ def test_fused_image_loss_has_no_cpu_path_and_validates_its_arguments():
         fused_image_loss(a.requires_grad_(True), b)
     assert lib.gsb200_image_loss(None, None, 32, 32, 0.2, 1.0, None, None, None, 0, None) == -1
     assert b"image_loss" in lib.gsb200_last_error()
+
+
+def test_load_point_cloud_row_into_gaussian_point_3d():
+    """Restated from the reference's tests/GaussianPointCloudRasterisation_test.py:58-99 (same name, arguments, row layout;
+    the reference function is a Taichi device function, GPCR:208-236, imported by its controller :4)."""
+    from taichi_3d_gaussian_splatting_b200 import load_point_cloud_row_into_gaussian_point_3d
+    from taichi_3d_gaussian_splatting_b200.GaussianPointCloudRasterisation import (
+        load_point_cloud_row_into_gaussian_point_3d as from_module)
+    assert from_module is load_point_cloud_row_into_gaussian_point_3d
+    g = torch.Generator().manual_seed(0)
+    pointcloud = torch.rand(5, 3, generator=g)
+    pointcloud_features = torch.rand(5, 56, generator=g)
+    result = load_point_cloud_row_into_gaussian_point_3d(pointcloud=pointcloud, pointcloud_features=pointcloud_features, point_id=2)
+    assert torch.equal(result.translation, pointcloud[2])
+    assert torch.equal(result.cov_rotation, pointcloud_features[2, :4])
+    assert torch.equal(result.cov_scale, pointcloud_features[2, 4:7])
+    assert torch.equal(result.alpha, pointcloud_features[2, 7])
+    assert torch.equal(result.color_r, pointcloud_features[2, 8:24])
+    assert torch.equal(result.color_g, pointcloud_features[2, 24:40])
+    assert torch.equal(result.color_b, pointcloud_features[2, 40:56])

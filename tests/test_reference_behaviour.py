@@ -93,6 +93,41 @@ def test_rasterisation_basic(backend):
         assert float(features.grad[:8000].abs().max()) > 0.0
 
 
+@pytest.mark.gpu
+def test_rasterisation_basic_at_the_reference_size():
+    """The reference's stress test at ITS size (tests/GaussianPointCloudRasterisation_test.py:111-150): 1920 x 1088, 1e5 points
+    (8000 valid, log-scales in [0, 1): every splat fills the screen, ~6.5e7 (tile, splat) pairs -- far beyond the default key
+    capacity, so the first frame also exercises the capacity regrowth), 100 x forward + ``image.sum().backward()``."""
+    rasterisation, device = _rasteriser("cuda")
+    height, width, num_points = 1088, 1920, 100000
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for idx in range(100):
+        point_cloud = torch.rand((num_points, 3), generator=g, device=device).requires_grad_(True)
+        features = torch.rand((num_points, 56), generator=g, device=device).requires_grad_(True)
+        mask = torch.zeros((num_points,), dtype=torch.int8, device=device)
+        mask[8000:] = 1
+        obj = torch.zeros((num_points,), dtype=torch.int32, device=device)
+        camera_info = CameraInfo(camera_height=height, camera_width=width, camera_id=0,
+                                 camera_intrinsics=torch.tensor([[500, 0, 960], [0, 500, 540], [0, 0, 1]], dtype=torch.float32,
+                                                                device=device))
+        T = torch.eye(4, dtype=torch.float32)
+        T[2, 3] = -0.5
+        q, t = SE3_to_quaternion_and_translation_torch(T.unsqueeze(0))
+        image, depth, count = rasterisation(GPCR.GaussianPointCloudRasterisationInput(
+            point_cloud=point_cloud, point_cloud_features=features, point_object_id=obj, point_invalid_mask=mask,
+            camera_info=camera_info, q_pointcloud_camera=q.to(device), t_pointcloud_camera=t.to(device)))
+        image.sum().backward()
+        if idx in (0, 99):
+            assert image.shape == (height, width, 3) and depth.shape == (height, width) and count.shape == (height, width)
+            assert bool(torch.isfinite(image).all()) and float(image.max()) > 0.0
+            assert bool(torch.isfinite(point_cloud.grad).all()) and bool(torch.isfinite(features.grad).all())
+            assert float(point_cloud.grad[8000:].abs().max()) == 0.0 and float(features.grad[8000:].abs().max()) == 0.0
+            assert float(features.grad[:8000].abs().max()) > 0.0
+            frame = rasterisation.last_frame
+            assert frame.num_points_in_camera <= 8000 and frame.num_keys <= frame.key_capacity
+            assert int(frame.num_overlap_tiles.sum()) > 10_000_000  # the reference's list: most of 8000 x 8160 pairs
+
+
 @pytest.mark.parametrize("backend", BACKENDS_WITH_SIMT)
 def test_backward_hook(backend):
     seen = {}
