@@ -88,6 +88,6 @@ def test_exchange_mode_returns_the_sum_over_views(band, with_hook):
         if with_hook:  # the hook of a rank sees that rank's own view
             hd, hc = hooks[("dense", v)], hooks[("compact", v)]
             assert torch.equal(hd.point_id_in_camera_list, hc.point_id_in_camera_list)
-            assert torch.allclose(hd.grad_point_in_camera, hc.grad_point_in_camera, rtol=1e-5, atol=1e-9)
+            assert float((hd.grad_point_in_camera - hc.grad_point_in_camera).abs().max()) <= 4.0 * noise_x + 2e-6 * float(dense_x.abs().max())
             assert torch.equal(hd.num_affected_pixels, hc.num_affected_pixels)
             assert hc.grad_pointfeatures_in_camera is None
