@@ -228,6 +228,57 @@ __device__ __forceinline__ void fast_planes(const float4 r0, const float4 r1, fl
 }
 #endif
 
+// ---- mbarrier + TMA 1-D bulk copy (global -> shared), used by the radix sort (key tiles) and the per-point stage (feature rows)
+#if defined(__CUDACC__) || defined(GSB_HOST_EMU)
+#ifdef GSB_HOST_EMU  // tests/simt: host build under the SIMT emulator -- the bulk copy is a memcpy that has landed at once
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned int) { *bar = 0; }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *, unsigned int) {}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, unsigned int bytes,
+                                              unsigned long long *) {
+    memcpy(dst_smem, src_gmem, bytes);
+}
+// every lane of the warp calls the wait (warp-uniform condition at both call sites): under the emulator it is a warp
+// rendezvous, so the lane that issued the (immediate) copy has done so before any lane reads the destination
+__device__ __forceinline__ void mbar_wait(unsigned long long *, unsigned int) { simt_emu::warp_exchange(0u); }
+#else
+// ---- mbarrier / bulk-copy helpers (TMA 1-D bulk copy, global -> shared)
+__device__ __forceinline__ unsigned int smem_addr(const void *p) {
+    return (unsigned int)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, unsigned int bytes,
+                                              unsigned long long *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_addr(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+#endif
+
+#endif
+
 // Work counters for the CPU-side emulation only (tests/simt, scripts/emu_work_stats.py); nothing in a device build.
 #ifdef GSB_HOST_EMU
 #define GSB_EMU_COUNT(slot, n) (simt_emu::counters()[slot] += (long long)(n))

@@ -37,51 +37,6 @@ __device__ __forceinline__ void st_u32_volatile(unsigned int *p, unsigned int v)
     *reinterpret_cast<volatile unsigned int *>(p) = v;
 }
 
-#ifdef GSB_HOST_EMU  // tests/simt: host build under the SIMT emulator -- the bulk copy is a memcpy that has landed at once
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned int) { *bar = 0; }
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *, unsigned int) {}
-__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, unsigned int bytes,
-                                              unsigned long long *) {
-    memcpy(dst_smem, src_gmem, bytes);
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *, unsigned int) {}
-#else
-// ---- mbarrier / bulk-copy helpers (TMA 1-D bulk copy, global -> shared)
-__device__ __forceinline__ unsigned int smem_addr(const void *p) {
-    return (unsigned int)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned int bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, unsigned int bytes,
-                                              unsigned long long *bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_addr(dst_smem)),
-        "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
-        : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_addr(bar)),
-        "r"(parity)
-        : "memory");
-}
-#endif
-
 // ------------------------------------------------------------------ histograms of all passes
 template <typename KeyT, int RBITS>
 __global__ void __launch_bounds__(256)
