@@ -250,39 +250,42 @@ blend_backward_transposed_kernel(const BlendBwdParams p) {
                     s0.w *= -1.0f / GSB_L2E;
                     s1.x *= -2.0f / GSB_L2E;
                 }
-                float dxs[8], dys[2];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) dxs[k] = (pxb + (float)k) - s0.x;
-                dys[0] = pyb - s0.y;
-                dys[1] = (pyb + 1.0f) - s0.y;
+                // conic * d at the first pixel of each of this lane's two rows; along a row d0 grows by exactly 1 per pixel, so
+                // q0 += a, q1 += b (two FADD instead of two FMUL + two FFMA per pixel)
+                const float dx0 = pxb - s0.x;
                 float acc[11];
 #pragma unroll
                 for (int k = 0; k < 11; ++k) acc[k] = 0.0f;
                 unsigned int nz = 0u;
 #pragma unroll
-                for (int t = 0; t < 16; ++t) {
-                    const int pp = t + 16 * half;  // the pixel = phase-1 lane
-                    const float G = xg[pp * TB_ROW + ci], aT = xa[pp * TB_ROW + ci];
-                    const float4 gp = S.g[warp][pp];
-                    const float d0 = dxs[t & 7], d1 = dys[t >> 3];
-                    const float q0 = s0.z * d0 + s0.w * d1;
-                    const float q1 = s0.w * d0 + s1.x * d1;
-                    const float vs0 = G * q0, vs1 = G * q1;
-                    acc[0] += vs0;
-                    acc[1] += vs1;
-                    acc[2] = fmaf(vs0, q0, acc[2]);  // the 1/2 of UT:345 is applied once per point in the epilogue kernel
-                    acc[3] = fmaf(vs0, q1, acc[3]);
-                    acc[4] = fmaf(vs1, q1, acc[4]);
-                    acc[5] = fmaf(aT, gp.x, acc[5]);
-                    acc[6] = fmaf(aT, gp.y, acc[6]);
-                    acc[7] = fmaf(aT, gp.z, acc[7]);
-                    acc[8] += G;
-                    if (STATS) {
-                        const float m2 = vs0 * vs0 + vs1 * vs1;
-                        acc[9] += EXACT_EXP ? sqrtf(m2) : sqrt_approx(m2);
-                        acc[10] += aT > 0.0f ? 1.0f : 0.0f;  // alpha >= 1/255 and T > 0: alpha*T > 0 exactly for the contributing pixels
+                for (int row = 0; row < 2; ++row) {
+                    const float d1 = (pyb + (float)row) - s0.y;
+                    float q0 = s0.z * dx0 + s0.w * d1;
+                    float q1 = s0.w * dx0 + s1.x * d1;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int pp = 8 * row + k + 16 * half;  // the pixel = phase-1 lane
+                        const float G = xg[pp * TB_ROW + ci], aT = xa[pp * TB_ROW + ci];
+                        const float4 gp = S.g[warp][pp];
+                        const float vs0 = G * q0, vs1 = G * q1;
+                        acc[0] += vs0;
+                        acc[1] += vs1;
+                        acc[2] = fmaf(vs0, q0, acc[2]);  // the 1/2 of UT:345 is applied once per point in the epilogue kernel
+                        acc[3] = fmaf(vs0, q1, acc[3]);
+                        acc[4] = fmaf(vs1, q1, acc[4]);
+                        acc[5] = fmaf(aT, gp.x, acc[5]);
+                        acc[6] = fmaf(aT, gp.y, acc[6]);
+                        acc[7] = fmaf(aT, gp.z, acc[7]);
+                        acc[8] += G;
+                        if (STATS) {
+                            const float m2 = vs0 * vs0 + vs1 * vs1;
+                            acc[9] += EXACT_EXP ? sqrtf(m2) : sqrt_approx(m2);
+                            acc[10] += aT > 0.0f ? 1.0f : 0.0f;  // alpha >= 1/255 and T > 0: alpha*T > 0 exactly for the contributing pixels
+                        }
+                        nz |= __float_as_uint(aT);
+                        q0 += s0.z;
+                        q1 += s0.w;
                     }
-                    nz |= __float_as_uint(aT);
                 }
                 // rows 0..1 + rows 2..3 of the patch
 #pragma unroll
