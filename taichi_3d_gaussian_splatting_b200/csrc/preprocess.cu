@@ -8,12 +8,12 @@
 //
 // This translation unit is compiled with -fmad=false: every float op is a plain IEEE op in the same
 // order as the CPU oracle, and exp() is evaluated in double and rounded once, so all discrete per-point
-// decisions (frustum test, tile bbox, depth key) are bit-reproducible.  The stage is HBM-bound
-// (~240 B read, ~70 B + 8..12 B/key written per in-frustum point), the extra ALU work is free.
-// The 224-byte feature rows of a warp's 32 points are one contiguous 7 KB piece of the (N,56) tensor: the warp fetches
-// it with ONE TMA bulk copy (cp.async.bulk + mbarrier -> SASS UBLKCP) issued as soon as the invalid mask says the warp has
-// a live row, and every lane then reads its row from shared memory -- instead of 14 LDG.128 per lane at a 224-byte stride
-// (32 different lines per load instruction, the L1 tag stage and the long-scoreboard stalls ncu showed in round 1).
+// decisions (frustum test, tile bbox, depth key) are bit-reproducible.  On paper the stage is HBM-bound (~240 B read,
+// ~70 B + 8..12 B/key written per in-frustum point); measured on a B200 it is bound by instruction issue and latency:
+// 8.0e7 warp instructions per C3 frame (unfused IEEE arithmetic, seven exp() in double per point) at 32 resident warps per SM.
+// Tried in round 2 and rejected (commit ae2158f, profiles/r02_call7.log): staging each warp's 32 contiguous feature rows
+// (7 KB) with one TMA bulk copy -- the extra 28 KB of shared memory per CTA cut the occupancy from 8 to 5 CTAs per SM and the
+// bulk copy put the whole row fetch in front of the scan's aggregate publish: 166 us instead of 139 us at C3.
 #include "common.cuh"
 
 namespace gsb {
@@ -148,7 +148,7 @@ __device__ __forceinline__ void bounding_box(float u, float v, float radii, int 
 }
 
 #ifndef GSB_PRE_MIN_BLOCKS
-#define GSB_PRE_MIN_BLOCKS 5  // 38.5 KB of shared memory per CTA (feature rows + filter staging) allow 5
+#define GSB_PRE_MIN_BLOCKS 8
 #endif
 // Per-warp staging area of the cooperative reach filter / key emission (32 splats of the warp).
 struct WarpStage {
@@ -188,28 +188,13 @@ preprocess_kernel(const PreParams p) {
     __shared__ unsigned long long s_warp_sums[SCAN_BLOCK_THREADS / 32];
     __shared__ unsigned long long s_block_exclusive;
     __shared__ WarpStage s_stage[SCAN_BLOCK_THREADS / 32];
-    __shared__ __align__(128) float s_rows[SCAN_BLOCK_THREADS / 32][32 * GSB_FEATURE_DIM];  // the warps' feature rows
-    __shared__ unsigned long long s_row_bar[SCAN_BLOCK_THREADS / 32];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_ticket = atomicAdd(&p.tickets[TICKET_SCAN], 1u);
-    if (lane == 0) mbar_init(&s_row_bar[warp], 1);
     __syncthreads();
     const int blk = (int)s_ticket;
     const long long i = (long long)blk * SCAN_BLOCK_THREADS + tid;
-
-    // ---- this warp's 32 feature rows: one bulk copy, in flight while the frustum test below runs
-    const bool live = i < p.N && p.invalid[i] != 1;
-    const bool fetch_rows = __any_sync(0xffffffffu, live);
-    if (fetch_rows && lane == 0) {
-        const long long wrow = (long long)blk * SCAN_BLOCK_THREADS + warp * 32;
-        const long long nrows = p.N - wrow < 32 ? p.N - wrow : 32;
-        const unsigned int bytes = (unsigned int)nrows * (unsigned int)(GSB_FEATURE_DIM * sizeof(float));  // multiple of 16
-        mbar_arrive_expect_tx(&s_row_bar[warp], bytes);
-        bulk_copy_g2s(s_rows[warp], p.features + (size_t)GSB_FEATURE_DIM * wrow, bytes, &s_row_bar[warp]);
-    }
-    const float4 *const my_row = reinterpret_cast<const float4 *>(&s_rows[warp][lane * GSB_FEATURE_DIM]);
 
     bool in = false;
     int ntiles = 0, nkeys = 0, min_tu = 0, max_tu = 0, min_tv = 0, max_tv = 0;
@@ -220,37 +205,31 @@ preprocess_kernel(const PreParams p) {
     float pc[3] = {0, 0, 0};
     float dir0 = 0.0f, dir1 = 0.0f, dir2 = 0.0f;  // unit view direction (GPCR:302), consumed by the SH stage
 
-    const PoseBlock *pb = p.poses;
-    float T[12], Kc[9];
-    float x = 0.0f, y = 0.0f, z = 0.0f, u = 0.0f, v = 0.0f;
-    if (live) {
-        pb = p.poses + p.obj_id[i];
+    if (i < p.N && p.invalid[i] != 1) {
+        const PoseBlock *pb = p.poses + p.obj_id[i];
+        float T[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) T[k] = __ldg(&pb->T[k]);
+        float Kc[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) Kc[k] = __ldg(&p.K[k]);
-        x = __ldg(&p.xyz[3 * i]); y = __ldg(&p.xyz[3 * i + 1]); z = __ldg(&p.xyz[3 * i + 2]);
+        const float x = __ldg(&p.xyz[3 * i]), y = __ldg(&p.xyz[3 * i + 1]), z = __ldg(&p.xyz[3 * i + 2]);
         // GP3D:14-27: T @ (x,y,z,1), then uv = (K @ pc) / pc.z
         pc[0] = ((T[0] * x + T[1] * y) + T[2] * z) + T[3] * 1.0f;
         pc[1] = ((T[4] * x + T[5] * y) + T[6] * z) + T[7] * 1.0f;
         pc[2] = ((T[8] * x + T[9] * y) + T[10] * z) + T[11] * 1.0f;
         float uv1[3];
         matmul<3, 3, 1>(Kc, pc, uv1);
-        u = uv1[0] / pc[2];
-        v = uv1[1] / pc[2];
+        const float u = uv1[0] / pc[2], v = uv1[1] / pc[2];
         in = pc[2] > p.near_plane && pc[2] < p.far_plane &&
              u >= (float)(-GSB_TILE_WIDTH * GSB_BOUNDARY_TILES) &&
              u < (float)(p.W + GSB_TILE_WIDTH * GSB_BOUNDARY_TILES) &&
              v >= (float)(-GSB_TILE_HEIGHT * GSB_BOUNDARY_TILES) &&
              v < (float)(p.H + GSB_TILE_HEIGHT * GSB_BOUNDARY_TILES);
-    }
-    // the rows have landed (every lane waits: a CTA must not retire with a bulk copy into its shared memory in flight)
-    if (fetch_rows) mbar_wait(&s_row_bar[warp], 0);
-    {
         if (in) {
             float4 *frow = reinterpret_cast<float4 *>(p.features + (size_t)GSB_FEATURE_DIM * i);
-            float4 qv = my_row[0];
-            const float4 sl = my_row[1];  // s0 s1 s2 logit
+            float4 qv = frow[0];  // plain load: this row's q is rewritten below
+            const float4 sl = __ldg(reinterpret_cast<const float4 *>(frow) + 1);  // s0 s1 s2 logit
             const float f[4] = {sl.x, sl.y, sl.z, sl.w};
             // GPCR:196-205: q <- q / |q| (invlen * q), written back in place
             if (!p.skip_q_normalise) {
@@ -394,7 +373,7 @@ preprocess_kernel(const PreParams p) {
     // the colour, so successor blocks' look-back no longer waits for them, and this block's own look-back
     // overlaps with them.
     if (in) {
-        const float4 *frow = my_row;
+        const float4 *frow = reinterpret_cast<const float4 *>(p.features + (size_t)GSB_FEATURE_DIM * i);
                     float sh[16];
                     sh[0] = 0.28209479177387814f;
                     sh[1] = -0.48860251190291987f * dir1;
@@ -420,7 +399,7 @@ preprocess_kernel(const PreParams p) {
                         float acc = 0.0f;
         #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
-                            const float4 c4 = frow[2 + 4 * ch + k4];
+                            const float4 c4 = __ldg(frow + 2 + 4 * ch + k4);
                             if (k4 == 0) acc = c4.x * sh[0];
                             else acc = acc + c4.x * sh[4 * k4];
                             acc = acc + c4.y * sh[4 * k4 + 1];
