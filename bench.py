@@ -60,6 +60,9 @@ def parse_args():
     ap.add_argument("--repeats", type=int, default=10, help="extra timed regions of --steps steps each (median / p10 / p90)")
     ap.add_argument("--exchange-streams", type=int, default=1, choices=[1, 2],
                     help="N > 1: 2 = the all-gather of the compact exchange on a second NCCL communicator, concurrent with the all-reduce")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "multimem", "nccl"],
+                    help="N > 1: collectives of the compact exchange: multimem = the hand-written NVLS kernel (gsb200_exchange_multimem), "
+                         "nccl = ncclAllReduce + ncclAllGather, auto = multimem where the group has multicast support, else nccl")
     ap.add_argument("--dense-exchange", action="store_true",
                     help="N > 1: one all-reduce of the dense gradients instead of the compact exchange (comparison)")
     return ap.parse_args()
@@ -208,7 +211,8 @@ def run_b200(args):
     from taichi_3d_gaussian_splatting_b200 import CameraInfo
     from taichi_3d_gaussian_splatting_b200 import GaussianPointCloudRasterisation as GPCR
     from taichi_3d_gaussian_splatting_b200 import fused_l1_loss_with_grad, profiling
-    from taichi_3d_gaussian_splatting_b200.parallel import ViewParallelExchange, exchange_gradients
+    from taichi_3d_gaussian_splatting_b200.parallel import (MulticastViewParallelExchange, ViewParallelExchange,
+                                                          exchange_gradients)
     from taichi_3d_gaussian_splatting_b200.synthetic import C4_YAWS, CONFIGS, make_scene
 
     rank = int(os.environ.get("RANK", "0"))
@@ -224,9 +228,22 @@ def run_b200(args):
     warmup = max(args.warmup, 3)
     steps = args.steps
     Input = GPCR.GaussianPointCloudRasterisationInput
-    exchange = None
+    exchange, exchange_kind = None, "dense all-reduce"
     if world > 1 and not args.dense_exchange:
-        exchange = ViewParallelExchange(gather_group=dist.new_group() if args.exchange_streams == 2 else None)
+        if args.exchange in ("auto", "multimem"):
+            try:
+                exchange = MulticastViewParallelExchange()
+                exchange.allocate(CONFIGS[args.workload]["num_points"], 1, device)  # the rendezvous is a collective: do it up front
+                exchange_kind = "multimem"
+            except Exception as e:  # no multicast support (or no symmetric-memory backend) on this box
+                if args.exchange == "multimem":
+                    raise
+                exchange = None
+                if rank == 0:
+                    print(f"[bench] multicast exchange unavailable ({type(e).__name__}: {e}); using the NCCL collectives", file=sys.stderr)
+        if exchange is None:
+            exchange = ViewParallelExchange(gather_group=dist.new_group() if args.exchange_streams == 2 else None)
+            exchange_kind = "nccl"
 
     def barrier():
         if world > 1:
@@ -345,6 +362,32 @@ def run_b200(args):
         dense_ms = timed(dense_step, steps) / steps
         exchange_check["dense_all_reduce_ms_per_step"] = round(dense_ms, 4)
         exchange_check["dense_all_reduce_Mpix_s"] = round(wl.mpix(dense_ms), 2)
+        # the collectives of the compact exchange alone (no compute in front: every rank arrives at the same time), and this
+        # rank's own fwd+bwd without any exchange -- what the exchange adds to a step is the difference to `ms_per_step`
+        gs, bl = exchange.allocate(N, 1, device)
+        for _ in range(3):
+            exchange.run(gs, bl)
+        exchange_check["compact_collectives_alone_ms"] = round(timed(lambda: exchange.run(gs, bl), 20) / 20, 4)
+        exchange_check["compact_payload_MB_per_rank"] = {"summed": round(48 * N / 1e6, 1), "gathered_from_each_rank": round(12 * N / 1e6, 1)}
+
+        def local_step():
+            scene.point_cloud.grad = None
+            scene.point_cloud_features.grad = None
+            im, _, _ = dense_op(wl.dev_input)
+            im.backward(wl.grad_image)
+        for _ in range(3):
+            local_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            local_step()
+        e1.record()
+        torch.cuda.synchronize()
+        mine = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=device)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        exchange_check["fwd_bwd_without_exchange_ms_per_rank"] = [round(float(x), 4) for x in every]
 
     # ---- e2e: per-step inputs in pinned HOST memory (target image, pose, intrinsics), loss scalar back
     target_host = torch.rand((H, W, 3), dtype=torch.float32).pin_memory()
@@ -563,10 +606,11 @@ def run_b200(args):
     if world == 1:
         parallelism = "single GPU"
     elif exchange is not None:
-        parallelism = (f"view-parallel x{world}: compact gradient exchange inside backward (NCCL all-reduce of (N,12) + all-gather "
-                       f"of (N,3) + camera centres"
-                       f"{', the two collectives concurrently on two communicators' if args.exchange_streams == 2 else ''}, then "
-                       f"gsb200_expand_view_gradients)")
+        how = ("one hand-written NVLS kernel, gsb200_exchange_multimem: multimem.ld_reduce / multimem.st over NVSwitch multicast memory"
+               if exchange_kind == "multimem" else
+               "NCCL all-reduce + all-gather" + (", concurrently on two communicators" if args.exchange_streams == 2 else ""))
+        parallelism = (f"view-parallel x{world}: compact gradient exchange inside backward (sum of the (N,12) columns + gather of the "
+                       f"(N,3) colour-argument gradients and camera centres: {how}), then gsb200_expand_view_gradients")
     else:
         parallelism = f"view-parallel x{world}: one NCCL all-reduce of the dense (N,59) gradients"
     line = {

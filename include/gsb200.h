@@ -222,6 +222,24 @@ int gsb200_backward(const GsbBackwardArgs *args);
 
 int gsb200_expand_view_gradients(const GsbExpandArgs *args);
 
+/* The two collectives of the compact exchange as ONE hand-written kernel over NVSwitch multicast memory (NVLS; csrc/exchange.cu):
+ * a two-shot all-reduce of grad_sum (multimem.ld_reduce of this rank's 1/R of the rows, multimem.st of the sums to all ranks)
+ * and an all-gather of the per-view blocks (multimem.st of this rank's block into slot `rank` on all ranks).  The buffers must
+ * live in one symmetric allocation mapped to a multicast address (torch.distributed._symmetric_memory); the caller brackets the
+ * call with two cross-rank barriers on the same stream: all ranks' compact rows written before, all multicast stores landed
+ * after (parallel.MulticastViewParallelExchange).  The alternative to ncclAllReduce + ncclAllGather of the NCCL path. */
+typedef struct GsbMultimemExchangeArgs {
+    int64_t num_points;
+    int32_t num_objects, rank, world_size;
+    int32_t num_blocks;          /* CTAs to launch; 0 = 2 per SM */
+    float *multicast_grad_sum;   /* multicast address of the (N,12) rows */
+    float *multicast_blocks;     /* multicast address of the (world_size, block_stride) blocks */
+    const float *local_block;    /* this rank's own block [3N | 3 n_obj], local address */
+    int64_t block_stride;        /* floats, multiple of 4, >= 3N + 3 n_obj */
+    void *stream;
+} GsbMultimemExchangeArgs;
+int gsb200_exchange_multimem(const GsbMultimemExchangeArgs *args);
+
 /* One WHOLE training iteration of the reference loop (GaussianPointTrainer.py:138-180) enqueued by one call, without any host
  * interaction: forward (gsb200_forward) -> clamp + L1 + D-SSIM loss and its gradient (gsb200_image_loss, LossFunction.py:20-38
  * without the optional scale regulariser) -> backward (gsb200_backward, with the controller accumulators if set) -> Adam on the

@@ -432,9 +432,7 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
             grad_sum = blocks = None
             if compact:
                 n_obj = ctx.num_objects
-                stride = (3 * N + 3 * n_obj + 3) // 4 * 4
-                grad_sum = torch.empty((N, 12), dtype=torch.float32, device=device)
-                blocks = torch.empty((exchange.world, stride), dtype=torch.float32, device=device)
+                grad_sum, blocks = exchange.allocate(N, n_obj, device)
                 blocks[exchange.rank, 3 * N:3 * N + 3 * n_obj] = t_pc.reshape(-1)
                 backward_flags |= _lib.GSB_FLAG_COMPACT_GRADS
             args = _lib.GsbBackwardArgs(

@@ -67,6 +67,13 @@ class GsbBackwardArgs(ctypes.Structure):
     ]
 
 
+class GsbMultimemExchangeArgs(ctypes.Structure):
+    _fields_ = [
+        ("num_points", c_i64), ("num_objects", c_i32), ("rank", c_i32), ("world_size", c_i32), ("num_blocks", c_i32),
+        ("multicast_grad_sum", c_vp), ("multicast_blocks", c_vp), ("local_block", c_vp), ("block_stride", c_i64), ("stream", c_vp),
+    ]
+
+
 class GsbTrainStepArgs(ctypes.Structure):
     _fields_ = [
         ("forward", GsbForwardArgs), ("backward", GsbBackwardArgs), ("ground_truth_image", c_vp), ("lambda_value", c_f32),
@@ -93,7 +100,7 @@ EXPORTS = (
     "gsb200_forward_timed", "gsb200_backward_timed", "gsb200_abi_sizes", "gsb200_l1_loss_temp_bytes", "gsb200_l1_loss",
     "gsb200_image_loss_temp_bytes", "gsb200_image_loss", "gsb200_adam_step", "gsb200_controller_update",
     "gsb200_forward_blend_work", "gsb200_backward_blend_work", "gsb200_device_selftest", "gsb200_expand_view_gradients",
-    "gsb200_train_step", "gsb200_abi_sizes_ext",
+    "gsb200_train_step", "gsb200_abi_sizes_ext", "gsb200_exchange_multimem",
 )
 
 _lib = None
@@ -144,6 +151,8 @@ def load() -> ctypes.CDLL:
     lib.gsb200_backward_blend_work.restype = ctypes.c_int
     lib.gsb200_expand_view_gradients.argtypes = [ctypes.POINTER(GsbExpandArgs)]
     lib.gsb200_expand_view_gradients.restype = ctypes.c_int
+    lib.gsb200_exchange_multimem.argtypes = [ctypes.POINTER(GsbMultimemExchangeArgs)]
+    lib.gsb200_exchange_multimem.restype = ctypes.c_int
     lib.gsb200_train_step.argtypes = [ctypes.POINTER(GsbTrainStepArgs)]
     lib.gsb200_train_step.restype = ctypes.c_int
     lib.gsb200_device_selftest.argtypes = [c_vp]

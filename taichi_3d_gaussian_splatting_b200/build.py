@@ -32,6 +32,7 @@ SOURCES = {
     "image_loss.cu": [],
     "adam.cu": [],
     "controller.cu": [],
+    "exchange.cu": [],
 }
 
 

@@ -1,0 +1,93 @@
+// exchange.cu -- the collectives of the compact view-parallel gradient exchange (parallel.py) as ONE hand-written kernel over
+// NVLink / NVSwitch multicast memory (NVLS), instead of an NCCL all-reduce followed by an NCCL all-gather:
+//   * the (N,12) summable columns: every rank owns 1/R of the rows, pulls their sum over all ranks with
+//     multimem.ld_reduce (the switch adds the R copies in flight) and pushes the result back to all ranks with multimem.st
+//     (the switch replicates the store) -- a two-shot all-reduce without staging buffers or protocol flags;
+//   * the per-view block [3N colour-argument gradients | 3 n_obj camera centres]: every rank pushes its own block into
+//     slot `rank` of every rank's buffer with multimem.st -- an all-gather with one store stream per rank.
+// Per GPU 48 MB/R + 12 MB leave and 48 MB + 96 MB arrive at N = 1e6, R = 8 (the NVLS minimum for this exchange); nothing is
+// copied through intermediate buffers.  The buffers live in ONE symmetric allocation (torch.distributed._symmetric_memory:
+// same offset on every rank, mapped into a multicast address); the caller brackets the kernel with two cross-rank barriers
+// (all compact rows written / all multicast stores landed).  sm_90+ PTX (multimem.*); SASS shows them as multimem ops.
+#include "common.cuh"
+
+namespace gsb {
+
+struct MultimemExchangeParams {
+    float *mc_sum;             // multicast address of the (N,12) rows
+    long long sum_float4;      // number of float4 in them (3 N)
+    float *mc_blocks;          // multicast address of the (R, block_stride) blocks
+    const float *local_block;  // this rank's own block (local address)
+    long long block_stride;    // floats between blocks
+    long long block_float4;    // float4 per block
+    int rank, world;
+};
+
+#ifndef GSB_HOST_EMU
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float *mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(mc)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st(float *mc, const float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+constexpr int MX_THREADS = 512;
+__global__ void __launch_bounds__(MX_THREADS) multimem_exchange_kernel(const MultimemExchangeParams p) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // the all-gather first: its stores are fire-and-forget and overlap the round trips of the reduction below
+    {
+        float *dst = p.mc_blocks + (size_t)p.rank * p.block_stride;
+        const float4 *src = reinterpret_cast<const float4 *>(p.local_block);
+        for (long long i = tid; i < p.block_float4; i += stride) multimem_st(dst + 4 * i, src[i]);
+    }
+    // two-shot all-reduce of this rank's slice of the summable rows
+    const long long per = (p.sum_float4 + p.world - 1) / p.world;
+    const long long lo = per * p.rank;
+    const long long hi = lo + per < p.sum_float4 ? lo + per : p.sum_float4;
+    for (long long i = lo + tid; i < hi; i += stride) {
+        float *a = p.mc_sum + 4 * i;
+        multimem_st(a, multimem_ld_reduce_add(a));
+    }
+}
+#endif
+
+}  // namespace gsb
+
+#ifndef GSB_HOST_EMU
+extern "C" int gsb200_exchange_multimem(const GsbMultimemExchangeArgs *a) {
+    using namespace gsb;
+    if (!a || !a->multicast_grad_sum || !a->multicast_blocks || !a->local_block || a->num_points < 0 || a->world_size < 1 ||
+        a->rank < 0 || a->rank >= a->world_size || a->block_stride < 3 * a->num_points + 3 * (int64_t)a->num_objects ||
+        a->block_stride % 4 != 0) {
+        set_error("exchange_multimem: bad arguments");
+        return GSB_EINVAL;
+    }
+    if (reinterpret_cast<uintptr_t>(a->multicast_grad_sum) % 16 || reinterpret_cast<uintptr_t>(a->multicast_blocks) % 16 ||
+        reinterpret_cast<uintptr_t>(a->local_block) % 16) {
+        set_error("exchange_multimem: pointers must be 16-byte aligned");
+        return GSB_EINVAL;
+    }
+    if (a->num_points == 0) return GSB_OK;
+    MultimemExchangeParams p;
+    p.mc_sum = a->multicast_grad_sum;
+    p.sum_float4 = 3 * a->num_points;
+    p.mc_blocks = a->multicast_blocks;
+    p.local_block = a->local_block;
+    p.block_stride = a->block_stride;
+    p.block_float4 = (3 * a->num_points + 3 * (int64_t)a->num_objects + 3) / 4;
+    p.rank = a->rank;
+    p.world = a->world_size;
+    const int blocks = a->num_blocks > 0 ? a->num_blocks : 2 * num_sms();
+    multimem_exchange_kernel<<<blocks, MX_THREADS, 0, static_cast<cudaStream_t>(a->stream)>>>(p);
+    GSB_CUDA_CHECK(cudaGetLastError());
+    return GSB_OK;
+}
+#endif

@@ -90,6 +90,13 @@ class ViewParallelExchange:
         if gather_group is not None and dist.get_world_size(gather_group) != self.world:
             raise ValueError("gather_group must span the same ranks as group")
 
+    def allocate(self, num_points: int, num_objects: int, device):
+        """The two exchange buffers of one backward: ``grad_sum`` (N,12) and ``blocks`` (R, stride), stride = 3N + 3 n_obj
+        rounded up to 16 bytes.  Plain device tensors here; the multicast variant hands out views of a symmetric allocation."""
+        stride = (3 * num_points + 3 * num_objects + 3) // 4 * 4
+        return (torch.empty((num_points, 12), dtype=torch.float32, device=device),
+                torch.empty((self.world, stride), dtype=torch.float32, device=device))
+
     def run(self, grad_sum: torch.Tensor, blocks: torch.Tensor) -> None:
         if blocks.shape[0] != self.world or not blocks.is_contiguous() or not grad_sum.is_contiguous():
             raise ValueError("blocks must be a contiguous (world, stride) tensor and grad_sum contiguous")
@@ -104,6 +111,60 @@ class ViewParallelExchange:
             w2 = dist.all_gather_into_tensor(blocks.view(-1), mine, group=self.gather_group, async_op=True)
             w1.wait()
             w2.wait()
+
+
+class MulticastViewParallelExchange(ViewParallelExchange):
+    """The same exchange with BOTH collectives done by one hand-written kernel over NVSwitch multicast memory
+    (``gsb200_exchange_multimem``, csrc/exchange.cu: ``multimem.ld_reduce`` / ``multimem.st``) instead of ncclAllReduce +
+    ncclAllGather.  The buffers of a scene size live in one symmetric allocation (``torch.distributed._symmetric_memory``:
+    same offset on every rank, mapped to a multicast address), created once and reused every step; the per-point backward
+    kernel writes its compact rows straight into it.  ``run`` = cross-rank barrier (every rank's rows are written), the
+    kernel, cross-rank barrier (every multicast store has landed).  Needs NVLS multicast support (one NVSwitch domain)."""
+
+    def __init__(self, group=None, barrier_timeout_ms: int = 20000):
+        super().__init__(group)
+        import torch.distributed._symmetric_memory as symm_mem
+        self._symm_mem = symm_mem
+        self._group = group if group is not None else dist.group.WORLD
+        self._cache = {}
+        self._timeout = int(barrier_timeout_ms)
+
+    def allocate(self, num_points: int, num_objects: int, device):
+        key = (num_points, num_objects, torch.device(device).index)
+        entry = self._cache.get(key)
+        if entry is None:
+            stride = (3 * num_points + 3 * num_objects + 3) // 4 * 4
+            sum_floats = 12 * num_points
+            flat = self._symm_mem.empty(sum_floats + self.world * stride, dtype=torch.float32, device=device)
+            hdl = self._symm_mem.rendezvous(flat, self._group)
+            if not hdl.multicast_ptr:
+                raise RuntimeError("MulticastViewParallelExchange: no NVLS multicast support for this group "
+                                   "(use ViewParallelExchange, the NCCL path)")
+            # multicast address of `flat`: the handle's pointers are those of the symmetric block, the tensor may sit at an offset
+            mc_flat = int(hdl.multicast_ptr) + (flat.data_ptr() - int(hdl.buffer_ptrs[hdl.rank]))
+            entry = dict(flat=flat, hdl=hdl, grad_sum=flat[:sum_floats].view(num_points, 12),
+                         blocks=flat[sum_floats:].view(self.world, stride), mc_sum=mc_flat, mc_blocks=mc_flat + 4 * sum_floats,
+                         stride=stride, num_points=num_points, num_objects=num_objects)
+            self._cache[key] = entry
+        self._current = entry
+        return entry["grad_sum"], entry["blocks"]
+
+    def run(self, grad_sum: torch.Tensor, blocks: torch.Tensor) -> None:
+        import ctypes
+        from . import _lib
+        e = self._current
+        if grad_sum.data_ptr() != e["grad_sum"].data_ptr() or blocks.data_ptr() != e["blocks"].data_ptr():
+            raise ValueError("MulticastViewParallelExchange.run needs the buffers handed out by allocate()")
+        hdl = e["hdl"]
+        with torch.cuda.device(grad_sum.device):
+            stream = torch.cuda.current_stream(grad_sum.device).cuda_stream
+            hdl.barrier(channel=0, timeout_ms=self._timeout)  # every rank's compact rows are in its buffer
+            args = _lib.GsbMultimemExchangeArgs(
+                num_points=e["num_points"], num_objects=e["num_objects"], rank=self.rank, world_size=self.world, num_blocks=0,
+                multicast_grad_sum=e["mc_sum"], multicast_blocks=e["mc_blocks"], local_block=blocks[self.rank].data_ptr(),
+                block_stride=e["stride"], stream=stream)
+            _lib.check(_lib.load().gsb200_exchange_multimem(ctypes.byref(args)), "gsb200_exchange_multimem")
+            hdl.barrier(channel=1, timeout_ms=self._timeout)  # every rank's multicast stores have landed everywhere
 
 
 def render_views(op, make_input, view_ids: Sequence[int]):

@@ -20,6 +20,10 @@ class _LocalExchange:
     def __init__(self, world, rank, store, replay):
         self.world, self.rank, self.store, self.replay = world, rank, store, replay
 
+    def allocate(self, num_points, num_objects, device):
+        stride = (3 * num_points + 3 * num_objects + 3) // 4 * 4
+        return (torch.empty((num_points, 12), device=device), torch.empty((self.world, stride), device=device))
+
     def run(self, grad_sum, blocks):
         if not self.replay:
             self.store[self.rank] = (grad_sum.clone(), blocks[self.rank].clone())
