@@ -42,19 +42,33 @@ constexpr int MX_THREADS = 512;
 __global__ void __launch_bounds__(MX_THREADS) multimem_exchange_kernel(const MultimemExchangeParams p) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int U = 4;  // independent requests in flight per thread (the reduction is a round trip through the switch)
     // the all-gather first: its stores are fire-and-forget and overlap the round trips of the reduction below
     {
         float *dst = p.mc_blocks + (size_t)p.rank * p.block_stride;
         const float4 *src = reinterpret_cast<const float4 *>(p.local_block);
-        for (long long i = tid; i < p.block_float4; i += stride) multimem_st(dst + 4 * i, src[i]);
+        for (long long i = tid; i < p.block_float4; i += U * stride) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i + u * stride < p.block_float4) v[u] = src[i + u * stride];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i + u * stride < p.block_float4) multimem_st(dst + 4 * (i + u * stride), v[u]);
+        }
     }
     // two-shot all-reduce of this rank's slice of the summable rows
     const long long per = (p.sum_float4 + p.world - 1) / p.world;
     const long long lo = per * p.rank;
     const long long hi = lo + per < p.sum_float4 ? lo + per : p.sum_float4;
-    for (long long i = lo + tid; i < hi; i += stride) {
-        float *a = p.mc_sum + 4 * i;
-        multimem_st(a, multimem_ld_reduce_add(a));
+    for (long long i = lo + tid; i < hi; i += U * stride) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride < hi) v[u] = multimem_ld_reduce_add(p.mc_sum + 4 * (i + u * stride));
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i + u * stride < hi) multimem_st(p.mc_sum + 4 * (i + u * stride), v[u]);
     }
 }
 #endif

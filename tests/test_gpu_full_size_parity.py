@@ -105,13 +105,15 @@ def test_full_size_forward_backward_vs_oracle(name, exact_exp):
 
     # ---- the assertions (allowances per 1e6 pixels / entries; the observed numbers are in the recorded file)
     px = H * W
-    # Observed on a B200 (profiles/r02_parity_counts.json): <= 2 pixels over 1e-4 (max 7e-4), <= 10 pixel-count flips of
-    # 2.06 M pixels, <= 282 of 48 M gradient entries outside 1e-3 rel + 1e-6 max|g|, none off by more than 1.3e-4 max|g|.
+    # Observed on a B200 over five runs (profiles/r02_parity_counts.json): <= 2 pixels over 1e-4 (max 7e-4), <= 14 pixel-count
+    # flips of 2.06 M pixels, <= 464 of 59 M gradient entries outside 1e-3 rel + 1e-6 max|g|, none off by more than 2.5e-4
+    # max|g| (the float atomics of loop A land in another order every run: two GPU runs differ from each other by up to
+    # 3e-4 / 6e-4 max|g|, bench.py exchange_check, so the bound on the largest deviation is north_star's 1e-3).
     assert d.max() <= 5e-3, entry                           # a flip moves a pixel by <= alpha_cut * T * |colour| ~ 4e-3
     assert bad.sum() <= max(4, 1e-5 * px), entry            # <= 10 flipped pixels per Mpix
     assert (bad & ~cnt_diff).sum() == 0, entry              # every pixel outside 1e-4 IS a cut-off flip (its count differs)
-    assert cnt_diff.sum() <= max(8, 2e-5 * px), entry
+    assert cnt_diff.sum() <= max(8, 3e-5 * px), entry
     for gname, _ in GROUPS:
         e = entry["grad_" + gname]
         assert e["violations_floor_1e-6"] <= max(20, 1e-4 * e["entries"]), entry
-        assert e["max_abs_err_over_max_abs_grad"] <= 3e-4, entry
+        assert e["max_abs_err_over_max_abs_grad"] <= 1e-3, entry
