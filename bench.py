@@ -63,6 +63,7 @@ def parse_args():
     ap.add_argument("--exchange", default="auto", choices=["auto", "multimem", "nccl"],
                     help="N > 1: collectives of the compact exchange: multimem = the hand-written NVLS kernel (gsb200_exchange_multimem), "
                          "nccl = ncclAllReduce + ncclAllGather, auto = multimem where the group has multicast support, else nccl")
+    ap.add_argument("--exchange-blocks", type=int, default=0, help="CTAs of the multimem exchange kernel (0 = two per SM)")
     ap.add_argument("--dense-exchange", action="store_true",
                     help="N > 1: one all-reduce of the dense gradients instead of the compact exchange (comparison)")
     return ap.parse_args()
@@ -232,7 +233,7 @@ def run_b200(args):
     if world > 1 and not args.dense_exchange:
         if args.exchange in ("auto", "multimem"):
             try:
-                exchange = MulticastViewParallelExchange()
+                exchange = MulticastViewParallelExchange(num_blocks=args.exchange_blocks)
                 exchange.allocate(CONFIGS[args.workload]["num_points"], 1, device)  # the rendezvous is a collective: do it up front
                 exchange_kind = "multimem"
             except Exception as e:  # no multicast support (or no symmetric-memory backend) on this box

@@ -121,8 +121,10 @@ class MulticastViewParallelExchange(ViewParallelExchange):
     kernel writes its compact rows straight into it.  ``run`` = cross-rank barrier (every rank's rows are written), the
     kernel, cross-rank barrier (every multicast store has landed).  Needs NVLS multicast support (one NVSwitch domain)."""
 
-    def __init__(self, group=None, barrier_timeout_ms: int = 20000):
+    def __init__(self, group=None, barrier_timeout_ms: int = 20000, num_blocks: int = 0):
+        """``num_blocks``: CTAs of the exchange kernel (0 = two per SM)."""
         super().__init__(group)
+        self._num_blocks = int(num_blocks)
         import torch.distributed._symmetric_memory as symm_mem
         self._symm_mem = symm_mem
         self._group = group if group is not None else dist.group.WORLD
@@ -160,7 +162,7 @@ class MulticastViewParallelExchange(ViewParallelExchange):
             stream = torch.cuda.current_stream(grad_sum.device).cuda_stream
             hdl.barrier(channel=0, timeout_ms=self._timeout)  # every rank's compact rows are in its buffer
             args = _lib.GsbMultimemExchangeArgs(
-                num_points=e["num_points"], num_objects=e["num_objects"], rank=self.rank, world_size=self.world, num_blocks=0,
+                num_points=e["num_points"], num_objects=e["num_objects"], rank=self.rank, world_size=self.world, num_blocks=self._num_blocks,
                 multicast_grad_sum=e["mc_sum"], multicast_blocks=e["mc_blocks"], local_block=blocks[self.rank].data_ptr(),
                 block_stride=e["stride"], stream=stream)
             _lib.check(_lib.load().gsb200_exchange_multimem(ctypes.byref(args)), "gsb200_exchange_multimem")
