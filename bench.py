@@ -320,10 +320,12 @@ def run_b200(args):
         sampler.start()
     for _ in range(warmup):
         wl.step()
-    total_ms = timed(wl.step, steps)
-    ms_per_step = total_ms / steps
+    # 1 + `repeats` timed regions of EXACTLY `steps` steps each; the headline is the MEDIAN region (BASELINE.md's protocol:
+    # median with p10 / p90 beside it), the first region is reported as well
+    regions = [timed(wl.step, steps) / steps for _ in range(1 + max(args.repeats, 0))]
+    first_region_ms = regions[0]
+    ms_per_step = statistics.median(regions)
     value = wl.mpix(ms_per_step)
-    regions = [ms_per_step] + [timed(wl.step, steps) / steps for _ in range(max(args.repeats, 0))]
     frame = op.last_frame
     M, Kk = frame.num_points_in_camera, frame.num_keys
     K_ref = int(frame.num_overlap_tiles.sum())  # pairs of the reference's 3-sigma squares (before the reach filter)
@@ -448,8 +450,8 @@ def run_b200(args):
         e2e_losses.append(float(loss_host[(k - 1) % 2]))
 
     run_e2e(3)
-    e2e_ms = timed(lambda: run_e2e(steps), 1, rewarm=0) / steps
-    e2e_regions = [e2e_ms] + [timed(lambda: run_e2e(steps), 1, rewarm=0) / steps for _ in range(max(args.repeats, 0))]
+    e2e_regions = [timed(lambda: run_e2e(steps), 1, rewarm=0) / steps for _ in range(1 + max(args.repeats, 0))]
+    e2e_ms = statistics.median(e2e_regions)
     e2e_value = wl.mpix(e2e_ms)
 
     # ---- forward-only numbers (inference: torch.no_grad, full outputs and rgb_only)
@@ -628,7 +630,8 @@ def run_b200(args):
                    "parallelism": parallelism,
                    "l2": "inputs larger than L2 (scene 236 MB + 200 MB workspace per frame vs 126 MB L2)",
                    "backward_impl": op.backward_impl},
-        "spread": dict(percentiles(regions), what=f"{len(regions)} timed regions of {steps} steps each (the first one is `value`)"),
+        "spread": dict(percentiles(regions), first_region_ms_per_step=round(first_region_ms, 4),
+                       what=f"{len(regions)} timed regions of {steps} steps each; `value` / `ms_per_step` are the median region"),
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(e2e_ms, 4),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "spread": percentiles(e2e_regions),
                 "what": "per step: pinned host target image + pose + intrinsics -> device (copy stream, one step ahead), forward, fused L1 loss + gradient kernel, backward, loss -> pinned host (read one step later, all inside the timed region)"},
