@@ -202,7 +202,12 @@ void gsb200_abi_sizes(int64_t *out3);
 void gsb200_abi_sizes_ext(int64_t *out, int32_t n);
 
 /* Workspace sizing.  far_plane*depth_to_sort_key_scale fixes the depth-key width; (H/16)*(W/16)
- * the tile-id width; both <= 32 bits total selects 32-bit sort keys. */
+ * the tile-id width; both <= 32 bits total selects 32-bit sort keys.
+ * Limits (GSB_EUNSUPPORTED beyond them): num_points < 2^26, key_capacity < 2^30.  The single-pass scan of the per-point stage
+ * carries (in-camera count, pair count) in one 64-bit word with 26 + 36 bits: a frame whose REFERENCE pair count (sum of
+ * num_overlap_tiles, before the reach filter and regardless of key_capacity) reached 2^36 = 6.9e10 would carry into the
+ * point count -- such a frame needs > 0.8 TB of keys in the reference and is far beyond key_capacity < 2^30, but it is the
+ * caller's responsibility not to submit one (e.g. millions of screen-filling splats at 4K). */
 int gsb200_workspace_layout(int64_t num_points, int32_t num_objects, int64_t key_capacity,
                             int32_t camera_height, int32_t camera_width, float far_plane,
                             float depth_to_sort_key_scale, uint32_t flags,
@@ -281,9 +286,11 @@ int gsb200_backward_timed(const GsbBackwardArgs *args, float *stage_ms_out);
 /* Diagnostics: the blend kernels' real work, counted on the device (SURVEY 8(d) "E": pixel x splat evaluations).  Call after
  * gsb200_forward (same args / workspace; re-renders the same outputs) resp. after it with the backward args of the same frame
  * (adds into accum like gsb200_backward's loop A; pass a scratch accumulator).  host_out2[0] = (warp, splat) visits -- 32
- * pixel x splat evaluations each --, host_out2[1] = evaluations that contribute (alpha >= 1/255 on a live pixel).  Blocks.
+ * pixel x splat evaluations each --, host_out2[1] = evaluations that contribute (alpha >= 1/255 on a live pixel).  The forward
+ * variant fills 8 slots: [2..4] are what-if counters taken at staging time -- (patch, splat) pairs with the kernel's 8x4 patches,
+ * with 8x8 patches (two pixels per thread) and with 16x4 patches -- the evidence for the patch shape in DESIGN.md.  Blocks.
  * (The reference's counterpart is the Taichi kernel profiler, GaussianPointTrainer.py:217-219.) */
-int gsb200_forward_blend_work(const GsbForwardArgs *args, uint64_t *host_out2);
+int gsb200_forward_blend_work(const GsbForwardArgs *args, uint64_t *host_out8);
 int gsb200_backward_blend_work(const GsbBackwardArgs *args, uint64_t *host_out2);
 
 /* Checks the two hardware facts the default arithmetic path relies on: rcp.approx(1.0f) == 1.0f (a non-contributing

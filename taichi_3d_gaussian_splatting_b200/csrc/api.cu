@@ -429,20 +429,29 @@ int gsb200_backward_timed(const GsbBackwardArgs *a, float *stage_ms_out) {
     return t.finish(stage_ms_out);
 }
 
-int gsb200_forward_blend_work(const GsbForwardArgs *a, uint64_t *host_out2) {
+int gsb200_forward_blend_work(const GsbForwardArgs *a, uint64_t *host_out8) {
     Workspace ws;
     int rc = resolve_fwd(a, &ws);
     if (rc != GSB_OK) return rc;
-    if (!host_out2 || a->rgb_only) {
-        set_error("forward_blend_work: host_out2 is null or rgb_only is set");
+    if (!host_out8 || a->rgb_only) {
+        set_error("forward_blend_work: host_out8 is null or rgb_only is set");
         return GSB_EINVAL;
     }
     cudaStream_t st = static_cast<cudaStream_t>(a->stream);
-    unsigned long long *cnt = reinterpret_cast<unsigned long long *>(ws.counters + 4);
-    GSB_CUDA_CHECK(cudaMemsetAsync(cnt, 0, 16, st));
-    if ((rc = launch_blend_forward_count(*a, ws, cnt, st)) != GSB_OK) return rc;
-    GSB_CUDA_CHECK(cudaMemcpyAsync(host_out2, cnt, 16, cudaMemcpyDeviceToHost, st));
-    GSB_CUDA_CHECK(cudaStreamSynchronize(st));
+    unsigned long long *cnt = nullptr;  // a blocking diagnostic: its own small allocation
+    GSB_CUDA_CHECK(cudaMalloc(&cnt, 64));
+    cudaError_t e = cudaMemsetAsync(cnt, 0, 64, st);
+    if (e == cudaSuccess) {
+        rc = launch_blend_forward_count(*a, ws, cnt, st);
+        if (rc == GSB_OK) e = cudaMemcpyAsync(host_out8, cnt, 64, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    cudaFree(cnt);
+    if (rc != GSB_OK) return rc;
+    if (e != cudaSuccess) {
+        set_error("forward_blend_work: %s", cudaGetErrorString(e));
+        return GSB_ECUDA;
+    }
     return GSB_OK;
 }
 

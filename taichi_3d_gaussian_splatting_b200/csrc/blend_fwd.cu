@@ -28,7 +28,10 @@ struct BlendFwdParams {
     int *last_effective;
     int *valid_count;
     unsigned long long *work_counters;  // COUNT instantiation only: [0] (warp, splat) visits, [1] (pixel, splat)
-                                        //   evaluations with alpha >= 1/255 on a live pixel (SURVEY 8(d) "E")
+                                        //   evaluations with alpha >= 1/255 on a live pixel (SURVEY 8(d) "E"); what-if
+                                        //   counters at staging time (before any saturation exit): [2] (8x4 patch, splat)
+                                        //   pairs, [3] the same with 8x8 patches (two pixels per thread, vertical pairs),
+                                        //   [4] with 16x4 patches (horizontal pairs)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) { return ex2_mufu(x); }
@@ -63,6 +66,7 @@ blend_forward_kernel(const BlendFwdParams p) {
     float T = 1.0f, Tlive = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, D = 0.0f, Wt = 0.0f;
     int last = start, cnt = 0;
     unsigned int n_visits = 0, n_pairs = 0;  // COUNT only
+    unsigned int n_p84 = 0, n_p88 = 0, n_p164 = 0;
     float4 *const ck0 = s_chunk[warp][0], *const ck1 = s_chunk[warp][1], *const ck2 = s_chunk[warp][2];
     unsigned char *const list = s_list[warp];
     const unsigned int lt_mask = (1u << lane) - 1u;
@@ -90,6 +94,11 @@ blend_forward_kernel(const BlendFwdParams p) {
             }
             s_r2[tid] = __ldg(rec + 2);
             mask = splat_patch_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y * r1.z, tile_x0, tile_y0);
+            if (COUNT) {  // patch w sits at column (w & 1), row (w >> 1)
+                n_p84 += __popc(mask);
+                n_p88 += __popc((mask | (mask >> 2)) & 0x33u);   // rows 0|1 and 2|3 merged
+                n_p164 += __popc((mask | (mask >> 1)) & 0x55u);  // the two columns merged
+            }
         }
 #pragma unroll
         for (int w = 0; w < 8; ++w) {
@@ -195,10 +204,16 @@ blend_forward_kernel(const BlendFwdParams p) {
         for (int d = 16; d > 0; d >>= 1) {
             n_visits += __shfl_xor_sync(0xffffffffu, n_visits, d);
             n_pairs += __shfl_xor_sync(0xffffffffu, n_pairs, d);
+            n_p84 += __shfl_xor_sync(0xffffffffu, n_p84, d);
+            n_p88 += __shfl_xor_sync(0xffffffffu, n_p88, d);
+            n_p164 += __shfl_xor_sync(0xffffffffu, n_p164, d);
         }
         if (lane == 0) {
             atomicAdd(p.work_counters, (unsigned long long)n_visits);
             atomicAdd(p.work_counters + 1, (unsigned long long)n_pairs);
+            atomicAdd(p.work_counters + 2, (unsigned long long)n_p84);
+            atomicAdd(p.work_counters + 3, (unsigned long long)n_p88);
+            atomicAdd(p.work_counters + 4, (unsigned long long)n_p164);
         }
     }
 }
