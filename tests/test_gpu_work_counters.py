@@ -39,3 +39,8 @@ def test_work_counters_agree_with_the_rendered_frame(name):
     assert w["backward_contributing_evaluations"] == blended
     assert w["backward_warp_splat_visits"] <= w["forward_warp_splat_visits"]
     assert w["forward_warp_splat_visits"] <= 8 * op.last_frame.num_keys
+    # what-if counters at staging time: every visit was staged; merging two patches never needs more (pair, splat) visits than
+    # the 8x4 patches and never fewer than half of them
+    p84, p88, p164 = w["staged_patch_pairs_8x4"], w["staged_patch_pairs_8x8"], w["staged_patch_pairs_16x4"]
+    assert w["forward_warp_splat_visits"] <= p84 <= 8 * op.last_frame.num_keys
+    assert p84 / 2 <= p88 <= p84 and p84 / 2 <= p164 <= p84
