@@ -467,6 +467,27 @@ def run_b200(args):
     fwd_ms = timed(fwd_only(op), steps) / steps
     fwd_rgb_ms = timed(fwd_only(op_rgb), steps) / steps
 
+    # inference THROUGHPUT with two frames in flight (parallel.render_views(..., streams=...)): consecutive frames on
+    # alternating streams, so the latency-bound per-point stage and sort of frame i+1 run under the blend of frame i
+    from taichi_3d_gaussian_splatting_b200.parallel import render_views
+    side_streams = [torch.cuda.Stream(device=device) for _ in range(2)]
+
+    def frames_in_flight(o, k):
+        main = torch.cuda.current_stream(device)
+        start = torch.cuda.Event()
+        start.record(main)
+        for st in side_streams:
+            st.wait_event(start)
+        render_views(o, lambda i: wl.dev_input, range(k), streams=side_streams)
+        for st in side_streams:
+            done = torch.cuda.Event()
+            done.record(st)
+            main.wait_event(done)
+    frames_in_flight(op_rgb, 4)
+    frames_in_flight(op, 4)
+    fwd2_ms = timed(lambda: frames_in_flight(op, steps), 1, rewarm=0) / steps
+    fwd2_rgb_ms = timed(lambda: frames_in_flight(op_rgb, steps), 1, rewarm=0) / steps
+
     # ---- inference e2e through the C ABI with HOST buffers (gsb200_render_host): pose + intrinsics H2D,
     #      forward (rgb_only), image D2H into pinned memory, every frame
     def render_host_e2e(k):
@@ -644,7 +665,12 @@ def run_b200(args):
                 "what": "per step: pinned host target image + pose + intrinsics -> device (copy stream, one step ahead), forward, fused L1 loss + gradient kernel, backward, loss -> pinned host (read one step later, all inside the timed region)"},
         "forward_only": {"Mpix_s": round(wl.mpix(fwd_ms), 2), "ms": round(fwd_ms, 4),
                          "rgb_only_Mpix_s": round(wl.mpix(fwd_rgb_ms), 2),
-                         "rgb_only_ms": round(fwd_rgb_ms, 4)},
+                         "rgb_only_ms": round(fwd_rgb_ms, 4),
+                         "two_frames_in_flight": {"Mpix_s": round(wl.mpix(fwd2_ms), 2), "ms_per_frame": round(fwd2_ms, 4),
+                                                  "rgb_only_Mpix_s": round(wl.mpix(fwd2_rgb_ms), 2),
+                                                  "rgb_only_ms_per_frame": round(fwd2_rgb_ms, 4),
+                                                  "what": "throughput of parallel.render_views(..., streams=2 streams): consecutive frames "
+                                                          "on alternating streams (per-point stage + sort of frame i+1 under the blend of frame i)"}},
         "forward_e2e_c_abi": render_host,
         "other_configs": side,
         "gpu_launches": launches_per_step * steps,

@@ -169,12 +169,22 @@ class MulticastViewParallelExchange(ViewParallelExchange):
             hdl.barrier(channel=1, timeout_ms=self._timeout)  # every rank's multicast stores have landed everywhere
 
 
-def render_views(op, make_input, view_ids: Sequence[int]):
+def render_views(op, make_input, view_ids: Sequence[int], streams: Optional[Sequence["torch.cuda.Stream"]] = None):
     """Inference helper: render this rank's shard of views (no communication). ``make_input(i)`` builds the
-    ``GaussianPointCloudRasterisationInput`` of view i."""
+    ``GaussianPointCloudRasterisationInput`` of view i.
+
+    ``streams``: two (or more) CUDA streams -> consecutive frames go to alternating streams, so that the latency-bound
+    stages of frame i+1 (per-point stage, radix sort: a few hundred resident warps) run under the issue-bound blend of frame i
+    instead of behind it.  Every frame owns its workspace and outputs, the operator's only host wait per frame ends after that
+    frame's first kernel, so nothing else changes; the caller must synchronise the streams (or wait on the outputs' stream)
+    before reading the images."""
     out = {}
     with torch.no_grad():
-        for i in view_ids:
-            image, depth, count = op(make_input(i))
+        for n, i in enumerate(view_ids):
+            if streams:
+                with torch.cuda.stream(streams[n % len(streams)]):
+                    image, depth, count = op(make_input(i))
+            else:
+                image, depth, count = op(make_input(i))
             out[i] = (image, depth, count)
     return out

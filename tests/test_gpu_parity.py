@@ -409,3 +409,31 @@ def test_filtered_and_unfiltered_key_lists_render_identically():
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
     assert torch.allclose(a[3], b[3], rtol=1e-4, atol=1e-5 * float(b[3].abs().max()))
     assert torch.allclose(a[4], b[4], rtol=1e-4, atol=1e-5 * float(b[4].abs().max()))
+
+
+def test_render_views_with_two_frames_in_flight_equals_sequential_rendering():
+    """parallel.render_views(..., streams=[s0, s1]): consecutive frames on alternating streams (each frame owns its
+    workspace and outputs) must give exactly the images of one-after-the-other rendering."""
+    from taichi_3d_gaussian_splatting_b200.parallel import render_views
+    scenes = [cuda_scene(_small_scene(95, npts=3000, yaw=float(y))) for y in (-6, -2, 2, 6, 9)]
+    base = scenes[0]
+    for sc in scenes[1:]:
+        sc.point_cloud, sc.point_cloud_features = base.point_cloud, base.point_cloud_features
+    op = make_op()
+
+    def make_input(i):
+        sc = scenes[i]
+        from gpu_helpers import Input
+        return Input(point_cloud=sc.point_cloud, point_cloud_features=sc.point_cloud_features, point_object_id=sc.point_object_id,
+                     point_invalid_mask=sc.point_invalid_mask, camera_info=sc.camera_info, q_pointcloud_camera=sc.q_pointcloud_camera,
+                     t_pointcloud_camera=sc.t_pointcloud_camera, color_max_sh_band=3)
+    seq = render_views(op, make_input, range(len(scenes)))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for st in streams:
+        st.wait_stream(torch.cuda.current_stream())
+    par = render_views(op, make_input, range(len(scenes)), streams=streams)
+    torch.cuda.synchronize()
+    for i in range(len(scenes)):
+        for a, b in zip(seq[i], par[i]):
+            assert torch.equal(a, b), i
