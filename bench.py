@@ -599,9 +599,11 @@ def run_b200(args):
     }
     p84, p88, p164 = work["staged_patch_pairs_8x4"], work["staged_patch_pairs_8x8"], work["staged_patch_pairs_16x4"]
     compute["patch_shape_what_if"] = {
-        "staged_patch_splat_pairs": {"8x4_one_pixel_per_thread": p84, "8x8_two_pixels_per_thread": p88, "16x4_two_pixels_per_thread": p164},
+        "staged_patch_splat_pairs": {"8x4_one_pixel_per_thread": p84, "8x8_two_pixels_per_thread": p88, "16x4_two_pixels_per_thread": p164,
+                                     "4x4_one_splat_per_half_warp": work["staged_patch_pairs_4x4"]},
         "relative_inner_loop_instructions": {"8x4": 1.0, "8x8": round(p88 * (4 + 2 * 28) / max(p84 * 32, 1), 3),
-                                             "16x4": round(p164 * (4 + 2 * 28) / max(p84 * 32, 1), 3)},
+                                             "16x4": round(p164 * (4 + 2 * 28) / max(p84 * 32, 1), 3),
+                                             "4x4_two_splats_per_warp_iteration_lower_bound": round(work["staged_patch_pairs_4x4"] / 2 / max(p84, 1), 3)},
         "what": "counted on the device at staging time: a two-pixels-per-thread warp (8x8 or 16x4 patch) visits a splat if either of its "
                 "two 8x4 halves can be reached and then pays ~4 shared + 2 x 28 per-pixel instructions instead of 32 per 8x4 visit"}
     ncu = None

@@ -31,7 +31,7 @@ struct BlendFwdParams {
                                         //   evaluations with alpha >= 1/255 on a live pixel (SURVEY 8(d) "E"); what-if
                                         //   counters at staging time (before any saturation exit): [2] (8x4 patch, splat)
                                         //   pairs, [3] the same with 8x8 patches (two pixels per thread, vertical pairs),
-                                        //   [4] with 16x4 patches (horizontal pairs)
+                                        //   [4] with 16x4 patches (horizontal pairs), [5] with 4x4 sub-patches
 };
 
 __device__ __forceinline__ float ex2_approx(float x) { return ex2_mufu(x); }
@@ -66,7 +66,7 @@ blend_forward_kernel(const BlendFwdParams p) {
     float T = 1.0f, Tlive = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, D = 0.0f, Wt = 0.0f;
     int last = start, cnt = 0;
     unsigned int n_visits = 0, n_pairs = 0;  // COUNT only
-    unsigned int n_p84 = 0, n_p88 = 0, n_p164 = 0;
+    unsigned int n_p84 = 0, n_p88 = 0, n_p164 = 0, n_p44 = 0;
     float4 *const ck0 = s_chunk[warp][0], *const ck1 = s_chunk[warp][1], *const ck2 = s_chunk[warp][2];
     unsigned char *const list = s_list[warp];
     const unsigned int lt_mask = (1u << lane) - 1u;
@@ -98,6 +98,14 @@ blend_forward_kernel(const BlendFwdParams p) {
                 n_p84 += __popc(mask);
                 n_p88 += __popc((mask | (mask >> 2)) & 0x33u);   // rows 0|1 and 2|3 merged
                 n_p164 += __popc((mask | (mask >> 1)) & 0x55u);  // the two columns merged
+                // ... and with 4x4 sub-patches (one splat per half-warp): the 16 sub-rectangles of the tile
+                const SplatReach rr = make_splat_reach(r0.z, r0.w, r1.x, r1.y * r1.z);
+                if (rr.mode == 2) n_p44 += 16;
+                else if (rr.mode == 1)
+                    for (int q = 0; q < 16; ++q) {
+                        const float X0 = tile_x0 + 4.0f * (q & 3) + 0.5f - r0.x, Y0 = tile_y0 + 4.0f * (q >> 2) + 0.5f - r0.y;
+                        n_p44 += rect_reachable(rr, X0, X0 + 3.0f, Y0, Y0 + 3.0f) ? 1 : 0;
+                    }
             }
         }
 #pragma unroll
@@ -207,6 +215,7 @@ blend_forward_kernel(const BlendFwdParams p) {
             n_p84 += __shfl_xor_sync(0xffffffffu, n_p84, d);
             n_p88 += __shfl_xor_sync(0xffffffffu, n_p88, d);
             n_p164 += __shfl_xor_sync(0xffffffffu, n_p164, d);
+            n_p44 += __shfl_xor_sync(0xffffffffu, n_p44, d);
         }
         if (lane == 0) {
             atomicAdd(p.work_counters, (unsigned long long)n_visits);
@@ -214,6 +223,7 @@ blend_forward_kernel(const BlendFwdParams p) {
             atomicAdd(p.work_counters + 2, (unsigned long long)n_p84);
             atomicAdd(p.work_counters + 3, (unsigned long long)n_p88);
             atomicAdd(p.work_counters + 4, (unsigned long long)n_p164);
+            atomicAdd(p.work_counters + 5, (unsigned long long)n_p44);
         }
     }
 }

@@ -117,6 +117,7 @@ def blend_work(op: GaussianPointCloudRasterisation, input_data, grad_image: torc
         out["forward_warp_splat_visits"], out["forward_contributing_evaluations"] = int(f[0]), int(f[1])
         # what-if at staging time: (patch, splat) pairs with 8x4 patches (the kernel's), 8x8 (two pixels per thread), 16x4
         out["staged_patch_pairs_8x4"], out["staged_patch_pairs_8x8"], out["staged_patch_pairs_16x4"] = int(f[2]), int(f[3]), int(f[4])
+        out["staged_patch_pairs_4x4"] = int(f[5])
         ba.flags = (ba.flags | _lib.GSB_FLAG_BACKWARD_TRANSPOSED | _lib.GSB_FLAG_NO_HOOK_STATS) & ~_lib.GSB_FLAG_EXACT_EXP
         keepalive[8].zero_()  # accum
         b = (ctypes.c_uint64 * 2)()
