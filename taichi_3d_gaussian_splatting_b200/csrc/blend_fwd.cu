@@ -37,8 +37,12 @@ struct BlendFwdParams {
 __device__ __forceinline__ float ex2_approx(float x) { return ex2_mufu(x); }
 
 #ifndef GSB_FWD_MIN_BLOCKS
-#define GSB_FWD_MIN_BLOCKS 5
+#define GSB_FWD_MIN_BLOCKS 4
 #endif
+#ifndef GSB_FWD_UNROLL
+#define GSB_FWD_UNROLL 8  // measured at C3: unroll 2 / 4 / 8 at 5 CTAs per SM 384 / 381 / 380 us, unroll 8 at 4 CTAs per SM (64 registers) 374 us
+#endif
+constexpr int FW_UNROLL = GSB_FWD_UNROLL;
 constexpr int FW_CHUNK = 32;  // splats per private chunk of a warp
 
 template <bool RGB_ONLY, bool EXACT_EXP, bool COUNT = false>
@@ -138,7 +142,7 @@ blend_forward_kernel(const BlendFwdParams p) {
             __syncwarp();
             if (COUNT) n_visits += (lane == 0) ? (unsigned int)n : 0u;
             if (lane == 0) GSB_EMU_COUNT(EC_FW_VISITS, n);
-#pragma unroll 4
+#pragma unroll FW_UNROLL
             for (int i = 0; i < n; ++i) {
                 const float4 r0 = ck0[i];  // u v a b               (fast: u v A B)
                 const float4 r1 = ck1[i];  // c rescale opacity depth (fast: C ro - depth)
