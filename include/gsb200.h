@@ -237,6 +237,9 @@ typedef struct GsbMultimemExchangeArgs {
     int64_t num_points;
     int32_t num_objects, rank, world_size;
     int32_t num_blocks;          /* CTAs to launch; 0 = 2 per SM */
+    int32_t phases;              /* 0 or 3 = both; 1 = only the all-gather push of this rank's block (needs no barrier in front if
+                                    the caller alternates the blocks buffer with the step parity); 2 = only the all-reduce */
+    int32_t reserved;
     float *multicast_grad_sum;   /* multicast address of the (N,12) rows */
     float *multicast_blocks;     /* multicast address of the (world_size, block_stride) blocks */
     const float *local_block;    /* this rank's own block [3N | 3 n_obj], local address */

@@ -453,6 +453,7 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
             _lib.check(lib.gsb200_backward(ctypes.byref(args)), "gsb200_backward")
             own_view_grad_xyz = None
             if compact:
+                exchange.rows_written(grad_sum, blocks)
                 if self.backward_valid_point_hook is not None:  # the hook sees this rank's own view (before the sum)
                     own_view_grad_xyz = grad_sum[frame.point_id_in_camera_list.long(), 0:3]
                 exchange.run(grad_sum, blocks)

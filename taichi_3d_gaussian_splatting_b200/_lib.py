@@ -70,7 +70,7 @@ class GsbBackwardArgs(ctypes.Structure):
 class GsbMultimemExchangeArgs(ctypes.Structure):
     _fields_ = [
         ("num_points", c_i64), ("num_objects", c_i32), ("rank", c_i32), ("world_size", c_i32), ("num_blocks", c_i32),
-        ("multicast_grad_sum", c_vp), ("multicast_blocks", c_vp), ("local_block", c_vp), ("block_stride", c_i64), ("stream", c_vp),
+        ("phases", c_i32), ("reserved", c_i32), ("multicast_grad_sum", c_vp), ("multicast_blocks", c_vp), ("local_block", c_vp), ("block_stride", c_i64), ("stream", c_vp),
     ]
 
 

@@ -6,7 +6,10 @@
 //   * the per-view block [3N colour-argument gradients | 3 n_obj camera centres]: every rank pushes its own block into
 //     slot `rank` of every rank's buffer with multimem.st -- an all-gather with one store stream per rank.
 // Per GPU 48 MB/R + 12 MB leave and 48 MB + 96 MB arrive at N = 1e6, R = 8 (the NVLS minimum for this exchange); nothing is
-// copied through intermediate buffers.  The buffers live in ONE symmetric allocation (torch.distributed._symmetric_memory:
+// copied through intermediate buffers.  The two halves can be launched separately (`phases`): a rank pushes its block as soon as its
+// own per-point kernel has finished -- BEFORE the barrier, into a buffer alternating with the step parity so that no peer can
+// still be reading it -- which lets the early ranks' pushes run under the slowest rank's compute; only the all-reduce needs
+// every rank's rows and follows the barrier.  The buffers live in ONE symmetric allocation (torch.distributed._symmetric_memory:
 // same offset on every rank, mapped into a multicast address); the caller brackets the kernel with two cross-rank barriers
 // (all compact rows written / all multicast stores landed).  sm_90+ PTX (multimem.*); SASS shows them as multimem ops.
 #include "common.cuh"
@@ -39,37 +42,45 @@ __device__ __forceinline__ void multimem_st(float *mc, const float4 v) {
 }
 
 constexpr int MX_THREADS = 512;
-__global__ void __launch_bounds__(MX_THREADS) multimem_exchange_kernel(const MultimemExchangeParams p) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    constexpr int U = 4;  // independent requests in flight per thread (the reduction is a round trip through the switch)
-    // the all-gather first: its stores are fire-and-forget and overlap the round trips of the reduction below
-    {
-        float *dst = p.mc_blocks + (size_t)p.rank * p.block_stride;
-        const float4 *src = reinterpret_cast<const float4 *>(p.local_block);
-        for (long long i = tid; i < p.block_float4; i += U * stride) {
-            float4 v[U];
+constexpr int MX_U = 4;  // independent requests in flight per thread (the reduction is a round trip through the switch)
+
+// all-gather: this rank's block -> slot `rank` on every rank (the switch replicates each store)
+__device__ __forceinline__ void push_block(const MultimemExchangeParams &p, long long tid, long long stride) {
+    float *dst = p.mc_blocks + (size_t)p.rank * p.block_stride;
+    const float4 *src = reinterpret_cast<const float4 *>(p.local_block);
+    for (long long i = tid; i < p.block_float4; i += MX_U * stride) {
+        float4 v[MX_U];
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (i + u * stride < p.block_float4) v[u] = src[i + u * stride];
+        for (int u = 0; u < MX_U; ++u)
+            if (i + u * stride < p.block_float4) v[u] = src[i + u * stride];
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (i + u * stride < p.block_float4) multimem_st(dst + 4 * (i + u * stride), v[u]);
-        }
+        for (int u = 0; u < MX_U; ++u)
+            if (i + u * stride < p.block_float4) multimem_st(dst + 4 * (i + u * stride), v[u]);
     }
-    // two-shot all-reduce of this rank's slice of the summable rows
+}
+
+// two-shot all-reduce of this rank's slice of the summable rows
+__device__ __forceinline__ void reduce_slice(const MultimemExchangeParams &p, long long tid, long long stride) {
     const long long per = (p.sum_float4 + p.world - 1) / p.world;
     const long long lo = per * p.rank;
     const long long hi = lo + per < p.sum_float4 ? lo + per : p.sum_float4;
-    for (long long i = lo + tid; i < hi; i += U * stride) {
-        float4 v[U];
+    for (long long i = lo + tid; i < hi; i += MX_U * stride) {
+        float4 v[MX_U];
 #pragma unroll
-        for (int u = 0; u < U; ++u)
+        for (int u = 0; u < MX_U; ++u)
             if (i + u * stride < hi) v[u] = multimem_ld_reduce_add(p.mc_sum + 4 * (i + u * stride));
 #pragma unroll
-        for (int u = 0; u < U; ++u)
+        for (int u = 0; u < MX_U; ++u)
             if (i + u * stride < hi) multimem_st(p.mc_sum + 4 * (i + u * stride), v[u]);
     }
+}
+
+template <bool PUSH, bool REDUCE>
+__global__ void __launch_bounds__(MX_THREADS) multimem_exchange_kernel(const MultimemExchangeParams p) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (PUSH) push_block(p, tid, stride);  // first: its stores are fire-and-forget and overlap the reduction's round trips
+    if (REDUCE) reduce_slice(p, tid, stride);
 }
 #endif
 
@@ -100,7 +111,15 @@ extern "C" int gsb200_exchange_multimem(const GsbMultimemExchangeArgs *a) {
     p.rank = a->rank;
     p.world = a->world_size;
     const int blocks = a->num_blocks > 0 ? a->num_blocks : 2 * num_sms();
-    multimem_exchange_kernel<<<blocks, MX_THREADS, 0, static_cast<cudaStream_t>(a->stream)>>>(p);
+    cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+    const int phases = a->phases == 0 ? 3 : a->phases;
+    if (phases == 3) multimem_exchange_kernel<true, true><<<blocks, MX_THREADS, 0, st>>>(p);
+    else if (phases == 1) multimem_exchange_kernel<true, false><<<blocks, MX_THREADS, 0, st>>>(p);
+    else if (phases == 2) multimem_exchange_kernel<false, true><<<blocks, MX_THREADS, 0, st>>>(p);
+    else {
+        set_error("exchange_multimem: phases must be 0 (both), 1 (gather), 2 (all-reduce) or 3");
+        return GSB_EINVAL;
+    }
     GSB_CUDA_CHECK(cudaGetLastError());
     return GSB_OK;
 }

@@ -97,6 +97,10 @@ class ViewParallelExchange:
         return (torch.empty((num_points, 12), dtype=torch.float32, device=device),
                 torch.empty((self.world, stride), dtype=torch.float32, device=device))
 
+    def rows_written(self, grad_sum: torch.Tensor, blocks: torch.Tensor) -> None:
+        """Called by the operator right after this rank's compact rows have been enqueued (before ``run``); the multicast
+        variant starts pushing its block here."""
+
     def run(self, grad_sum: torch.Tensor, blocks: torch.Tensor) -> None:
         if blocks.shape[0] != self.world or not blocks.is_contiguous() or not grad_sum.is_contiguous():
             raise ValueError("blocks must be a contiguous (world, stride) tensor and grad_sum contiguous")
@@ -137,36 +141,58 @@ class MulticastViewParallelExchange(ViewParallelExchange):
         if entry is None:
             stride = (3 * num_points + 3 * num_objects + 3) // 4 * 4
             sum_floats = 12 * num_points
-            flat = self._symm_mem.empty(sum_floats + self.world * stride, dtype=torch.float32, device=device)
+            # [grad_sum | blocks of even steps | blocks of odd steps]: a rank pushes its block BEFORE the step's barrier, so
+            # the buffer it writes must not be the one a slow peer may still be expanding from (the previous step's)
+            flat = self._symm_mem.empty(sum_floats + 2 * self.world * stride, dtype=torch.float32, device=device)
             hdl = self._symm_mem.rendezvous(flat, self._group)
             if not hdl.multicast_ptr:
                 raise RuntimeError("MulticastViewParallelExchange: no NVLS multicast support for this group "
                                    "(use ViewParallelExchange, the NCCL path)")
             # multicast address of `flat`: the handle's pointers are those of the symmetric block, the tensor may sit at an offset
             mc_flat = int(hdl.multicast_ptr) + (flat.data_ptr() - int(hdl.buffer_ptrs[hdl.rank]))
-            entry = dict(flat=flat, hdl=hdl, grad_sum=flat[:sum_floats].view(num_points, 12),
-                         blocks=flat[sum_floats:].view(self.world, stride), mc_sum=mc_flat, mc_blocks=mc_flat + 4 * sum_floats,
-                         stride=stride, num_points=num_points, num_objects=num_objects)
+            blocks = [flat[sum_floats + b * self.world * stride:sum_floats + (b + 1) * self.world * stride].view(self.world, stride)
+                      for b in range(2)]
+            entry = dict(flat=flat, hdl=hdl, grad_sum=flat[:sum_floats].view(num_points, 12), blocks=blocks, mc_sum=mc_flat,
+                         mc_blocks=[mc_flat + 4 * (sum_floats + b * self.world * stride) for b in range(2)], stride=stride,
+                         num_points=num_points, num_objects=num_objects, parity=1)
             self._cache[key] = entry
+        entry["parity"] ^= 1  # one allocate() per backward on every rank: the parities stay in step
         self._current = entry
-        return entry["grad_sum"], entry["blocks"]
+        return entry["grad_sum"], entry["blocks"][entry["parity"]]
 
-    def run(self, grad_sum: torch.Tensor, blocks: torch.Tensor) -> None:
+    def _launch(self, phases: int, blocks: torch.Tensor) -> None:
         import ctypes
         from . import _lib
         e = self._current
-        if grad_sum.data_ptr() != e["grad_sum"].data_ptr() or blocks.data_ptr() != e["blocks"].data_ptr():
-            raise ValueError("MulticastViewParallelExchange.run needs the buffers handed out by allocate()")
+        with torch.cuda.device(blocks.device):
+            args = _lib.GsbMultimemExchangeArgs(
+                num_points=e["num_points"], num_objects=e["num_objects"], rank=self.rank, world_size=self.world,
+                num_blocks=self._num_blocks, phases=phases, multicast_grad_sum=e["mc_sum"],
+                multicast_blocks=e["mc_blocks"][e["parity"]], local_block=blocks[self.rank].data_ptr(), block_stride=e["stride"],
+                stream=torch.cuda.current_stream(blocks.device).cuda_stream)
+            _lib.check(_lib.load().gsb200_exchange_multimem(ctypes.byref(args)), "gsb200_exchange_multimem")
+
+    def _check(self, grad_sum, blocks):
+        e = self._current
+        if grad_sum.data_ptr() != e["grad_sum"].data_ptr() or blocks.data_ptr() != e["blocks"][e["parity"]].data_ptr():
+            raise ValueError("MulticastViewParallelExchange needs the buffers handed out by the latest allocate()")
+        return e
+
+    def rows_written(self, grad_sum: torch.Tensor, blocks: torch.Tensor) -> None:
+        """This rank's rows are enqueued: push its block to every rank now, without waiting for the others -- early ranks'
+        pushes run under the slowest rank's compute.  Safe without a barrier: the destination is the buffer of this step's
+        parity, and a peer can only still be reading the OTHER one (to get here this rank has passed both barriers of the
+        previous step, which every peer enqueues behind its expansion of the step before that)."""
+        self._check(grad_sum, blocks)
+        self._launch(1, blocks)
+
+    def run(self, grad_sum: torch.Tensor, blocks: torch.Tensor) -> None:
+        e = self._check(grad_sum, blocks)
         hdl = e["hdl"]
         with torch.cuda.device(grad_sum.device):
-            stream = torch.cuda.current_stream(grad_sum.device).cuda_stream
             hdl.barrier(channel=0, timeout_ms=self._timeout)  # every rank's compact rows are in its buffer
-            args = _lib.GsbMultimemExchangeArgs(
-                num_points=e["num_points"], num_objects=e["num_objects"], rank=self.rank, world_size=self.world, num_blocks=self._num_blocks,
-                multicast_grad_sum=e["mc_sum"], multicast_blocks=e["mc_blocks"], local_block=blocks[self.rank].data_ptr(),
-                block_stride=e["stride"], stream=stream)
-            _lib.check(_lib.load().gsb200_exchange_multimem(ctypes.byref(args)), "gsb200_exchange_multimem")
-            hdl.barrier(channel=1, timeout_ms=self._timeout)  # every rank's multicast stores have landed everywhere
+            self._launch(2, blocks)                            # two-shot all-reduce of the summable columns
+            hdl.barrier(channel=1, timeout_ms=self._timeout)  # every rank's multicast stores (sums and blocks) have landed
 
 
 def render_views(op, make_input, view_ids: Sequence[int], streams: Optional[Sequence["torch.cuda.Stream"]] = None):

@@ -24,6 +24,9 @@ class _LocalExchange:
         stride = (3 * num_points + 3 * num_objects + 3) // 4 * 4
         return (torch.empty((num_points, 12), device=device), torch.empty((self.world, stride), device=device))
 
+    def rows_written(self, grad_sum, blocks):
+        pass
+
     def run(self, grad_sum, blocks):
         if not self.replay:
             self.store[self.rank] = (grad_sum.clone(), blocks[self.rank].clone())
