@@ -231,7 +231,9 @@ def run_b200(args):
     Input = GPCR.GaussianPointCloudRasterisationInput
     exchange, exchange_kind = None, "dense all-reduce"
     if world > 1 and not args.dense_exchange:
-        if args.exchange in ("auto", "multimem"):
+        # measured (profiles/r02_bench_n*_{multimem,nccl}.json): at 2 ranks the NCCL collectives win (1.69 vs 1.73 ms per step: two
+        # barriers + two launches outweigh 60 MB of wire time), from 4 ranks on the hand-written NVLS kernel does (8 ranks: 1.90 vs 2.00)
+        if args.exchange == "multimem" or (args.exchange == "auto" and world >= 4):
             try:
                 exchange = MulticastViewParallelExchange(num_blocks=args.exchange_blocks)
                 exchange.allocate(CONFIGS[args.workload]["num_points"], 1, device)  # the rendezvous is a collective: do it up front
