@@ -64,6 +64,9 @@ def parse_args():
                     help="N > 1: collectives of the compact exchange: multimem = the hand-written NVLS kernel (gsb200_exchange_multimem), "
                          "nccl = ncclAllReduce + ncclAllGather, auto = multimem where the group has multicast support, else nccl")
     ap.add_argument("--exchange-blocks", type=int, default=0, help="CTAs of the multimem exchange kernel (0 = two per SM)")
+    ap.add_argument("--serial-expansion", action="store_true",
+                    help="multimem exchange: expand the dense gradients after the all-reduce in one pass (comparison) instead of "
+                         "expanding the SH columns on a second stream while the all-reduce is on the wire")
     ap.add_argument("--dense-exchange", action="store_true",
                     help="N > 1: one all-reduce of the dense gradients instead of the compact exchange (comparison)")
     return ap.parse_args()
@@ -235,7 +238,7 @@ def run_b200(args):
         # barriers + two launches outweigh 60 MB of wire time), from 4 ranks on the hand-written NVLS kernel does (8 ranks: 1.90 vs 2.00)
         if args.exchange == "multimem" or (args.exchange == "auto" and world >= 4):
             try:
-                exchange = MulticastViewParallelExchange(num_blocks=args.exchange_blocks)
+                exchange = MulticastViewParallelExchange(num_blocks=args.exchange_blocks, overlap_expansion=not args.serial_expansion)
                 exchange.allocate(CONFIGS[args.workload]["num_points"], 1, device)  # the rendezvous is a collective: do it up front
                 exchange_kind = "multimem"
             except Exception as e:  # no multicast support (or no symmetric-memory backend) on this box
@@ -644,7 +647,9 @@ def run_b200(args):
                                   f"thread per physical core"}
 
     launches_per_step = profiling.KERNELS_PER_FORWARD(frame.layout.sort_passes) + profiling.KERNELS_PER_BACKWARD + \
-        (1 if exchange is not None else 0)  # + gsb200_expand_view_gradients
+        (0 if exchange is None else                       # + gsb200_expand_view_gradients (two launches when split around the
+         (1 if exchange_kind != "multimem" else            #   all-reduce) + the two launches of gsb200_exchange_multimem
+          (3 if args.serial_expansion else 4)))
     if world == 1:
         parallelism = "single GPU"
     elif exchange is not None:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GSB200_VERSION 101 /* major*100 + minor */
+#define GSB200_VERSION 102 /* major*100 + minor */
 
 #define GSB_TILE_WIDTH 16     /* GPCR:27 */
 #define GSB_TILE_HEIGHT 16    /* GPCR:28 */
@@ -70,7 +70,8 @@ typedef struct GsbWorkspaceLayout {
     int64_t total_bytes;
     int64_t zero_bytes;        /* [0, zero_bytes) is memset to 0 at the start of every forward */
     int64_t counters;          /* int64[8]: [0]=M in-frustum points, [1]=K (tile,splat) pairs emitted/needed,
-                                  [2]=overflow (K > key_capacity), [3]=sorted-buffer selector (0=a,1=b) */
+                                  [2]=overflow (K > key_capacity), [4]=largest depth key int32(depth * scale) of the frame
+                                  (low 32 bits): the sort only runs the passes its live bits need */
     int64_t tickets;           /* uint32[16] dynamic block tickets */
     int64_t scan_state;        /* uint64[scan_blocks+1] decoupled look-back state of the compaction scan (one word per 128-point CTA) */
     int64_t sort_hist;         /* uint32[8][1024] global digit histograms */
@@ -83,8 +84,10 @@ typedef struct GsbWorkspaceLayout {
     int64_t num_tiles;         /* int32[N]  num_overlap_tiles, GPCR:904-911 */
     int64_t records;           /* float[N][12]: u v a b | c rescale opacity depth | r g b radius */
     int64_t point_in_camera;   /* float[N][3] GPCR:877 */
-    int64_t keys_a, keys_b;    /* sort keys ping-pong, key_bytes each, key_capacity_padded entries */
+    int64_t keys_a, keys_b;    /* sort keys, key_bytes each, key_capacity_padded entries: a = as emitted (never written by
+                                  the sort), b = sorted (whatever the number of radix passes that ran) */
     int64_t vals_a, vals_b;    /* int32 payload = in-camera offset, GPCR:930 */
+    int64_t keys_c, vals_c;    /* scratch of the radix passes (third buffer of the a -> [c -> b ->] ... -> b rotation) */
     int32_t key_bytes;         /* 4 or 8 */
     int32_t tile_bits, depth_bits, sort_passes;
     int64_t key_capacity_padded;
@@ -187,6 +190,9 @@ typedef struct GsbExpandArgs {
     const int32_t *point_object_id; /* (N) */
     int32_t color_max_sh_band;
     float grad_color_factor, grad_high_order_color_factor;
+    int32_t part;                    /* 0: everything.  1: only the 48 SH columns (reads the blocks, not grad_sum); 2: only xyz and the
+                                        q / s / logit columns (reads grad_sum, not the blocks).  1 and 2 write disjoint pieces of
+                                        the outputs, so 1 can run on another stream while the all-reduce of grad_sum is in flight */
     float *grad_pointcloud;          /* (N,3) out */
     float *grad_pointcloud_features; /* (N,56) out */
     void *stream;

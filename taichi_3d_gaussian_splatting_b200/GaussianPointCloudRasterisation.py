@@ -148,13 +148,10 @@ class Frame:
     def point_radii(self) -> torch.Tensor:
         return self.records[:, 11]
 
-    def _sorted_is_b(self) -> bool:
-        return self.layout.sort_passes % 2 == 1
-
     @property
     def sorted_keys(self) -> torch.Tensor:
         """Sorted packed keys (tile << depth_bits | depth), int64 regardless of the device key width."""
-        off = self.layout.keys_b if self._sorted_is_b() else self.layout.keys_a
+        off = self.layout.keys_b  # the sort always ends in b
         n = min(self.num_keys, self.key_capacity)
         if self.layout.key_bytes == 4:
             return self._view(off, self.layout.key_capacity_padded, torch.int32)[:n].to(torch.int64) & 0xFFFFFFFF
@@ -162,7 +159,7 @@ class Frame:
 
     @property
     def point_offset_with_sort_key(self) -> torch.Tensor:
-        off = self.layout.vals_b if self._sorted_is_b() else self.layout.vals_a
+        off = self.layout.vals_b
         n = min(self.num_keys, self.key_capacity)
         return self._view(off, self.layout.key_capacity_padded, torch.int32)[:n]
 
@@ -456,16 +453,21 @@ class GaussianPointCloudRasterisation(torch.nn.Module):
                 exchange.rows_written(grad_sum, blocks)
                 if self.backward_valid_point_hook is not None:  # the hook sees this rank's own view (before the sum)
                     own_view_grad_xyz = grad_sum[frame.point_id_in_camera_list.long(), 0:3]
-                exchange.run(grad_sum, blocks)
-                eargs = _lib.GsbExpandArgs(
-                    num_points=N, num_views=exchange.world, num_objects=ctx.num_objects, grad_sum=_ptr(grad_sum),
-                    grad_color_views=_ptr(blocks), view_stride=blocks.shape[1], pointcloud=_ptr(pointcloud),
-                    point_object_id=_ptr(point_object_id), color_max_sh_band=band_i,
-                    grad_color_factor=cfg.grad_color_factor,
-                    grad_high_order_color_factor=cfg.grad_high_order_color_factor,
-                    grad_pointcloud=_ptr(grad_pointcloud), grad_pointcloud_features=_ptr(grad_pointcloud_features),
-                    stream=stream.cuda_stream)
-                _lib.check(lib.gsb200_expand_view_gradients(ctypes.byref(eargs)), "gsb200_expand_view_gradients")
+
+                def expand(part: int) -> None:
+                    """Dense gradients from the exchanged compact rows, on the CURRENT stream (part 0: everything; 1: the SH
+                    columns, which need only the gathered blocks; 2: the summed columns) -- csrc/blend_bwd.cu."""
+                    eargs = _lib.GsbExpandArgs(
+                        num_points=N, num_views=exchange.world, num_objects=ctx.num_objects, grad_sum=_ptr(grad_sum),
+                        grad_color_views=_ptr(blocks), view_stride=blocks.shape[1], pointcloud=_ptr(pointcloud),
+                        point_object_id=_ptr(point_object_id), color_max_sh_band=band_i,
+                        grad_color_factor=cfg.grad_color_factor,
+                        grad_high_order_color_factor=cfg.grad_high_order_color_factor, part=part,
+                        grad_pointcloud=_ptr(grad_pointcloud), grad_pointcloud_features=_ptr(grad_pointcloud_features),
+                        stream=torch.cuda.current_stream(device).cuda_stream)
+                    _lib.check(lib.gsb200_expand_view_gradients(ctypes.byref(eargs)), "gsb200_expand_view_gradients")
+
+                exchange.run_and_expand(grad_sum, blocks, expand)
 
             hook = self.backward_valid_point_hook
             if hook is not None:  # GPCR:1127-1142

@@ -27,7 +27,7 @@ class GsbWorkspaceLayout(ctypes.Structure):
         ("scan_state", c_i64), ("sort_hist", c_i64), ("sort_state", c_i64), ("tile_start", c_i64),
         ("tile_end", c_i64), ("poses", c_i64), ("point_id", c_i64), ("point_offset", c_i64), ("num_tiles", c_i64),
         ("records", c_i64), ("point_in_camera", c_i64), ("keys_a", c_i64), ("keys_b", c_i64),
-        ("vals_a", c_i64), ("vals_b", c_i64), ("key_bytes", c_i32), ("tile_bits", c_i32),
+        ("vals_a", c_i64), ("vals_b", c_i64), ("keys_c", c_i64), ("vals_c", c_i64), ("key_bytes", c_i32), ("tile_bits", c_i32),
         ("depth_bits", c_i32), ("sort_passes", c_i32), ("key_capacity_padded", c_i64),
         ("sort_blocks", c_i32), ("scan_blocks", c_i32), ("radix_bits", c_i32), ("reserved", c_i32),
     ]
@@ -89,7 +89,7 @@ class GsbExpandArgs(ctypes.Structure):
         ("num_points", c_i64), ("num_views", c_i32), ("num_objects", c_i32), ("grad_sum", c_vp),
         ("grad_color_views", c_vp), ("view_stride", c_i64), ("pointcloud", c_vp), ("point_object_id", c_vp),
         ("color_max_sh_band", c_i32), ("grad_color_factor", c_f32), ("grad_high_order_color_factor", c_f32),
-        ("grad_pointcloud", c_vp), ("grad_pointcloud_features", c_vp), ("stream", c_vp),
+        ("part", c_i32), ("grad_pointcloud", c_vp), ("grad_pointcloud_features", c_vp), ("stream", c_vp),
     ]
 
 

@@ -90,6 +90,8 @@ static int compute_layout(int64_t N, int32_t n_obj, int64_t key_capacity, int32_
     L->keys_b = take(L->key_capacity_padded * L->key_bytes);
     L->vals_a = take(L->key_capacity_padded * 4);
     L->vals_b = take(L->key_capacity_padded * 4);
+    L->keys_c = take(L->key_capacity_padded * L->key_bytes);
+    L->vals_c = take(L->key_capacity_padded * 4);
     L->total_bytes = off;
     return GSB_OK;
 }
@@ -126,6 +128,8 @@ int resolve_workspace(void *base, int64_t bytes, int64_t N, int32_t n_obj, int64
     ws->keys_b = b + L.keys_b;
     ws->vals_a = reinterpret_cast<int *>(b + L.vals_a);
     ws->vals_b = reinterpret_cast<int *>(b + L.vals_b);
+    ws->keys_c = b + L.keys_c;
+    ws->vals_c = reinterpret_cast<int *>(b + L.vals_c);
     return GSB_OK;
 }
 
@@ -339,7 +343,7 @@ int gsb200_train_step(const GsbTrainStepArgs *t) {
 }
 
 int gsb200_expand_view_gradients(const GsbExpandArgs *a) {
-    if (!a || a->num_points < 0 || a->num_views < 1 || a->num_objects < 1 ||
+    if (!a || a->num_points < 0 || a->num_views < 1 || a->num_objects < 1 || a->part < 0 || a->part > 2 ||
         (a->num_points > 0 && (!a->grad_sum || !a->grad_color_views || !a->pointcloud || !a->point_object_id ||
                                !a->grad_pointcloud || !a->grad_pointcloud_features)) ||
         a->view_stride < 3 * a->num_points + 3 * (int64_t)a->num_objects) {
@@ -561,8 +565,8 @@ int gsb200_sort_pairs(const void *keys_in, const int32_t *vals_in, void *keys_ou
     GSB_CUDA_CHECK(cudaMemsetAsync(b, 0, (size_t)(512 + 8 * 1024 * 4 + state_bytes), st));
     const long long n_host = n;
     GSB_CUDA_CHECK(cudaMemcpyAsync(n_dev, &n_host, sizeof(n_host), cudaMemcpyHostToDevice, st));
-    return sort_pairs_device(keys_in, vals_in, keys_out, vals_out, n_dev, padded, key_bytes, end_bit, hist,
-                             state, tickets, tmp_keys, tmp_vals, nullptr, st);
+    return sort_pairs_device(keys_in, vals_in, keys_out, vals_out, n_dev, padded, key_bytes, 0, end_bit, nullptr, hist,
+                             state, tickets, tmp_keys, tmp_vals, st);
 }
 
 int gsb200_render_host(const GsbForwardArgs *device_args, const float *host_q, const float *host_t,

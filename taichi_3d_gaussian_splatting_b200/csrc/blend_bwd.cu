@@ -262,14 +262,13 @@ int launch_blend_backward_work(const GsbBackwardArgs &a, const Workspace &ws, un
 }
 
 static BlendBwdParams make_blend_bwd_params(const GsbBackwardArgs &a, const Workspace &ws) {
-    const GsbWorkspaceLayout &L = ws.layout;
     BlendBwdParams p;
     p.H = a.camera_height;
     p.W = a.camera_width;
     p.tiles_x = a.camera_width / GSB_TILE_WIDTH;
     p.tile_start = ws.tile_start;
     p.tile_end = ws.tile_end;
-    p.sorted_vals = (L.sort_passes % 2) == 1 ? ws.vals_b : ws.vals_a;
+    p.sorted_vals = ws.vals_b;  // the sort always ends in b
     p.records = ws.records;
     p.grad_image = a.grad_rasterized_image;
     p.acc_alpha = a.pixel_accumulated_alpha;
@@ -281,14 +280,13 @@ static BlendBwdParams make_blend_bwd_params(const GsbBackwardArgs &a, const Work
 }
 
 int launch_blend_backward(const GsbBackwardArgs &a, const Workspace &ws, cudaStream_t stream) {
-    const GsbWorkspaceLayout &L = ws.layout;
     BlendBwdParams p;
     p.H = a.camera_height;
     p.W = a.camera_width;
     p.tiles_x = a.camera_width / GSB_TILE_WIDTH;
     p.tile_start = ws.tile_start;
     p.tile_end = ws.tile_end;
-    p.sorted_vals = (L.sort_passes % 2) == 1 ? ws.vals_b : ws.vals_a;
+    p.sorted_vals = ws.vals_b;  // the sort always ends in b
     p.records = ws.records;
     p.grad_image = a.grad_rasterized_image;
     p.acc_alpha = a.pixel_accumulated_alpha;
@@ -582,6 +580,10 @@ struct ExpandParams {
     float *grad_feat;
 };
 
+// PART: 0 = everything; 1 = only the 48 SH columns (needs the all-gathered blocks, not the summed rows); 2 = only the summed
+// columns xyz / q / s / logit (needs the all-reduced rows, not the blocks).  Parts 1 and 2 write disjoint 32-byte-aligned
+// pieces of every row, so part 1 can run -- on another stream -- while the all-reduce is still on the wire (parallel.py).
+template <int PART>
 __global__ void __launch_bounds__(GSB_POINTS_THREADS, 4)
 expand_view_gradients_kernel(const ExpandParams p) {
     __shared__ __align__(16) float s_feat[GSB_POINTS_THREADS / 32][32 * PT_ROW];
@@ -593,12 +595,15 @@ expand_view_gradients_kernel(const ExpandParams p) {
     for (long long base = (long long)blockIdx.x * blockDim.x + warp * 32; base < p.N; base += stride) {
         const long long id = base + lane;
         if (id < p.N) {
-            const float4 *srow = reinterpret_cast<const float4 *>(p.grad_sum + 12 * (size_t)id);
-            const float4 s0 = __ldg(srow), s1 = __ldg(srow + 1), s2 = __ldg(srow + 2);
-            my_xyz[0] = s0.x; my_xyz[1] = s0.y; my_xyz[2] = s0.z;
             float4 *gf = reinterpret_cast<float4 *>(my_feat);
-            gf[0] = make_float4(s0.w, s1.x, s1.y, s1.z);
-            gf[1] = make_float4(s1.w, s2.x, s2.y, s2.z);
+            if (PART != 1) {
+                const float4 *srow = reinterpret_cast<const float4 *>(p.grad_sum + 12 * (size_t)id);
+                const float4 s0 = __ldg(srow), s1 = __ldg(srow + 1), s2 = __ldg(srow + 2);
+                my_xyz[0] = s0.x; my_xyz[1] = s0.y; my_xyz[2] = s0.z;
+                gf[0] = make_float4(s0.w, s1.x, s1.y, s1.z);
+                gf[1] = make_float4(s1.w, s2.x, s2.y, s2.z);
+            }
+            if (PART != 2) {
             float acc[3][16];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch)
@@ -627,6 +632,7 @@ expand_view_gradients_kernel(const ExpandParams p) {
                                                       4 * k4 + 1 < p.first_cleared ? acc[ch][4 * k4 + 1] : 0.0f,
                                                       4 * k4 + 2 < p.first_cleared ? acc[ch][4 * k4 + 2] : 0.0f,
                                                       4 * k4 + 3 < p.first_cleared ? acc[ch][4 * k4 + 3] : 0.0f);
+            }
         }
         __syncwarp();
         const long long rows = p.N - base < 32 ? p.N - base : 32;
@@ -635,13 +641,16 @@ expand_view_gradients_kernel(const ExpandParams p) {
         for (int it = 0; it < GSB_FEATURE_DIM / 4; ++it) {
             const int f = it * 32 + lane;
             const int row = f / (GSB_FEATURE_DIM / 4), c4 = f - row * (GSB_FEATURE_DIM / 4);
-            if (row < rows) out_f[f] = *reinterpret_cast<const float4 *>(&s_feat[warp][row * PT_ROW + 4 * c4]);
+            const bool mine = PART == 0 || (PART == 1 ? c4 >= 2 : c4 < 2);  // float4 0..1 = q s logit, 2..13 = SH
+            if (row < rows && mine) out_f[f] = *reinterpret_cast<const float4 *>(&s_feat[warp][row * PT_ROW + 4 * c4]);
         }
-        float *const out_x = p.grad_xyz + 3 * (size_t)base;
+        if (PART != 1) {
+            float *const out_x = p.grad_xyz + 3 * (size_t)base;
 #pragma unroll
-        for (int it = 0; it < 3; ++it) {
-            const int f = it * 32 + lane;
-            if (f < 3 * rows) out_x[f] = s_xyz[warp][f];
+            for (int it = 0; it < 3; ++it) {
+                const int f = it * 32 + lane;
+                if (f < 3 * rows) out_x[f] = s_xyz[warp][f];
+            }
         }
         __syncwarp();
     }
@@ -709,7 +718,9 @@ int launch_expand_view_gradients(const GsbExpandArgs &a, cudaStream_t stream) {
     long long blocks = (a.num_points + GSB_POINTS_THREADS - 1) / GSB_POINTS_THREADS;
     const long long cap = 16LL * num_sms();
     if (blocks > cap) blocks = cap;
-    expand_view_gradients_kernel<<<(int)blocks, GSB_POINTS_THREADS, 0, stream>>>(p);
+    if (a.part == 1) expand_view_gradients_kernel<1><<<(int)blocks, GSB_POINTS_THREADS, 0, stream>>>(p);
+    else if (a.part == 2) expand_view_gradients_kernel<2><<<(int)blocks, GSB_POINTS_THREADS, 0, stream>>>(p);
+    else expand_view_gradients_kernel<0><<<(int)blocks, GSB_POINTS_THREADS, 0, stream>>>(p);
     GSB_CUDA_CHECK(cudaGetLastError());
     return GSB_OK;
 }

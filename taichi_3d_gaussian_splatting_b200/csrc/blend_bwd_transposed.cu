@@ -54,6 +54,25 @@ constexpr int TB_P1_UNROLL = GSB_TB_P1_UNROLL;
 #ifndef GSB_TB_MIN_BLOCKS
 #define GSB_TB_MIN_BLOCKS 3  // 73 KB of shared memory per CTA allow 3; tuning knob (GSB200_DEFINES="-DGSB_TB_MIN_BLOCKS=2")
 #endif
+// P if (idx < last && P >= 1/255) else 0 -- the two tests folded into one predicate (ISETP, FSETP.AND, FSEL instead of
+// the two selects the compiler makes of the && expression)
+__device__ __forceinline__ float keep_if_contributing(float P, int idx, int last) {
+#ifdef GSB_HOST_EMU
+    return ((idx < last) && (P >= 1.0f / 255.0f)) ? P : 0.0f;
+#else
+    float r;
+    asm("{\n"
+        ".reg .pred p, q;\n"
+        "setp.lt.s32 q, %2, %3;\n"
+        "setp.ge.and.f32 p, %1, 0f3B808081, q;\n"   // 1.0f / 255.0f
+        "selp.f32 %0, %1, 0f00000000, p;\n"
+        "}\n"
+        : "=f"(r)
+        : "f"(P), "r"(idx), "r"(last));
+    return r;
+#endif
+}
+
 template <bool EXACT_EXP, bool STATS, bool COUNT = false>
 __global__ void __launch_bounds__(GSB_TILE_PIXELS, GSB_TB_MIN_BLOCKS)
 blend_backward_transposed_kernel(const BlendBwdParams p) {
@@ -223,7 +242,7 @@ blend_backward_transposed_kernel(const BlendBwdParams p) {
                         // A pair that does not contribute gets P = 0: then alpha = 0, 1/(1-alpha) = 1, T and w0 keep their
                         // values and G = aT = 0 -- no other select is needed.
                         float P = fast_alpha(d0, d1, r0.z, r0.w, r1.x, r1.y);
-                        P = ((idx < last) && (P >= 1.0f / 255.0f)) ? P : 0.0f;
+                        P = keep_if_contributing(P, idx, last);
                         const float alpha = fminf(P, 0.99f);
                         const float inv = rcp_approx(1.0f - alpha);
                         T *= inv;                 // T_i = T_{i+1} / (1 - alpha), GPCR:640

@@ -36,6 +36,26 @@ struct BlendFwdParams {
 
 __device__ __forceinline__ float ex2_approx(float x) { return ex2_mufu(x); }
 
+// cnt += 1 and last = idx for a blended pair (wgt > 0): one FSETP and two predicated moves instead of the four instructions
+// the compiler makes of the two selects
+__device__ __forceinline__ void count_if_blended(float wgt, int idx, int &cnt, int &last) {
+#ifdef GSB_HOST_EMU
+    if (wgt > 0.0f) {
+        cnt += 1;
+        last = idx;
+    }
+#else
+    asm("{\n"
+        ".reg .pred p;\n"
+        "setp.gt.f32 p, %2, 0f00000000;\n"
+        "@p add.s32 %0, %0, 1;\n"
+        "@p mov.b32 %1, %3;\n"
+        "}\n"
+        : "+r"(cnt), "+r"(last)
+        : "f"(wgt), "r"(idx));
+#endif
+}
+
 #ifndef GSB_FWD_MIN_BLOCKS
 #define GSB_FWD_MIN_BLOCKS 4
 #endif
@@ -65,8 +85,8 @@ blend_forward_kernel(const BlendFwdParams p) {
     const float tile_x0 = (float)(tu * GSB_TILE_WIDTH), tile_y0 = (float)(tv * GSB_TILE_HEIGHT);
     const int start = p.tile_start[tile], end = p.tile_end[tile];
 
-    // T is the working transmittance: it is forced to 0 once the pixel has saturated, which makes every later splat
-    // fail the T(1-a) >= 1e-4 test without a separate flag; Tlive keeps the value to output.
+    // T is the working transmittance; once the pixel has saturated it is <= 0 (exact path: 0, with Tlive keeping the value
+    // to output; fast path: minus the last live value), which makes every later splat fail the T(1-a) >= 1e-4 test.
     float T = 1.0f, Tlive = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, D = 0.0f, Wt = 0.0f;
     int last = start, cnt = 0;
     unsigned int n_visits = 0, n_pairs = 0;  // COUNT only
@@ -117,8 +137,8 @@ blend_forward_kernel(const BlendFwdParams p) {
             const unsigned int bits = __ballot_sync(0xffffffffu, (mask >> w) & 1u);
             if (lane == 0) s_bits[buf][w][warp] = bits;
         }
-        if (__syncthreads_and(T == 0.0f)) break;  // staging visible + tile-level early exit
-        if (__all_sync(0xffffffffu, T == 0.0f)) continue;  // whole patch saturated: only help with loads
+        if (__syncthreads_and(!(T > 0.0f))) break;  // staging visible + tile-level early exit
+        if (__all_sync(0xffffffffu, !(T > 0.0f))) continue;  // whole patch saturated: only help with loads
         // ordered visit list of this patch: the set bits of its 8 words
         int count = 0;
 #pragma unroll
@@ -174,13 +194,15 @@ blend_forward_kernel(const BlendFwdParams p) {
                     }
                 } else {
                     // Branch-free: a pair that fails the alpha cut gets alpha = 0 (T, the sums and the counters are left
-                    // as they are); a pixel that saturates -- now or earlier, T == 0 -- gets zero weight and T = 0.
+                    // as they are).  A pixel that saturates keeps the MAGNITUDE of its last transmittance with the sign
+                    // flipped: T < 0 makes every later nT = T (1 - alpha) fail the 1e-4 test, so it gets zero weight without
+                    // a separate flag, and |T| is the value to output (GPCR:457-460, 476).
                     float P = fast_alpha(dx, dy, r0.z, r0.w, r1.x, r1.y);
                     P = (P < 1.0f / 255.0f) ? 0.0f : P;        // GPCR:451 (same comparison as the reference)
                     const float alpha = fminf(P, 0.99f);        // GPCR:453
                     const float nT = T * (1.0f - alpha);
                     const bool ok = nT >= 0.0001f;              // GPCR:457
-                    const float wgt = ok ? alpha * T : 0.0f;
+                    const float wgt = ok ? alpha * T : 0.0f;   // > 0 exactly for the blended pairs (alpha > 0 and T > 0)
                     if (COUNT) n_pairs += (P != 0.0f && T > 0.0f) ? 1u : 0u;
                     GSB_EMU_COUNT(EC_FW_PAIRS, (P != 0.0f && T > 0.0f) ? 1 : 0);
                     C0 = fmaf(r2.x, wgt, C0);
@@ -189,16 +211,13 @@ blend_forward_kernel(const BlendFwdParams p) {
                     if (!RGB_ONLY) {
                         D = fmaf(r1.w, wgt, D);
                         Wt += wgt;
-                        const bool blended = ok && P != 0.0f;
-                        cnt += blended ? 1 : 0;
-                        last = blended ? __float_as_int(r2.w) : last;
-                        Tlive = ok ? nT : Tlive;
+                        count_if_blended(wgt, __float_as_int(r2.w), cnt, last);
                     }
-                    T = ok ? nT : 0.0f;
+                    T = ok ? nT : -fabsf(T);
                 }
             }
             __syncwarp();  // everybody has read the chunk before the next one overwrites it
-            if (__all_sync(0xffffffffu, T == 0.0f)) break;
+            if (__all_sync(0xffffffffu, !(T > 0.0f))) break;
         }
     }
     const size_t pix = (size_t)pv * p.W + pu;
@@ -207,7 +226,7 @@ blend_forward_kernel(const BlendFwdParams p) {
     p.image[3 * pix + 2] = C2;
     if (!RGB_ONLY) {
         p.depth[pix] = D / fmaxf(Wt, 1e-6f);  // GPCR:479-480
-        p.acc_alpha[pix] = 1.0f - Tlive;
+        p.acc_alpha[pix] = 1.0f - (EXACT_EXP ? Tlive : fabsf(T));
         p.last_effective[pix] = last;
         p.valid_count[pix] = cnt;
     }
@@ -234,14 +253,13 @@ blend_forward_kernel(const BlendFwdParams p) {
 
 #ifndef GSB_HOST_EMU
 int launch_blend_forward(const GsbForwardArgs &a, const Workspace &ws, cudaStream_t stream) {
-    const GsbWorkspaceLayout &L = ws.layout;
     BlendFwdParams p;
     p.H = a.camera_height;
     p.W = a.camera_width;
     p.tiles_x = a.camera_width / GSB_TILE_WIDTH;
     p.tile_start = ws.tile_start;
     p.tile_end = ws.tile_end;
-    p.sorted_vals = (L.sort_passes % 2) == 1 ? ws.vals_b : ws.vals_a;
+    p.sorted_vals = ws.vals_b;  // the sort always ends in b
     p.records = ws.records;
     p.image = a.rasterized_image;
     p.depth = a.rasterized_depth;
@@ -268,14 +286,13 @@ int launch_blend_forward(const GsbForwardArgs &a, const Workspace &ws, cudaStrea
 // the alpha cut on a live pixel -- SURVEY 8(d)'s "E" measured on the device instead of estimated.
 int launch_blend_forward_count(const GsbForwardArgs &a, const Workspace &ws, unsigned long long *counters_dev,
                                cudaStream_t stream) {
-    const GsbWorkspaceLayout &L = ws.layout;
     BlendFwdParams p;
     p.H = a.camera_height;
     p.W = a.camera_width;
     p.tiles_x = a.camera_width / GSB_TILE_WIDTH;
     p.tile_start = ws.tile_start;
     p.tile_end = ws.tile_end;
-    p.sorted_vals = (L.sort_passes % 2) == 1 ? ws.vals_b : ws.vals_a;
+    p.sorted_vals = ws.vals_b;  // the sort always ends in b
     p.records = ws.records;
     p.image = a.rasterized_image;
     p.depth = a.rasterized_depth;

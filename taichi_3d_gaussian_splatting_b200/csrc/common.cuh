@@ -22,8 +22,10 @@ void set_error(const char *fmt, ...);
     } while (0)
 
 // ---- counters living at the head of the workspace
-enum Counter { CNT_M = 0, CNT_K = 1, CNT_OVERFLOW = 2, CNT_SORTED_SEL = 3 };
-enum Ticket { TICKET_SCAN = 0, TICKET_SORT0 = 1 /* ..+7 */ };
+// CNT_MAX_DEPTH_KEY: largest int32(depth * scale) over the frame's in-camera points (low 32 bits of the slot; the per-point
+// kernel atomicMax-es it, the sort derives the number of live depth bits from it)
+enum Counter { CNT_M = 0, CNT_K = 1, CNT_OVERFLOW = 2, CNT_MAX_DEPTH_KEY = 4 };
+enum Ticket { TICKET_SCAN = 0, TICKET_SORT0 = 1 /* ..+7: one per pass; +8: histogram blocks done */ };
 
 // Per-object pose block in the workspace (20 floats):
 //   [0..11]  T_camera_pointcloud 3x4 row-major (R | t)     GP3D:51-62
@@ -50,8 +52,8 @@ struct Workspace {
     int *num_tiles;
     float4 *records;        // 3 float4 per in-camera point
     float *point_in_camera; // 3 floats per in-camera point
-    void *keys_a, *keys_b;
-    int *vals_a, *vals_b;
+    void *keys_a, *keys_b, *keys_c;  // emitted keys (a), sorted keys (b), scratch of the radix passes (c)
+    int *vals_a, *vals_b, *vals_c;
     GsbWorkspaceLayout layout;
 };
 
@@ -79,10 +81,10 @@ int launch_blend_backward_work(const GsbBackwardArgs &a, const Workspace &ws, un
 
 int sort_radix_bits(int bits);
 int sort_pairs_device(const void *keys_in, const int *vals_in, void *keys_out, int *vals_out,
-                      const long long *n_dev, int64_t n_capacity, int key_bytes, int end_bit,
-                      unsigned int *hist /*8*256, zeroed*/, unsigned int *state /*zeroed*/,
-                      unsigned int *tickets /*8, zeroed*/, void *tmp_keys, int *tmp_vals,
-                      long long *sel_out, cudaStream_t stream);
+                      const long long *n_dev, int64_t n_capacity, int key_bytes, int depth_bits, int end_bit,
+                      const int *max_depth_key /*device or NULL*/, unsigned int *hist /*8*256, zeroed*/,
+                      unsigned int *state /*zeroed*/, unsigned int *tickets /*9, zeroed*/, void *tmp_keys,
+                      int *tmp_vals, cudaStream_t stream);
 
 #ifndef GSB_SORT_ITEMS
 #define GSB_SORT_ITEMS 12

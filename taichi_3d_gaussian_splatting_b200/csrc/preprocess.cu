@@ -466,7 +466,15 @@ preprocess_kernel(const PreParams p) {
     // (tile_u outer, tile_v inner) order.  The key ranges of the warp's splats are adjacent (prefix sum), so
     // dealing the keys round-robin to the lanes makes the stores contiguous and the work balanced.
     {
-        st.depth_key[lane] = (int)(pc[2] * p.depth_scale);
+        const int depth_key = (int)(pc[2] * p.depth_scale);
+        st.depth_key[lane] = depth_key;
+        {   // largest depth key of the frame -> CNT_MAX_DEPTH_KEY: the sort runs only the passes its live bits need
+            int wmax = in ? depth_key : 0;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, d));
+            int *const slot = reinterpret_cast<int *>(p.counters + CNT_MAX_DEPTH_KEY);
+            if (lane == 0 && wmax > *reinterpret_cast<volatile int *>(slot)) atomicMax(slot, wmax);
+        }
         st.off[lane] = (int)off;
         st.key_base[lane] = key_base;
         int incl_k = in ? nkeys : 0;

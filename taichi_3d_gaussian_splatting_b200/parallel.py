@@ -117,6 +117,13 @@ class ViewParallelExchange:
             w2.wait()
 
 
+    def run_and_expand(self, grad_sum: torch.Tensor, blocks: torch.Tensor, expand) -> None:
+        """The collectives followed by the expansion to dense gradients.  ``expand(part)`` enqueues
+        ``gsb200_expand_view_gradients`` on the current stream (0 = everything, 1 = SH columns, 2 = summed columns)."""
+        self.run(grad_sum, blocks)
+        expand(0)
+
+
 class MulticastViewParallelExchange(ViewParallelExchange):
     """The same exchange with BOTH collectives done by one hand-written kernel over NVSwitch multicast memory
     (``gsb200_exchange_multimem``, csrc/exchange.cu: ``multimem.ld_reduce`` / ``multimem.st``) instead of ncclAllReduce +
@@ -125,10 +132,13 @@ class MulticastViewParallelExchange(ViewParallelExchange):
     kernel writes its compact rows straight into it.  ``run`` = cross-rank barrier (every rank's rows are written), the
     kernel, cross-rank barrier (every multicast store has landed).  Needs NVLS multicast support (one NVSwitch domain)."""
 
-    def __init__(self, group=None, barrier_timeout_ms: int = 20000, num_blocks: int = 0):
-        """``num_blocks``: CTAs of the exchange kernel (0 = two per SM)."""
+    def __init__(self, group=None, barrier_timeout_ms: int = 20000, num_blocks: int = 0, overlap_expansion: bool = True):
+        """``num_blocks``: CTAs of the exchange kernel (0 = two per SM).  ``overlap_expansion``: expand the SH columns (they
+        need only the gathered blocks) on a second stream while the all-reduce of the summed columns is on the wire."""
         super().__init__(group)
         self._num_blocks = int(num_blocks)
+        self._overlap = bool(overlap_expansion)
+        self._side_stream = None
         import torch.distributed._symmetric_memory as symm_mem
         self._symm_mem = symm_mem
         self._group = group if group is not None else dist.group.WORLD
@@ -193,6 +203,30 @@ class MulticastViewParallelExchange(ViewParallelExchange):
             hdl.barrier(channel=0, timeout_ms=self._timeout)  # every rank's compact rows are in its buffer
             self._launch(2, blocks)                            # two-shot all-reduce of the summable columns
             hdl.barrier(channel=1, timeout_ms=self._timeout)  # every rank's multicast stores (sums and blocks) have landed
+
+
+    def run_and_expand(self, grad_sum: torch.Tensor, blocks: torch.Tensor, expand) -> None:
+        """Every rank's block is in place after the FIRST barrier (the pushes were launched before it), so the 48 SH columns
+        -- 4/5 of the expansion's traffic, HBM-bound -- are expanded on a second stream while the all-reduce of the summed
+        columns is still bound by the NVLink wire; only the small part 2 (xyz, q, s, logit) follows the second barrier."""
+        if not self._overlap:
+            return super().run_and_expand(grad_sum, blocks, expand)
+        e = self._check(grad_sum, blocks)
+        hdl = e["hdl"]
+        dev = grad_sum.device
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            if self._side_stream is None or self._side_stream.device != dev:
+                self._side_stream = torch.cuda.Stream(device=dev)
+            side = self._side_stream
+            hdl.barrier(channel=0, timeout_ms=self._timeout)  # rows written and blocks pushed on every rank
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                expand(1)                                      # SH columns from the gathered blocks
+            self._launch(2, blocks)                            # two-shot all-reduce of the summed columns
+            hdl.barrier(channel=1, timeout_ms=self._timeout)  # the sums have landed everywhere
+            expand(2)                                          # xyz / q / s / logit columns
+            main.wait_stream(side)
 
 
 def render_views(op, make_input, view_ids: Sequence[int], streams: Optional[Sequence["torch.cuda.Stream"]] = None):

@@ -126,7 +126,8 @@ extern "C" long long emu_backward_points(long long N, const int *point_offset, c
 // gsb200_expand_view_gradients: dense gradients of a batch of views from the exchanged compact rows
 extern "C" long long emu_expand_view_gradients(long long N, int R, const float *grad_sum, const float *grad_color_views,
                                                long long view_stride, const float *xyz, const int *obj_id,
-                                               int color_max_sh_band, float c_f, float h_f, float *grad_xyz, float *grad_feat) {
+                                               int color_max_sh_band, float c_f, float h_f, float *grad_xyz, float *grad_feat,
+                                               int part) {
     using namespace gsb;
     ExpandParams p;
     p.N = N;
@@ -144,7 +145,11 @@ extern "C" long long emu_expand_view_gradients(long long N, int R, const float *
     p.grad_feat = grad_feat;
     simt_emu::M().switches = 0;
     const int blocks = (int)std::min<long long>((N + GSB_POINTS_THREADS - 1) / GSB_POINTS_THREADS, 16 * 148);
-    if (N > 0) simt_emu::launch(expand_view_gradients_kernel, blocks, GSB_POINTS_THREADS, p);
+    if (N > 0) {
+        if (part == 1) simt_emu::launch(expand_view_gradients_kernel<1>, blocks, GSB_POINTS_THREADS, p);
+        else if (part == 2) simt_emu::launch(expand_view_gradients_kernel<2>, blocks, GSB_POINTS_THREADS, p);
+        else simt_emu::launch(expand_view_gradients_kernel<0>, blocks, GSB_POINTS_THREADS, p);
+    }
     return simt_emu::M().switches;
 }
 

@@ -1,7 +1,8 @@
 // emu_sort.cpp -- the one-sweep LSD radix sort and the tile-range kernel (csrc/sort.cu) compiled as host C++ under
 // simt_emu.h.  TEST INFRASTRUCTURE, see simt_emu.h.  The pass loop below restates sort_pairs_typed() of sort.cu (histogram
-// kernel, then one kernel per 8-bit digit, ping-pong so that the last pass lands in the output); the CTAs of a pass run in
-// launch = ticket order, so the per-digit look-back always finds its predecessors complete.
+// kernel, then one launch per 8-bit digit of the widest possible key; the kernels themselves decide which passes run and
+// rotate through the three buffers so that the sorted list ends in the output); the CTAs of a pass run in launch = ticket
+// order, so the per-digit look-back always finds its predecessors complete.
 #include "simt_emu.h"
 #include "../../taichi_3d_gaussian_splatting_b200/csrc/sort.cu"
 
@@ -11,26 +12,16 @@ struct HistArgs {
     const KeyT *keys;
     const long long *n;
     long long cap;
-    int passes;
-    unsigned int *hist;
+    int depth_bits, end_bit;
+    const int *max_depth_key;
+    unsigned int *hist, *done;
 };
+// depth_bits / max_depth_key: the live-bit compaction of sort.cu (max_depth_key == nullptr: every bit is live)
 template <class KeyT>
-struct PassArgs {
-    const KeyT *ki;
-    const int *vi;
-    KeyT *ko;
-    int *vo;
-    const long long *n;
-    long long cap;
-    int shift;
-    const unsigned int *hist;
-    unsigned int *state, *ticket;
-};
-template <class KeyT>
-long long sort_typed(const KeyT *keys_in, const int *vals_in, KeyT *keys_out, int *vals_out, long long n, int end_bit) {
+long long sort_typed(const KeyT *keys_in, const int *vals_in, KeyT *keys_out, int *vals_out, long long n, int depth_bits,
+                     int end_bit, const int *max_depth_key) {
     using namespace gsb;
-    constexpr int RB = 8, RADIX = 1 << RB;
-    const int passes = (end_bit + RB - 1) / RB;
+    const int passes = (end_bit + RBITS - 1) / RBITS;  // launches: the worst case, as sort_pairs_typed() does
     const long long cap = (n + SORT_TILE - 1) / SORT_TILE * SORT_TILE;
     const int blocks = (int)(cap / SORT_TILE);
     if (blocks == 0 || passes == 0) return 0;
@@ -38,27 +29,36 @@ long long sort_typed(const KeyT *keys_in, const int *vals_in, KeyT *keys_out, in
     std::vector<int> vin(cap, 0), vtmp(cap), vout(cap);
     std::copy(keys_in, keys_in + n, in.begin());
     std::copy(vals_in, vals_in + n, vin.begin());
-    std::vector<unsigned int> hist(8 * 1024, 0u), state((size_t)passes * blocks * RADIX, 0u), tickets(8, 0u);
+    const std::vector<KeyT> in_before(in);
+    std::vector<unsigned int> hist(8 * 1024, 0u), state((size_t)passes * blocks * RADIX, 0u), tickets(16, 0u);
     simt_emu::M().switches = 0;
-    HistArgs<KeyT> ha{in.data(), &n, cap, passes, hist.data()};
-    simt_emu::launch([](const HistArgs<KeyT> &a) { sort_histogram_kernel<KeyT, RB>(a.keys, a.n, a.cap, a.passes, a.hist); },
-                     std::min(blocks, 4 * 148), 256, ha);
-    const KeyT *src_k = in.data();
-    const int *src_v = vin.data();
+    HistArgs<KeyT> ha{in.data(), &n, cap, depth_bits, end_bit, max_depth_key, hist.data(), tickets.data() + 8};
+    simt_emu::launch(
+        [](const HistArgs<KeyT> &a) {
+            sort_histogram_kernel<KeyT>(a.keys, a.n, a.cap, a.depth_bits, a.end_bit, a.max_depth_key, a.hist, a.done);
+        },
+        std::min(blocks, 4 * 148), SORT_BLOCK_THREADS, ha);
+    PassParams<KeyT> P;
+    P.keys_a = in.data();
+    P.vals_a = vin.data();
+    P.keys_b = out.data();
+    P.vals_b = vout.data();
+    P.keys_c = tmp.data();
+    P.vals_c = vtmp.data();
+    P.n_dev = &n;
+    P.capacity = cap;
+    P.depth_bits = depth_bits;
+    P.end_bit = end_bit;
+    P.blocks = blocks;
+    P.max_depth_key = max_depth_key;
+    P.hist = hist.data();
+    P.state = state.data();
+    P.tickets = tickets.data();
     for (int p = 0; p < passes; ++p) {
-        const bool last_to_out = ((passes - 1 - p) % 2) == 0;
-        KeyT *dst_k = last_to_out ? out.data() : tmp.data();
-        int *dst_v = last_to_out ? vout.data() : vtmp.data();
-        PassArgs<KeyT> pa{src_k, src_v, dst_k, dst_v, &n, cap, p * RB, hist.data() + p * RADIX,
-                          state.data() + (size_t)p * blocks * RADIX, tickets.data() + p};
-        simt_emu::launch(
-            [](const PassArgs<KeyT> &a) {
-                onesweep_pass_kernel<KeyT, RB>(a.ki, a.vi, a.ko, a.vo, a.n, a.cap, a.shift, a.hist, a.state, a.ticket);
-            },
-            blocks, SORT_BLOCK_THREADS, pa);
-        src_k = dst_k;
-        src_v = dst_v;
+        P.pass = p;
+        simt_emu::launch([](const PassParams<KeyT> &a) { onesweep_pass_kernel<KeyT>(a); }, blocks, SORT_BLOCK_THREADS, P);
     }
+    if (in != in_before) return -1;  // the input buffer must never be written
     std::copy(out.begin(), out.begin() + n, keys_out);
     std::copy(vout.begin(), vout.begin() + n, vals_out);
     return simt_emu::M().switches;
@@ -76,9 +76,21 @@ struct RangeArgs {
 extern "C" long long emu_sort_pairs(const void *keys_in, const int *vals_in, void *keys_out, int *vals_out, long long n,
                                     int key_bytes, int end_bit) {
     if (key_bytes == 4)
-        return sort_typed<unsigned int>((const unsigned int *)keys_in, vals_in, (unsigned int *)keys_out, vals_out, n, end_bit);
+        return sort_typed<unsigned int>((const unsigned int *)keys_in, vals_in, (unsigned int *)keys_out, vals_out, n, 0,
+                                        end_bit, nullptr);
     return sort_typed<unsigned long long>((const unsigned long long *)keys_in, vals_in, (unsigned long long *)keys_out,
-                                          vals_out, n, end_bit);
+                                          vals_out, n, 0, end_bit, nullptr);
+}
+
+// the frame pipeline's call: keys = tile << depth_bits | depth key, *max_depth_key = the frame's largest depth key
+extern "C" long long emu_sort_pairs_compacted(const void *keys_in, const int *vals_in, void *keys_out, int *vals_out,
+                                              long long n, int key_bytes, int depth_bits, int end_bit,
+                                              const int *max_depth_key) {
+    if (key_bytes == 4)
+        return sort_typed<unsigned int>((const unsigned int *)keys_in, vals_in, (unsigned int *)keys_out, vals_out, n,
+                                        depth_bits, end_bit, max_depth_key);
+    return sort_typed<unsigned long long>((const unsigned long long *)keys_in, vals_in, (unsigned long long *)keys_out,
+                                          vals_out, n, depth_bits, end_bit, max_depth_key);
 }
 
 // tile_start / tile_end must be zero-initialised (GPCR:954-957)

@@ -28,6 +28,7 @@ def build_emulator():
     L.emu_backward_points.restype = ctypes.c_longlong
     L.emu_expand_view_gradients.restype = ctypes.c_longlong
     L.emu_sort_pairs.restype = ctypes.c_longlong
+    L.emu_sort_pairs_compacted.restype = ctypes.c_longlong
     L.emu_image_loss.restype = ctypes.c_longlong
     L.emu_image_loss_temp_bytes.restype = ctypes.c_longlong
     return L
@@ -89,12 +90,24 @@ def emu_sort(emu, keys, vals, end_bit):
     return ko, vo
 
 
+def emu_sort_frame(emu, pre, Kk):
+    """The frame pipeline's sort (csrc/sort.cu launch_sort): compacted digits from the frame's largest depth key, which the
+    per-point kernel left in counters[4]."""
+    keys, vals = np.ascontiguousarray(pre.keys[:Kk]), np.ascontiguousarray(pre.vals[:Kk], dtype=np.int32)
+    ko, vo = np.empty_like(keys), np.empty_like(vals)
+    max_key = np.array([int(pre.counters[4]) & 0xFFFFFFFF], np.int32)
+    if Kk:
+        assert emu.emu_sort_pairs_compacted(c(keys), c(vals), c(ko), c(vo), ctypes.c_longlong(Kk), keys.dtype.itemsize,
+                                            pre.depth_bits, pre.tile_bits + pre.depth_bits, c(max_key)) > 0
+    return ko, vo
+
+
 def emulated_forward(emu, scene, cfg=None, exact=True, filter_tiles=True):
     """Forward of the CUDA path under the emulator; returns the saved-for-backward state with the outputs."""
     cfg = cfg or {}
     pre = run_preprocess(emu, scene, cfg, key64=False, filter_tiles=filter_tiles)
     M, Kk = int(pre.counters[0]), int(pre.counters[1])
-    sk, sv = emu_sort(emu, pre.keys[:Kk], pre.vals[:Kk], pre.tile_bits + pre.depth_bits)
+    sk, sv = emu_sort_frame(emu, pre, Kk)
     order = np.argsort(pre.keys[:Kk], kind="stable")
     assert np.array_equal(sk, pre.keys[:Kk][order]) and np.array_equal(sv, pre.vals[:Kk][order])
     start, end = np.zeros(pre.T, np.int32), np.zeros(pre.T, np.int32)

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in gsb200.h but not exported by libgsb200.so"
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
-    assert lib.gsb200_version() == 101
+    assert lib.gsb200_version() == 102
 
 
 def test_workspace_layout_arithmetic():
@@ -32,9 +32,9 @@ def test_workspace_layout_arithmetic():
     assert L.scan_blocks == (1_000_000 + 127) // 128  # preprocess CTAs of 128 points
     assert L.key_capacity_padded % 3072 == 0 and L.key_capacity_padded >= 8_000_000  # sort CTAs of 3072 keys
     offs = [L.counters, L.tickets, L.scan_state, L.sort_hist, L.sort_state, L.tile_start, L.tile_end,
-            L.poses, L.point_id, L.num_tiles, L.records, L.point_in_camera, L.keys_a, L.keys_b, L.vals_a, L.vals_b]
+            L.poses, L.point_id, L.num_tiles, L.records, L.point_in_camera, L.keys_a, L.keys_b, L.vals_a, L.vals_b, L.keys_c, L.vals_c]
     assert offs == sorted(offs) and all(o % 256 == 0 for o in offs)
-    assert L.zero_bytes == L.poses and L.total_bytes > L.vals_b
+    assert L.zero_bytes == L.poses and L.total_bytes > L.vals_c
     # the reference's exact 64-bit packing when asked for, or when the live bits do not fit 32
     L64 = _lib.workspace_layout(1000, 1, 5000, 64, 64, 1000.0, 100.0, _lib.GSB_FLAG_FORCE_KEY64)
     assert (L64.key_bytes, L64.depth_bits) == (8, 32)

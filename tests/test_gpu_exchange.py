@@ -36,6 +36,21 @@ class _LocalExchange:
             grad_sum += self.store[r][0]
             blocks[r].copy_(self.store[r][1])
 
+    def run_and_expand(self, grad_sum, blocks, expand):
+        """The split expansion of parallel.MulticastViewParallelExchange: the SH columns from the gathered blocks while the
+        summed columns are still unsummed (here: poisoned), the summed columns afterwards."""
+        if not self.replay:
+            self.run(grad_sum, blocks)
+            return expand(0)
+        own = grad_sum.clone()
+        for r in range(self.world):
+            blocks[r].copy_(self.store[r][1])
+        grad_sum.fill_(float("nan"))  # part 1 must not read it
+        expand(1)
+        grad_sum.copy_(own)
+        self.run(grad_sum, blocks)
+        expand(2)
+
 
 @pytest.mark.parametrize("band", [3, 1])
 @pytest.mark.parametrize("with_hook", [False, True])

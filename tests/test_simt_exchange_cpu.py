@@ -67,7 +67,18 @@ def test_compact_rows_plus_expansion_equal_the_sum_of_the_dense_gradients(emu, n
     out_x, out_f = np.full((N, 3), 7.0, np.float32), np.full((N, 56), 7.0, np.float32)
     f = ctypes.c_float
     assert emu.emu_expand_view_gradients(ctypes.c_longlong(N), num_views, c(gsum), c(blocks), ctypes.c_longlong(stride), c(xyz),
-                                         c(obj), band, f(5.0), f(1.0), c(out_x), c(out_f)) > 0
+                                         c(obj), band, f(5.0), f(1.0), c(out_x), c(out_f), 0) > 0
+    # the two halves of the split expansion (SH columns from the blocks alone / summed columns from grad_sum alone) together
+    # write exactly what the one-pass expansion writes, each leaving the other's piece untouched
+    part_x, part_f = np.full((N, 3), 7.0, np.float32), np.full((N, 56), 7.0, np.float32)
+    nan_sum, nan_blocks = np.full_like(gsum, np.nan), blocks.copy()
+    assert emu.emu_expand_view_gradients(ctypes.c_longlong(N), num_views, c(nan_sum), c(blocks), ctypes.c_longlong(stride), c(xyz),
+                                         c(obj), band, f(5.0), f(1.0), c(part_x), c(part_f), 1) > 0
+    assert (part_x == 7.0).all() and (part_f[:, :8] == 7.0).all() and np.array_equal(part_f[:, 8:], out_f[:, 8:])
+    nan_blocks[:, :3 * N] = np.nan
+    assert emu.emu_expand_view_gradients(ctypes.c_longlong(N), num_views, c(gsum), c(nan_blocks), ctypes.c_longlong(stride), c(xyz),
+                                         c(obj), band, f(5.0), f(1.0), c(part_x), c(part_f), 2) > 0
+    assert np.array_equal(part_x, out_x) and np.array_equal(part_f, out_f)
     if num_views == 1:  # same operations in the same order as the dense kernel
         assert np.array_equal(out_x, dense_x.astype(np.float32)) and np.array_equal(out_f, dense_f.astype(np.float32))
     scale = np.abs(dense_f).max()

@@ -37,6 +37,34 @@ def test_emulated_radix_sort_is_the_stable_sort(emu, dtype, end_bit, n):
     assert np.array_equal(ko, keys[order]) and np.array_equal(vo, vals[order])
 
 
+@pytest.mark.parametrize("dtype,depth_bits,tile_bits", [(np.uint32, 17, 13), (np.uint32, 15, 12), (np.uint32, 10, 3), (np.uint64, 32, 13)])
+@pytest.mark.parametrize("live", [0, 1, 3, 7, 8, 9, 10, 16, "all"])
+def test_emulated_radix_sort_compacts_the_dead_depth_bits(emu, dtype, depth_bits, tile_bits, live):
+    """csrc/sort.cu live-bit compaction: keys tile << depth_bits | depth where only the low `live` depth bits are used (the
+    frame's largest depth key is handed over like the per-point kernel leaves it).  The digits of the compacted key are cut
+    out of the stored key -- including digits straddling the depth / tile boundary -- the launches beyond the last needed pass
+    exit, and the result is the stable sort of the stored keys whatever the number of passes that ran."""
+    live = min(depth_bits, 31) if live == "all" else live  # depth keys are non-negative int32 (31 bits in the 64-bit packing)
+    if live > depth_bits:
+        pytest.skip("more live bits than the depth field has")
+    n = 7000
+    rng = np.random.default_rng(depth_bits * 100 + tile_bits * 10 + live)
+    depth = rng.integers(0, 1 << live, n, dtype=np.uint64) if live else np.zeros(n, np.uint64)
+    if live:
+        depth[rng.integers(0, n)] = (1 << live) - 1  # the maximum really has `live` bits
+    tile = rng.integers(0, min(1 << tile_bits, 40), n, dtype=np.uint64) * np.uint64(max(((1 << tile_bits) - 1) // 39, 1))
+    keys = ((tile << np.uint64(depth_bits)) | depth).astype(dtype)
+    vals = rng.permutation(n).astype(np.int32)
+    ko, vo = np.empty_like(keys), np.empty_like(vals)
+    for max_key in ([int(depth.max())] if live < min(depth_bits, 31) else [int(depth.max()), None]):
+        mk = np.array([max_key], np.int32) if max_key is not None else None
+        sw = emu.emu_sort_pairs_compacted(c(keys), c(vals), c(ko), c(vo), ctypes.c_longlong(n), keys.dtype.itemsize, depth_bits,
+                                          depth_bits + tile_bits, c(mk) if mk is not None else None)
+        assert sw > 0  # -1: the input buffer was written
+        order = np.argsort(keys, kind="stable")
+        assert np.array_equal(ko, keys[order]) and np.array_equal(vo, vals[order])
+
+
 def test_emulated_tile_ranges_known_answer(emu):
     """The reference's own known answer (tests/GaussianPointCloudRasterisation_test.py:18-51 shape): keys tile << 32 | depth."""
     tiles = np.array([0, 0, 0, 2, 2, 5, 5, 5, 5, 7], np.uint64)
