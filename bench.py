@@ -65,7 +65,7 @@ def parse_args():
                          "nccl = ncclAllReduce + ncclAllGather, auto = multimem where the group has multicast support, else nccl")
     ap.add_argument("--exchange-blocks", type=int, default=0, help="CTAs of the multimem exchange kernel (0 = two per SM)")
     ap.add_argument("--serial-expansion", action="store_true",
-                    help="multimem exchange: expand the dense gradients after the all-reduce in one pass (comparison) instead of "
+                    help="N > 1: expand the dense gradients after the all-reduce in one pass (comparison) instead of "
                          "expanding the SH columns on a second stream while the all-reduce is on the wire")
     ap.add_argument("--dense-exchange", action="store_true",
                     help="N > 1: one all-reduce of the dense gradients instead of the compact exchange (comparison)")
@@ -248,7 +248,8 @@ def run_b200(args):
                 if rank == 0:
                     print(f"[bench] multicast exchange unavailable ({type(e).__name__}: {e}); using the NCCL collectives", file=sys.stderr)
         if exchange is None:
-            exchange = ViewParallelExchange(gather_group=dist.new_group() if args.exchange_streams == 2 else None)
+            exchange = ViewParallelExchange(gather_group=dist.new_group() if args.exchange_streams == 2 else None,
+                                            overlap_expansion=not args.serial_expansion)
             exchange_kind = "nccl"
 
     def barrier():
@@ -648,8 +649,8 @@ def run_b200(args):
 
     launches_per_step = profiling.KERNELS_PER_FORWARD(frame.layout.sort_passes) + profiling.KERNELS_PER_BACKWARD + \
         (0 if exchange is None else                       # + gsb200_expand_view_gradients (two launches when split around the
-         (1 if exchange_kind != "multimem" else            #   all-reduce) + the two launches of gsb200_exchange_multimem
-          (3 if args.serial_expansion else 4)))
+         ((1 if args.serial_expansion or args.exchange_streams == 2 else 2) if exchange_kind != "multimem" else  # all-reduce)
+          (3 if args.serial_expansion else 4)))            # + the two launches of gsb200_exchange_multimem
     if world == 1:
         parallelism = "single GPU"
     elif exchange is not None:

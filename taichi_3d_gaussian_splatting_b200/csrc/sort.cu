@@ -116,8 +116,35 @@ sort_histogram_kernel(const KeyT *__restrict__ keys, const long long *__restrict
     DigitSel<KeyT> sel[8];
 #pragma unroll
     for (int p = 0; p < 8; ++p) sel[p] = make_digit_sel<KeyT>(p, depth_bits, live);
+    // 16 bytes per load and HIST_U loads in flight per thread: with one 4-byte load per trip (round 1) the sweep was bound by
+    // the load latency (8 KB in flight per SM), not by the shared-memory atomics
+    constexpr int VEC = 16 / (int)sizeof(KeyT), HIST_U = 2;
     const long long stride = (long long)gridDim.x * SORT_BLOCK_THREADS;
-    for (long long i = (long long)blockIdx.x * SORT_BLOCK_THREADS + tid; i < n; i += stride) {
+    const long long nvec = n / VEC;  // the key buffers are 16-byte aligned (workspace: 256; gsb200_sort_pairs checks keys_in)
+    const uint4 *const kv = reinterpret_cast<const uint4 *>(keys);
+    for (long long i = (long long)blockIdx.x * SORT_BLOCK_THREADS + tid; i < nvec; i += HIST_U * stride) {
+        uint4 v[HIST_U];
+#pragma unroll
+        for (int u = 0; u < HIST_U; ++u)
+            if (i + u * stride < nvec) v[u] = kv[i + u * stride];
+#pragma unroll
+        for (int u = 0; u < HIST_U; ++u) {
+            if (i + u * stride >= nvec) continue;
+            KeyT kk[VEC];
+            if (sizeof(KeyT) == 4) {
+                kk[0] = (KeyT)v[u].x; kk[1] = (KeyT)v[u].y; kk[VEC - 2] = (KeyT)v[u].z; kk[VEC - 1] = (KeyT)v[u].w;
+            } else {
+                kk[0] = (KeyT)v[u].x | ((KeyT)v[u].y << (4 * sizeof(KeyT)));
+                kk[VEC - 1] = (KeyT)v[u].z | ((KeyT)v[u].w << (4 * sizeof(KeyT)));
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+#pragma unroll
+                for (int p = 0; p < 8; ++p)
+                    if (p < passes) atomicAdd(&s_hist[p * RADIX + digit_of(kk[e], sel[p])], 1u);
+        }
+    }
+    for (long long i = nvec * VEC + (long long)blockIdx.x * SORT_BLOCK_THREADS + tid; i < n; i += stride) {  // < VEC tail keys
         const KeyT k = keys[i];
 #pragma unroll
         for (int p = 0; p < 8; ++p)

@@ -77,14 +77,17 @@ class ViewParallelExchange:
     rank's ``[3N colour-argument gradients | 3 n_obj camera centres]`` in row ``rank`` and receives the other ranks' rows
     (in-place all-gather: the send buffer is the rank's slot of the receive buffer)."""
 
-    def __init__(self, group=None, gather_group=None):
+    def __init__(self, group=None, gather_group=None, overlap_expansion: bool = True):
         """``gather_group``: optionally a SECOND process group over the same ranks (``dist.new_group()``): the all-gather
         then runs on its communicator concurrently with the all-reduce (two NCCL kernels in flight hide each other's
-        latency) instead of behind it."""
+        latency) instead of behind it.  ``overlap_expansion``: gather first and expand the SH columns (they need only the
+        gathered blocks) on a second stream while the all-reduce of the summed columns is on the wire."""
         if not dist.is_available() or not dist.is_initialized():
             raise RuntimeError("ViewParallelExchange needs an initialised torch.distributed process group")
         self.group = group
         self.gather_group = gather_group
+        self._overlap = bool(overlap_expansion)
+        self._side_stream = None
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         if gather_group is not None and dist.get_world_size(gather_group) != self.world:
@@ -117,11 +120,32 @@ class ViewParallelExchange:
             w2.wait()
 
 
+    def _side(self, device) -> "torch.cuda.Stream":
+        if self._side_stream is None or self._side_stream.device != device:
+            self._side_stream = torch.cuda.Stream(device=device)
+        return self._side_stream
+
     def run_and_expand(self, grad_sum: torch.Tensor, blocks: torch.Tensor, expand) -> None:
         """The collectives followed by the expansion to dense gradients.  ``expand(part)`` enqueues
-        ``gsb200_expand_view_gradients`` on the current stream (0 = everything, 1 = SH columns, 2 = summed columns)."""
-        self.run(grad_sum, blocks)
-        expand(0)
+        ``gsb200_expand_view_gradients`` on the current stream (0 = everything, 1 = SH columns, 2 = summed columns).
+
+        On CUDA tensors the 48 SH columns -- 4/5 of the expansion's traffic, HBM-bound -- are expanded on a second stream as soon
+        as the blocks are gathered, while the all-reduce of the summed columns is bound by the NVLink wire; only the small
+        part 2 (xyz, q, s, logit) waits for the sums.  The two parts write disjoint pieces of the dense gradients."""
+        if not (self._overlap and grad_sum.is_cuda) or self.gather_group is not None:
+            self.run(grad_sum, blocks)
+            return expand(0)
+        if blocks.shape[0] != self.world or not blocks.is_contiguous() or not grad_sum.is_contiguous():
+            raise ValueError("blocks must be a contiguous (world, stride) tensor and grad_sum contiguous")
+        dev = grad_sum.device
+        main, side = torch.cuda.current_stream(dev), self._side(dev)
+        dist.all_gather_into_tensor(blocks.view(-1), blocks[self.rank], group=self.group)
+        side.wait_stream(main)                      # the gathered blocks are in place
+        dist.all_reduce(grad_sum, op=dist.ReduceOp.SUM, group=self.group)  # NCCL's stream; main waits for it
+        with torch.cuda.stream(side):
+            expand(1)                               # runs beside the all-reduce
+        expand(2)
+        main.wait_stream(side)
 
 
 class MulticastViewParallelExchange(ViewParallelExchange):
@@ -135,10 +159,9 @@ class MulticastViewParallelExchange(ViewParallelExchange):
     def __init__(self, group=None, barrier_timeout_ms: int = 20000, num_blocks: int = 0, overlap_expansion: bool = True):
         """``num_blocks``: CTAs of the exchange kernel (0 = two per SM).  ``overlap_expansion``: expand the SH columns (they
         need only the gathered blocks) on a second stream while the all-reduce of the summed columns is on the wire."""
-        super().__init__(group)
+        super().__init__(group, overlap_expansion=overlap_expansion)
         self._num_blocks = int(num_blocks)
         self._overlap = bool(overlap_expansion)
-        self._side_stream = None
         import torch.distributed._symmetric_memory as symm_mem
         self._symm_mem = symm_mem
         self._group = group if group is not None else dist.group.WORLD
@@ -215,15 +238,12 @@ class MulticastViewParallelExchange(ViewParallelExchange):
         hdl = e["hdl"]
         dev = grad_sum.device
         with torch.cuda.device(dev):
-            main = torch.cuda.current_stream(dev)
-            if self._side_stream is None or self._side_stream.device != dev:
-                self._side_stream = torch.cuda.Stream(device=dev)
-            side = self._side_stream
+            main, side = torch.cuda.current_stream(dev), self._side(dev)
             hdl.barrier(channel=0, timeout_ms=self._timeout)  # rows written and blocks pushed on every rank
             side.wait_stream(main)
-            with torch.cuda.stream(side):
-                expand(1)                                      # SH columns from the gathered blocks
-            self._launch(2, blocks)                            # two-shot all-reduce of the summed columns
+            self._launch(2, blocks)                            # two-shot all-reduce of the summed columns: launched FIRST, so
+            with torch.cuda.stream(side):                      #   that the wire-bound kernel gets its CTAs before the expansion
+                expand(1)                                      #   (SH columns from the gathered blocks) fills the rest of the SMs
             hdl.barrier(channel=1, timeout_ms=self._timeout)  # the sums have landed everywhere
             expand(2)                                          # xyz / q / s / logit columns
             main.wait_stream(side)
