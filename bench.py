@@ -64,9 +64,12 @@ def parse_args():
                     help="N > 1: collectives of the compact exchange: multimem = the hand-written NVLS kernel (gsb200_exchange_multimem), "
                          "nccl = ncclAllReduce + ncclAllGather, auto = multimem where the group has multicast support, else nccl")
     ap.add_argument("--exchange-blocks", type=int, default=0, help="CTAs of the multimem exchange kernel (0 = two per SM)")
-    ap.add_argument("--serial-expansion", action="store_true",
-                    help="N > 1: expand the dense gradients after the all-reduce in one pass (comparison) instead of "
-                         "expanding the SH columns on a second stream while the all-reduce is on the wire")
+    ap.add_argument("--overlap-expansion-nccl", action="store_true",
+                    help="NCCL exchange: gather first and expand the SH columns beside the all-reduce (measured slower at 2 ranks)")
+    ap.add_argument("--overlap-expansion", action="store_true",
+                    help="multimem exchange: expand the SH columns on a second stream while the all-reduce is on the wire instead of "
+                         "one expansion pass behind it (measured slower at 8 GPUs: 1.809 vs 1.797 ms per step)")
+    ap.add_argument("--serial-expansion", action="store_true", help="(default behaviour; kept so that older call scripts still parse)")
     ap.add_argument("--dense-exchange", action="store_true",
                     help="N > 1: one all-reduce of the dense gradients instead of the compact exchange (comparison)")
     return ap.parse_args()
@@ -238,7 +241,7 @@ def run_b200(args):
         # barriers + two launches outweigh 60 MB of wire time), from 4 ranks on the hand-written NVLS kernel does (8 ranks: 1.90 vs 2.00)
         if args.exchange == "multimem" or (args.exchange == "auto" and world >= 4):
             try:
-                exchange = MulticastViewParallelExchange(num_blocks=args.exchange_blocks, overlap_expansion=not args.serial_expansion)
+                exchange = MulticastViewParallelExchange(num_blocks=args.exchange_blocks, overlap_expansion=args.overlap_expansion and not args.serial_expansion)
                 exchange.allocate(CONFIGS[args.workload]["num_points"], 1, device)  # the rendezvous is a collective: do it up front
                 exchange_kind = "multimem"
             except Exception as e:  # no multicast support (or no symmetric-memory backend) on this box
@@ -249,7 +252,7 @@ def run_b200(args):
                     print(f"[bench] multicast exchange unavailable ({type(e).__name__}: {e}); using the NCCL collectives", file=sys.stderr)
         if exchange is None:
             exchange = ViewParallelExchange(gather_group=dist.new_group() if args.exchange_streams == 2 else None,
-                                            overlap_expansion=not args.serial_expansion)
+                                            overlap_expansion=args.overlap_expansion_nccl and not args.serial_expansion)
             exchange_kind = "nccl"
 
     def barrier():
@@ -649,8 +652,9 @@ def run_b200(args):
 
     launches_per_step = profiling.KERNELS_PER_FORWARD(frame.layout.sort_passes) + profiling.KERNELS_PER_BACKWARD + \
         (0 if exchange is None else                       # + gsb200_expand_view_gradients (two launches when split around the
-         ((1 if args.serial_expansion or args.exchange_streams == 2 else 2) if exchange_kind != "multimem" else  # all-reduce)
-          (3 if args.serial_expansion else 4)))            # + the two launches of gsb200_exchange_multimem
+         ((2 if args.overlap_expansion_nccl and not args.serial_expansion and args.exchange_streams == 1 else 1)
+          if exchange_kind != "multimem" else              # all-reduce)
+          (4 if args.overlap_expansion and not args.serial_expansion else 3)))  # + the two launches of gsb200_exchange_multimem
     if world == 1:
         parallelism = "single GPU"
     elif exchange is not None:

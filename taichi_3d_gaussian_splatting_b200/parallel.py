@@ -77,11 +77,12 @@ class ViewParallelExchange:
     rank's ``[3N colour-argument gradients | 3 n_obj camera centres]`` in row ``rank`` and receives the other ranks' rows
     (in-place all-gather: the send buffer is the rank's slot of the receive buffer)."""
 
-    def __init__(self, group=None, gather_group=None, overlap_expansion: bool = True):
+    def __init__(self, group=None, gather_group=None, overlap_expansion: bool = False):
         """``gather_group``: optionally a SECOND process group over the same ranks (``dist.new_group()``): the all-gather
         then runs on its communicator concurrently with the all-reduce (two NCCL kernels in flight hide each other's
         latency) instead of behind it.  ``overlap_expansion``: gather first and expand the SH columns (they need only the
-        gathered blocks) on a second stream while the all-reduce of the summed columns is on the wire."""
+        gathered blocks) on a second stream while the all-reduce of the summed columns is on the wire -- measured SLOWER with
+        the NCCL collectives at 2 ranks (1.698 vs 1.676 ms per step, profiles/r02_call18_2gpu.log), hence off by default."""
         if not dist.is_available() or not dist.is_initialized():
             raise RuntimeError("ViewParallelExchange needs an initialised torch.distributed process group")
         self.group = group
@@ -156,9 +157,12 @@ class MulticastViewParallelExchange(ViewParallelExchange):
     kernel writes its compact rows straight into it.  ``run`` = cross-rank barrier (every rank's rows are written), the
     kernel, cross-rank barrier (every multicast store has landed).  Needs NVLS multicast support (one NVSwitch domain)."""
 
-    def __init__(self, group=None, barrier_timeout_ms: int = 20000, num_blocks: int = 0, overlap_expansion: bool = True):
+    def __init__(self, group=None, barrier_timeout_ms: int = 20000, num_blocks: int = 0, overlap_expansion: bool = False):
         """``num_blocks``: CTAs of the exchange kernel (0 = two per SM).  ``overlap_expansion``: expand the SH columns (they
-        need only the gathered blocks) on a second stream while the all-reduce of the summed columns is on the wire."""
+        need only the gathered blocks) on a second stream while the all-reduce of the summed columns is on the wire.  Measured
+        at 8 GPUs (profiles/r02_call19_8gpu.log): 1.809 ms per step against 1.797 ms with the one-pass expansion behind the
+        second barrier (1.804 with one exchange CTA per SM) -- the expansion's 128-register CTAs and its 290 MB of HBM traffic
+        slow the wire-bound kernel down by more than the 45 us they hide -- so it is off by default."""
         super().__init__(group, overlap_expansion=overlap_expansion)
         self._num_blocks = int(num_blocks)
         self._overlap = bool(overlap_expansion)
