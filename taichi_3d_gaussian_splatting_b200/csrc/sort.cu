@@ -394,7 +394,10 @@ static int sort_pairs_typed(const KeyT *keys_in, const int *vals_in, KeyT *keys_
                                             (int)smem));
         attr_set = true;
     }
-    int hist_blocks = blocks < 4 * num_sms() ? blocks : 4 * num_sms();
+#ifndef GSB_HIST_BLOCKS_PER_SM
+#define GSB_HIST_BLOCKS_PER_SM 4
+#endif
+    int hist_blocks = blocks < GSB_HIST_BLOCKS_PER_SM * num_sms() ? blocks : GSB_HIST_BLOCKS_PER_SM * num_sms();
     sort_histogram_kernel<KeyT><<<hist_blocks, SORT_BLOCK_THREADS, 0, stream>>>(keys_in, n_dev, capacity, depth_bits, end_bit,
                                                                                   max_depth_key, hist, tickets + 8);
     GSB_CUDA_CHECK(cudaGetLastError());
