@@ -209,7 +209,7 @@ ISSUE_PEAK = NUM_SMS * 4 * SM_CLOCK_HZ          # warp instructions / s (one per
 FP32_LANE_PEAK = NUM_SMS * 128 * SM_CLOCK_HZ    # FP32 lane operations / s (an FMA counts once)
 MUFU_LANE_PEAK = NUM_SMS * 16 * SM_CLOCK_HZ     # MUFU (ex2 / rcp) lane operations / s
 # SASS instructions per (warp, splat) visit of the inner loops (cuobjdump of this build)
-FWD_INSTR_PER_VISIT, BWD_INSTR_PER_VISIT = 32, 31 + 34
+FWD_INSTR_PER_VISIT, BWD_INSTR_PER_VISIT = 29, 30 + 34
 
 
 def run_b200(args):
@@ -618,11 +618,11 @@ def run_b200(args):
     compute["patch_shape_what_if"] = {
         "staged_patch_splat_pairs": {"8x4_one_pixel_per_thread": p84, "8x8_two_pixels_per_thread": p88, "16x4_two_pixels_per_thread": p164,
                                      "4x4_one_splat_per_half_warp": work["staged_patch_pairs_4x4"]},
-        "relative_inner_loop_instructions": {"8x4": 1.0, "8x8": round(p88 * (4 + 2 * 28) / max(p84 * 32, 1), 3),
-                                             "16x4": round(p164 * (4 + 2 * 28) / max(p84 * 32, 1), 3),
+        "relative_inner_loop_instructions": {"8x4": 1.0, "8x8": round(p88 * (4 + 2 * 25) / max(p84 * FWD_INSTR_PER_VISIT, 1), 3),
+                                             "16x4": round(p164 * (4 + 2 * 25) / max(p84 * FWD_INSTR_PER_VISIT, 1), 3),
                                              "4x4_two_splats_per_warp_iteration_lower_bound": round(work["staged_patch_pairs_4x4"] / 2 / max(p84, 1), 3)},
         "what": "counted on the device at staging time: a two-pixels-per-thread warp (8x8 or 16x4 patch) visits a splat if either of its "
-                "two 8x4 halves can be reached and then pays ~4 shared + 2 x 28 per-pixel instructions instead of 32 per 8x4 visit"}
+                "two 8x4 halves can be reached and then pays ~4 shared + 2 x 25 per-pixel instructions instead of 29 per 8x4 visit"}
     ncu = None
     npath = os.path.join(ROOT, "profiles", "r02_ncu_blend.json")
     if args.workload == "C3" and os.path.exists(npath):  # committed ncu --set full capture of both blend kernels (not live)
