@@ -624,7 +624,7 @@ def run_b200(args):
         "what": "counted on the device at staging time: a two-pixels-per-thread warp (8x8 or 16x4 patch) visits a splat if either of its "
                 "two 8x4 halves can be reached and then pays ~4 shared + 2 x 25 per-pixel instructions instead of 29 per 8x4 visit"}
     ncu = None
-    npath = os.path.join(ROOT, "profiles", "r02_ncu_blend.json")
+    npath = os.path.join(ROOT, "profiles", "r02_ncu_step_full.json")
     if args.workload == "C3" and os.path.exists(npath):  # committed ncu --set full capture of both blend kernels (not live)
         with open(npath) as f:
             ncu = json.load(f)

@@ -4,7 +4,8 @@ import csv, json, sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = rows[0]
 names = {"blend_forward_kernel": "blend_forward", "blend_backward_transposed_kernel": "blend_backward", "blend_backward_kernel": "blend_backward_butterfly",
-         "preprocess_kernel": "preprocess", "onesweep_pass_kernel": "sort_pass", "backward_points_kernel": "backward_points"}
+         "preprocess_kernel": "preprocess", "onesweep_pass_kernel": "sort_pass", "backward_points_kernel": "backward_points",
+         "sort_histogram_kernel": "sort_histogram", "tile_ranges_kernel": "tile_ranges"}
 get = lambda r, k: float(r[hdr.index(k)].replace(",", "")) if k in hdr and r[hdr.index(k)] not in ("", "n/a") else None  # noqa: E731
 out = {"source": sys.argv[3] if len(sys.argv) > 3 else sys.argv[1]}
 for r in rows[2:]:
