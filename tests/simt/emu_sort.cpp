@@ -93,6 +93,16 @@ extern "C" long long emu_sort_pairs_compacted(const void *keys_in, const int *va
                                           vals_out, n, depth_bits, end_bit, max_depth_key);
 }
 
+// the digit selector of one pass on its own (csrc/sort.cu make_digit_sel / digit_of / active_passes): digit `pass` of the
+// compacted key  tile << live | depth  cut out of the stored key  tile << depth_bits | depth; returns -1 for a pass beyond
+// the last active one
+extern "C" int emu_sort_digit(unsigned long long key, int key_bytes, int pass, int depth_bits, int end_bit, int live) {
+    using namespace gsb;
+    if (pass >= active_passes(end_bit, depth_bits, live)) return -1;
+    if (key_bytes == 4) return digit_of<unsigned int>((unsigned int)key, make_digit_sel<unsigned int>(pass, depth_bits, live));
+    return digit_of<unsigned long long>(key, make_digit_sel<unsigned long long>(pass, depth_bits, live));
+}
+
 // tile_start / tile_end must be zero-initialised (GPCR:954-957)
 extern "C" void emu_tile_ranges(const void *sorted_keys, long long n, int key_bytes, int depth_bits, int num_tiles,
                                 int *tile_start, int *tile_end) {

@@ -65,6 +65,32 @@ def test_emulated_radix_sort_compacts_the_dead_depth_bits(emu, dtype, depth_bits
         assert np.array_equal(ko, keys[order]) and np.array_equal(vo, vals[order])
 
 
+def test_digit_selector_of_the_compacted_key_for_every_layout(emu):
+    """csrc/sort.cu make_digit_sel: for EVERY (depth_bits, tile_bits, live depth bits, pass) the two shift-and-mask pairs cut
+    exactly byte `pass` of the compacted key  tile << live | depth  out of the stored key  tile << depth_bits | depth, the
+    number of active passes is ceil((tile_bits + live) / 8), and a pass beyond it is reported as inactive."""
+    rng = np.random.default_rng(5)
+    emu.emu_sort_digit.restype = ctypes.c_int
+    checked = 0
+    for key_bytes, layouts in ((4, [(d, t) for d in range(1, 25) for t in (1, 5, 8, 12, 13) if d + t <= 32]),
+                               (8, [(32, t) for t in (1, 7, 13, 20, 32)] + [(20, 20), (31, 33)])):
+        for depth_bits, tile_bits in layouts:
+            for live in range(0, min(depth_bits, 31) + 1):
+                end_bit = depth_bits + tile_bits
+                passes = max((tile_bits + live + 7) // 8, 1)
+                for _ in range(3):
+                    depth = int(rng.integers(0, 1 << live)) if live else 0
+                    tile = int(rng.integers(0, 1 << min(tile_bits, 62)))
+                    stored = (tile << depth_bits) | depth
+                    compact = (tile << live) | depth
+                    for p in range(9):
+                        got = emu.emu_sort_digit(ctypes.c_ulonglong(stored), key_bytes, p, depth_bits, end_bit, live)
+                        want = (compact >> (8 * p)) & 255 if p < passes else -1
+                        assert got == want, (key_bytes, depth_bits, tile_bits, live, p, hex(stored), got, want)
+                        checked += 1
+    assert checked > 20000
+
+
 def test_emulated_tile_ranges_known_answer(emu):
     """The reference's own known answer (tests/GaussianPointCloudRasterisation_test.py:18-51 shape): keys tile << 32 | depth."""
     tiles = np.array([0, 0, 0, 2, 2, 5, 5, 5, 5, 7], np.uint64)
