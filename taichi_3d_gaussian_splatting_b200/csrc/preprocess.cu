@@ -150,9 +150,6 @@ __device__ __forceinline__ void bounding_box(float u, float v, float radii, int 
 #ifndef GSB_PRE_MIN_BLOCKS
 #define GSB_PRE_MIN_BLOCKS 8
 #endif
-#ifndef GSB_PRE_HOIST_LOADS
-#define GSB_PRE_HOIST_LOADS 1  // the index-only loads of a point issued up front (see the kernel): 136 vs 140 us at C3 (profiles/r02_call23.log); 0 = round-1 order
-#endif
 // Per-warp staging area of the cooperative reach filter / key emission (32 splats of the warp).
 struct WarpStage {
     float u[32], v[32], a[32], b2[32], c[32], nb_ic[32], nb_ia[32], t2[32];
@@ -208,12 +205,12 @@ preprocess_kernel(const PreParams p) {
     float pc[3] = {0, 0, 0};
     float dir0 = 0.0f, dir1 = 0.0f, dir2 = 0.0f;  // unit view direction (GPCR:302), consumed by the SH stage
 
-#if GSB_PRE_HOIST_LOADS
     // Every global load of a point that depends on nothing but its index is issued HERE, in one go: the invalid mask, the
     // object id, the position and the first 32 bytes of the feature row (q | s, logit).  The kernel is bound by the latency
     // of a CTA's dependency chain: mask -> object id -> pose -> position -> frustum test -> feature row
-    // were four dependent round trips, now they are one plus the (L1-resident) pose.  Rows outside the frustum or unused
-    // fetch 32 bytes they do not need (they are allocated: (N,56)); the arithmetic is untouched.
+    // were four dependent round trips, now they are one plus the (L1-resident) pose: 140.4 -> 136.2 us at C3
+    // (profiles/r02_call23.log).  Rows outside the frustum or unused fetch 32 bytes they do not need (they are allocated:
+    // (N,56)); the arithmetic is untouched.
     signed char h_inv = 1;
     int h_ob = 0;
     float h_x = 0.0f, h_y = 0.0f, h_z = 0.0f;
@@ -230,21 +227,13 @@ preprocess_kernel(const PreParams p) {
     }
     if (i < p.N && h_inv != 1) {
         const PoseBlock *pb = p.poses + h_ob;
-#else
-    if (i < p.N && p.invalid[i] != 1) {
-        const PoseBlock *pb = p.poses + p.obj_id[i];
-#endif
         float T[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) T[k] = __ldg(&pb->T[k]);
         float Kc[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) Kc[k] = __ldg(&p.K[k]);
-#if GSB_PRE_HOIST_LOADS
         const float x = h_x, y = h_y, z = h_z;
-#else
-        const float x = __ldg(&p.xyz[3 * i]), y = __ldg(&p.xyz[3 * i + 1]), z = __ldg(&p.xyz[3 * i + 2]);
-#endif
         // GP3D:14-27: T @ (x,y,z,1), then uv = (K @ pc) / pc.z
         pc[0] = ((T[0] * x + T[1] * y) + T[2] * z) + T[3] * 1.0f;
         pc[1] = ((T[4] * x + T[5] * y) + T[6] * z) + T[7] * 1.0f;
@@ -259,13 +248,8 @@ preprocess_kernel(const PreParams p) {
              v < (float)(p.H + GSB_TILE_HEIGHT * GSB_BOUNDARY_TILES);
         if (in) {
             float4 *frow = reinterpret_cast<float4 *>(p.features + (size_t)GSB_FEATURE_DIM * i);
-#if GSB_PRE_HOIST_LOADS
             float4 qv = h_q;
             const float4 sl = h_sl;
-#else
-            float4 qv = frow[0];  // plain load: this row's q is rewritten below
-            const float4 sl = __ldg(reinterpret_cast<const float4 *>(frow) + 1);  // s0 s1 s2 logit
-#endif
             const float f[4] = {sl.x, sl.y, sl.z, sl.w};
             // GPCR:196-205: q <- q / |q| (invlen * q), written back in place
             if (!p.skip_q_normalise) {

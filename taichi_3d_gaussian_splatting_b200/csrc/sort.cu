@@ -20,9 +20,6 @@ constexpr unsigned int SS_VALUE_MASK = (1u << 30) - 1;
 #ifndef GSB_SORT_LOOKBACK
 #define GSB_SORT_LOOKBACK 4
 #endif
-#ifndef GSB_SORT_MATCH_FIRST
-#define GSB_SORT_MATCH_FIRST 0  // ranking: 1 = the MATCH.ANY of a thread in a loop of their own, then the counter chain
-#endif
 constexpr int LOOKBACK = GSB_SORT_LOOKBACK;  // predecessors whose state is fetched per look-back round
 constexpr int RBITS = 8;                     // digit width
 constexpr int RADIX = 1 << RBITS;            // = SORT_BLOCK_THREADS: thread t owns digit t
@@ -284,36 +281,9 @@ onesweep_pass_kernel(const PassParams<KeyT> P) {
     unsigned short ranks[SORT_ITEMS_PER_THREAD];
     const unsigned int lt_mask = (1u << lane) - 1u;
     unsigned short *const my_cnt = s.warp_cnt[warp];
-#if GSB_SORT_MATCH_FIRST
-    // The twelve MATCH.ANY of a thread are independent of the counters, so they are written as a loop of their own (ncu of
-    // the one-loop form: ~30 % of the pass's stall samples sit on the instruction behind each MATCH, profiles/
-    // r02_ncu_step_full_summary.txt); what the counter chain needs of each -- the number of peers below this lane, the group
-    // size and whether this lane leads its group -- is kept in one 16-bit word that is then replaced by the rank.  ptxas
-    // re-interleaves the two loops with the MATCH of key j+1 ahead of the counter update of key j (its consumer ~13
-    // instructions behind it instead of 3); neither an empty-asm fence nor a __syncwarp keeps the twelve MATCH together.
-#pragma unroll
-    for (int j = 0; j < SORT_ITEMS_PER_THREAD; ++j) {
-        const int idx = wbase + j * 32 + lane;
-        keys[j] = s.keys[idx];
-        const int d = idx < count ? digit_of(keys[j], sel) : RADIX;
-        const unsigned int peers = __match_any_sync(0xffffffffu, d);
-        const unsigned int below = __popc(peers & lt_mask);
-        ranks[j] = (unsigned short)(below | ((unsigned int)__popc(peers) << 6) | (below == 0 ? 0x8000u : 0u));  // 5 + 6 + 1 bits
-    }
-#pragma unroll
-    for (int j = 0; j < SORT_ITEMS_PER_THREAD; ++j) {
-        const int idx = wbase + j * 32 + lane;
-        const bool valid = idx < count;
-        const int d = valid ? digit_of(keys[j], sel) : 0;
-        const unsigned int info = ranks[j];
-        unsigned int prev = 0;
-        if (valid) prev = my_cnt[d];
-        ranks[j] = (unsigned short)(prev + (info & 31u));
-        __syncwarp();
-        if (valid && (info & 0x8000u)) my_cnt[d] = (unsigned short)(prev + ((info >> 6) & 63u));
-        __syncwarp();
-    }
-#else
+    // (Measured without effect, profiles/r02_call22.log: the twelve MATCH.ANY of a thread written as a loop of their own in
+    //  front of the counter chain -- 40 % of a pass's stall samples sit on the instruction behind each MATCH, but ptxas
+    //  re-interleaves the two loops with one MATCH ahead whatever fence is put between them: 128.3 vs 128.3 us.)
 #pragma unroll
     for (int j = 0; j < SORT_ITEMS_PER_THREAD; ++j) {
         const int idx = wbase + j * 32 + lane;
@@ -328,7 +298,6 @@ onesweep_pass_kernel(const PassParams<KeyT> P) {
         if (valid && (peers & lt_mask) == 0) my_cnt[d] = (unsigned short)(prev + __popc(peers));
         __syncwarp();
     }
-#endif
     __syncthreads();
 
     // per-digit totals (thread t owns digit t), warp-exclusive bases; publish the aggregate at once
