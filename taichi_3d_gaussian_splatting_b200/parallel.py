@@ -130,9 +130,10 @@ class ViewParallelExchange:
         """The collectives followed by the expansion to dense gradients.  ``expand(part)`` enqueues
         ``gsb200_expand_view_gradients`` on the current stream (0 = everything, 1 = SH columns, 2 = summed columns).
 
-        On CUDA tensors the 48 SH columns -- 4/5 of the expansion's traffic, HBM-bound -- are expanded on a second stream as soon
-        as the blocks are gathered, while the all-reduce of the summed columns is bound by the NVLink wire; only the small
-        part 2 (xyz, q, s, logit) waits for the sums.  The two parts write disjoint pieces of the dense gradients."""
+        Default: the collectives, then one expansion pass.  With ``overlap_expansion=True`` (CUDA tensors, one communicator) the
+        blocks are gathered FIRST and the 48 SH columns -- 4/5 of the expansion's traffic, HBM-bound -- are expanded on a second
+        stream while the all-reduce of the summed columns is on the wire; only the small part 2 (xyz, q, s, logit) waits for the
+        sums.  The two parts write disjoint pieces of the dense gradients.  (Opt-in: measured slower at 2 ranks.)"""
         if not (self._overlap and grad_sum.is_cuda) or self.gather_group is not None:
             self.run(grad_sum, blocks)
             return expand(0)
@@ -233,9 +234,11 @@ class MulticastViewParallelExchange(ViewParallelExchange):
 
 
     def run_and_expand(self, grad_sum: torch.Tensor, blocks: torch.Tensor, expand) -> None:
-        """Every rank's block is in place after the FIRST barrier (the pushes were launched before it), so the 48 SH columns
+        """Default: ``run`` (barrier, all-reduce kernel, barrier), then one expansion pass.  With ``overlap_expansion=True``:
+        every rank's block is in place after the FIRST barrier (the pushes were launched before it), so the 48 SH columns
         -- 4/5 of the expansion's traffic, HBM-bound -- are expanded on a second stream while the all-reduce of the summed
-        columns is still bound by the NVLink wire; only the small part 2 (xyz, q, s, logit) follows the second barrier."""
+        columns is still bound by the NVLink wire; only the small part 2 (xyz, q, s, logit) follows the second barrier.
+        (Opt-in: measured slower at 8 GPUs, see ``__init__``.)"""
         if not self._overlap:
             return super().run_and_expand(grad_sum, blocks, expand)
         e = self._check(grad_sum, blocks)
