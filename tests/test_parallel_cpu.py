@@ -54,6 +54,17 @@ def _worker(rank, world, port, out_dir):
     blocks2[rank] = torch.arange(3 * n + 8, dtype=torch.float32) + 1000.0 * rank
     ex2.run(gsum2, blocks2)
     assert torch.equal(gsum2, gsum) and torch.equal(blocks2, blocks)
+    # run_and_expand: what the operator's backward calls -- the collectives, then ONE expansion pass (part 0); on CPU tensors
+    # also when the split expansion is asked for (it needs CUDA streams)
+    for overlap in (False, True):
+        ex3 = ViewParallelExchange(overlap_expansion=overlap)
+        gsum3 = torch.full((n, 12), float(rank + 1))
+        blocks3 = torch.full((world, 3 * n + 8), -1.0)
+        blocks3[rank] = torch.arange(3 * n + 8, dtype=torch.float32) + 1000.0 * rank
+        parts = []
+        ex3.run_and_expand(gsum3, blocks3, lambda part: parts.append((part, gsum3.clone(), blocks3.clone())))
+        assert [p[0] for p in parts] == [0]                                   # one pass ...
+        assert torch.equal(parts[0][1], gsum) and torch.equal(parts[0][2], blocks)  # ... that sees the exchanged buffers
     torch.save({"xyz": g_xyz, "feat": g_feat, "avg": g_avg, "views": shard_views(8, rank, world), "flat": flat, "other": other,
                 "gsum": gsum, "blocks": blocks},
                os.path.join(out_dir, f"rank{rank}.pt"))
