@@ -65,6 +65,24 @@ def test_emulated_radix_sort_compacts_the_dead_depth_bits(emu, dtype, depth_bits
         assert np.array_equal(ko, keys[order]) and np.array_equal(vo, vals[order])
 
 
+def test_emulated_radix_sort_many_ctas_with_compaction(emu):
+    """40 000 keys = 14 CTAs per pass: the per-digit look-back walks several rounds of four predecessors, the last block of
+    the histogram kernel turns the counts of 14 blocks into prefixes, and the three-buffer rotation ends in the output after
+    the 3 active passes of a C3-like layout (13 tile bits, 17 depth bits of which 10 are live; 4 launches)."""
+    n = 40000
+    rng = np.random.default_rng(77)
+    depth = rng.integers(0, 1 << 10, n, dtype=np.uint64)
+    depth[123] = (1 << 10) - 1
+    tile = rng.integers(0, 8040, n, dtype=np.uint64)
+    keys = ((tile << np.uint64(17)) | depth).astype(np.uint32)
+    vals = np.arange(n, dtype=np.int32)
+    ko, vo = np.empty_like(keys), np.empty_like(vals)
+    mk = np.array([int(depth.max())], np.int32)
+    assert emu.emu_sort_pairs_compacted(c(keys), c(vals), c(ko), c(vo), ctypes.c_longlong(n), 4, 17, 30, c(mk)) > 0
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(ko, keys[order]) and np.array_equal(vo, vals[order])
+
+
 def test_digit_selector_of_the_compacted_key_for_every_layout(emu):
     """csrc/sort.cu make_digit_sel: for EVERY (depth_bits, tile_bits, live depth bits, pass) the two shift-and-mask pairs cut
     exactly byte `pass` of the compacted key  tile << live | depth  out of the stored key  tile << depth_bits | depth, the
